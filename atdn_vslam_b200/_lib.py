@@ -1,0 +1,101 @@
+"""ctypes binding of libatdn_b200.so (include/atdn_b200.h).  Fails loudly: a missing library, a
+missing symbol or a non-zero return code raises -- there is no PyTorch / CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libatdn_b200.so")
+
+MODE_ROWS, MODE_PATCH = 0, 1
+EPI_STORE16, EPI_STORE32, EPI_CORR, EPI_GRU_ZR, EPI_GRU_Q, EPI_PV = range(6)
+F_RELU, F_RESID, F_FLOWTAIL, F_TANH_LO, F_B_BATCHED = 1, 2, 4, 8, 16
+
+EXPORTS = (
+    "atdn_last_error", "atdn_version", "atdn_check_device", "atdn_tc_gemm", "atdn_corr_lookup",
+    "atdn_stem_im2col", "atdn_flow_im2col", "atdn_inorm_stats", "atdn_inorm_apply", "atdn_softmax_rows",
+    "atdn_flow_head_update", "atdn_convex_upsample", "atdn_coords_init", "atdn_conv32", "atdn_linear32",
+    "atdn_lstm_cell", "atdn_keyframe_search",
+)
+
+
+class TcDesc(C.Structure):
+    _fields_ = [
+        ("bn", C.c_int32), ("epi", C.c_int32), ("flags", C.c_int32), ("a_mode", C.c_int32), ("b_mode", C.c_int32),
+        ("n_valid", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
+        ("taps_h", C.c_int32), ("taps_w", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32), ("stride", C.c_int32),
+        ("a_split_chunk", C.c_int32),
+        ("a", C.c_void_p), ("a_dims", C.c_int64 * 4), ("a_strides", C.c_int64 * 3),
+        ("a2", C.c_void_p), ("a2_dims", C.c_int64 * 4), ("a2_strides", C.c_int64 * 3),
+        ("b", C.c_void_p), ("b_dims", C.c_int64 * 4), ("b_strides", C.c_int64 * 3),
+        ("alpha", C.c_float), ("bias", C.c_void_p), ("out", C.c_void_p), ("out_pitch", C.c_int64),
+        ("out_ch_off", C.c_int64), ("resid16", C.c_void_p), ("resid_pitch", C.c_int64), ("resid_ch_off", C.c_int64),
+        ("h32", C.c_void_p), ("z32", C.c_void_p), ("rh16", C.c_void_p), ("aux32", C.c_void_p), ("gamma", C.c_void_p),
+        ("lvl", C.c_void_p * 3), ("lvl_pitch", C.c_int32 * 4), ("corr_h", C.c_int32), ("corr_w", C.c_int32),
+    ]
+
+
+class Conv32Desc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("y", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("skip", C.c_void_p),
+        ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+        ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
+        ("k", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("mish", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m atdn_vslam_b200.build` "
+            "(atdn_vslam_b200 has no PyTorch/CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError(f"{LIB_PATH} does not export {name}")
+    lib.atdn_last_error.restype = C.c_char_p
+    for name in EXPORTS[1:]:
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        raise RuntimeError(f"{what} failed with code {code}: {load().atdn_last_error().decode(errors='replace')}")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t, offset_elems=0):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr() + offset_elems * t.element_size())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("atdn_vslam_b200 kernels need CUDA tensors on an sm_100 device (no CPU fallback)")
+
+
+def tc_gemm(desc: TcDesc):
+    check(load().atdn_tc_gemm(C.byref(desc), stream_ptr()), "atdn_tc_gemm")
+
+
+def _set(arr, values):
+    for i, v in enumerate(values):
+        arr[i] = int(v)

@@ -1,0 +1,270 @@
+// fp32 CUDA-core kernels for the small-channel networks: CLVO (ATDNVO) encoder + LSTM + heads, the
+// MappingVAE keyframe encoder, and the keyframe L2 search.  These layers have 2..128 channels on
+// small maps: memory/latency-bound, not tensor-core work.
+#include <math.h>
+
+#include "common.h"
+
+namespace atdn {
+
+__device__ __forceinline__ float mishf(float x) {
+  // x * tanh(softplus(x)); softplus with the same threshold (20) as torch
+  const float sp = x > 20.0f ? x : log1pf(expf(x));
+  return x * tanhf(sp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direct convolution, NCHW fp32.  CTA = 16x16 output pixels x 16 output channels; input channels are
+// streamed through shared memory 4 at a time together with their [ci][tap][co16] weight slab.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoT = 16, kCiT = 4, kTile = 16;
+
+struct Conv32Params {
+  const float *x, *w, *bias, *in_scale, *in_shift, *skip, *bn_scale, *bn_shift;
+  float* y;
+  int B, Cin, Cout, H, W, OH, OW, K, stride, pad, mish, tiles_x, in_tile;
+};
+
+__global__ void __launch_bounds__(256) conv32_kernel(Conv32Params p) {
+  extern __shared__ float sm[];
+  const int IT = p.in_tile;                       // (kTile-1)*stride + K
+  float* s_in = sm;                               // [kCiT][IT][IT]
+  float* s_w = sm + kCiT * IT * IT;               // [kCiT][K*K][kCoT]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int tile_x = blockIdx.x % p.tiles_x, tile_y = blockIdx.x / p.tiles_x;
+  const int co0 = blockIdx.y * kCoT, b = blockIdx.z;
+  const int ox = tile_x * kTile + tx, oy = tile_y * kTile + ty;
+  const int ix0 = tile_x * kTile * p.stride - p.pad, iy0 = tile_y * kTile * p.stride - p.pad;
+  const int KK = p.K * p.K;
+  float acc[kCoT];
+#pragma unroll
+  for (int i = 0; i < kCoT; ++i) acc[i] = 0.0f;
+
+  for (int ci0 = 0; ci0 < p.Cin; ci0 += kCiT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCiT * IT * IT; i += 256) {
+      const int c = i / (IT * IT), r = i - c * IT * IT;
+      const int yy = iy0 + r / IT, xx = ix0 + r % IT;
+      float v = 0.0f;
+      const int ci = ci0 + c;
+      if (ci < p.Cin && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+        v = __ldg(p.x + ((static_cast<long long>(b) * p.Cin + ci) * p.H + yy) * p.W + xx);
+        if (p.in_scale) v = v * __ldg(p.in_scale + ci) + __ldg(p.in_shift + ci);
+      }
+      s_in[i] = v;
+    }
+    for (int i = threadIdx.x; i < kCiT * KK * kCoT; i += 256) {
+      const int co = i % kCoT, t = (i / kCoT) % KK, c = i / (kCoT * KK);
+      const int ci = ci0 + c;
+      float v = 0.0f;
+      if (ci < p.Cin && co0 + co < p.Cout) v = __ldg(p.w + (static_cast<long long>(co0 + co) * p.Cin + ci) * KK + t);
+      s_w[i] = v;
+    }
+    __syncthreads();
+    for (int c = 0; c < kCiT; ++c) {
+      const float* in_c = s_in + c * IT * IT + (ty * p.stride) * IT + tx * p.stride;
+      const float* w_c = s_w + c * KK * kCoT;
+      for (int ky = 0; ky < p.K; ++ky) {
+        for (int kx = 0; kx < p.K; ++kx) {
+          const float v = in_c[ky * IT + kx];
+          const float4* w4 = reinterpret_cast<const float4*>(w_c + (ky * p.K + kx) * kCoT);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 ww = w4[q];
+            acc[4 * q] += v * ww.x;
+            acc[4 * q + 1] += v * ww.y;
+            acc[4 * q + 2] += v * ww.z;
+            acc[4 * q + 3] += v * ww.w;
+          }
+        }
+      }
+    }
+  }
+  if (ox >= p.OW || oy >= p.OH) return;
+#pragma unroll
+  for (int i = 0; i < kCoT; ++i) {
+    const int co = co0 + i;
+    if (co >= p.Cout) break;
+    const long long o = ((static_cast<long long>(b) * p.Cout + co) * p.OH + oy) * p.OW + ox;
+    float v = acc[i] + (p.bias ? __ldg(p.bias + co) : 0.0f);
+    if (p.skip) v += p.skip[o];
+    if (p.mish) v = mishf(v);
+    if (p.bn_scale) v = v * __ldg(p.bn_scale + co) + __ldg(p.bn_shift + co);
+    p.y[o] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Linear (+Mish) and LSTM cell: one warp per output row, looping over the batch
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ y, int B,
+                                                       int IN, int OUT, int act) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= OUT) return;
+  const float* wr = w + static_cast<long long>(row) * IN;
+  for (int b = 0; b < B; ++b) {
+    const float* xb = x + static_cast<long long>(b) * IN;
+    float acc = 0.0f;
+    for (int i = lane; i < IN; i += 32) acc += __ldg(wr + i) * xb[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float v = acc + (bias ? bias[row] : 0.0f);
+      if (act == 1) v = mishf(v);
+      y[static_cast<long long>(b) * OUT + row] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) lstm_gates_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                         const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                                         const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                                         float* __restrict__ gates, int B, int IN, int HID) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= 4 * HID) return;
+  const float* wi = w_ih + static_cast<long long>(row) * IN;
+  const float* wh = w_hh + static_cast<long long>(row) * HID;
+  for (int b = 0; b < B; ++b) {
+    float a1 = 0.0f, a2 = 0.0f;
+    for (int i = lane; i < IN; i += 32) a1 += __ldg(wi + i) * x[static_cast<long long>(b) * IN + i];
+    for (int i = lane; i < HID; i += 32) a2 += __ldg(wh + i) * h[static_cast<long long>(b) * HID + i];
+    for (int o = 16; o > 0; o >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    // torch: (x W_ih^T + b_ih) + (h W_hh^T + b_hh)
+    if (lane == 0) gates[static_cast<long long>(b) * 4 * HID + row] = (a1 + b_ih[row]) + (a2 + b_hh[row]);
+  }
+}
+
+__global__ void lstm_pointwise_kernel(const float* __restrict__ gates, float* __restrict__ h, float* __restrict__ c,
+                                      int B, int HID) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * HID) return;
+  const int b = idx / HID, j = idx - b * HID;
+  const float* g = gates + static_cast<long long>(b) * 4 * HID;
+  const float ig = 1.0f / (1.0f + expf(-g[j]));
+  const float fg = 1.0f / (1.0f + expf(-g[HID + j]));
+  const float gg = tanhf(g[2 * HID + j]);
+  const float og = 1.0f / (1.0f + expf(-g[3 * HID + j]));
+  const float cn = fg * c[idx] + ig * gg;
+  c[idx] = cn;
+  h[idx] = og * tanhf(cn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Keyframe search: streaming squared-L2 per row (one CTA per keyframe), then first arg-min
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kf_dist_kernel(const float* __restrict__ emb, const float* __restrict__ code,
+                                                      float* __restrict__ dist, int dim) {
+  __shared__ float red[8];
+  const float4* e = reinterpret_cast<const float4*>(emb + static_cast<long long>(blockIdx.x) * dim);
+  const float4* q = reinterpret_cast<const float4*>(code);
+  float acc = 0.0f;
+  for (int i = threadIdx.x; i < dim / 4; i += 256) {
+    const float4 a = __ldg(e + i), b = __ldg(q + i);
+    const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+    acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    dist[blockIdx.x] = sqrtf(t);
+  }
+}
+
+__global__ void __launch_bounds__(1024) kf_argmin_kernel(const float* __restrict__ dist, long long n,
+                                                         int* __restrict__ index) {
+  __shared__ float sv[1024];
+  __shared__ long long si[1024];
+  float best = INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const float v = dist[i];
+    if (v < best) { best = v; bi = i; }   // strict <: keeps the lowest index of equal values
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const float v = sv[threadIdx.x + s];
+      const long long j = si[threadIdx.x + s];
+      if (v < sv[threadIdx.x] || (v == sv[threadIdx.x] && j < si[threadIdx.x])) {
+        sv[threadIdx.x] = v;
+        si[threadIdx.x] = j;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *index = static_cast<int>(si[0]);
+}
+
+}  // namespace atdn
+
+using namespace atdn;
+
+extern "C" int atdn_conv32(const atdn_conv32_desc* d, void* stream) {
+  if (int e = require_sm100()) return e;
+  ATDN_REQUIRE(d && d->x && d->y && d->w, ATDN_ERR_ARG, "atdn_conv32: null argument");
+  ATDN_REQUIRE(d->k >= 1 && d->k <= 7 && d->stride >= 1 && d->stride <= 3, ATDN_ERR_UNSUP, "atdn_conv32: k=%d stride=%d", d->k, d->stride);
+  ATDN_REQUIRE((d->in_scale == nullptr) == (d->in_shift == nullptr) && (d->bn_scale == nullptr) == (d->bn_shift == nullptr), ATDN_ERR_ARG,
+               "atdn_conv32: scale/shift must come in pairs");
+  Conv32Params p;
+  p.x = d->x; p.w = d->w; p.bias = d->bias; p.in_scale = d->in_scale; p.in_shift = d->in_shift; p.skip = d->skip;
+  p.bn_scale = d->bn_scale; p.bn_shift = d->bn_shift; p.y = d->y;
+  p.B = d->batch; p.Cin = d->cin; p.Cout = d->cout; p.H = d->in_h; p.W = d->in_w; p.K = d->k; p.stride = d->stride;
+  p.pad = d->pad; p.mish = d->mish;
+  p.OH = (d->in_h + 2 * d->pad - d->k) / d->stride + 1;
+  p.OW = (d->in_w + 2 * d->pad - d->k) / d->stride + 1;
+  ATDN_REQUIRE(p.OH >= 1 && p.OW >= 1, ATDN_ERR_ARG, "atdn_conv32: empty output");
+  p.tiles_x = ceil_div(p.OW, kTile);
+  p.in_tile = (kTile - 1) * d->stride + d->k;
+  const int smem = (kCiT * p.in_tile * p.in_tile + kCiT * d->k * d->k * kCoT) * (int)sizeof(float);
+  static int max_smem = 48 * 1024;
+  if (smem > max_smem) {
+    ATDN_CUDA(cudaFuncSetAttribute(conv32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    max_smem = smem;
+  }
+  dim3 grid(p.tiles_x * ceil_div(p.OH, kTile), ceil_div(p.Cout, kCoT), p.B);
+  conv32_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int atdn_linear32(const float* x, const float* w, const float* bias, float* y, int32_t batch, int32_t in_f,
+                             int32_t out_f, int32_t act, void* stream) {
+  if (int e = require_sm100()) return e;
+  ATDN_REQUIRE(x && w && y && batch >= 1 && in_f >= 1 && out_f >= 1, ATDN_ERR_ARG, "atdn_linear32: bad arguments");
+  linear32_kernel<<<ceil_div(out_f, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, batch, in_f, out_f, act);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int atdn_lstm_cell(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                              float* h, float* c, float* gates, int32_t batch, int32_t in_f, int32_t hidden, void* stream) {
+  if (int e = require_sm100()) return e;
+  ATDN_REQUIRE(x && w_ih && w_hh && b_ih && b_hh && h && c && gates, ATDN_ERR_ARG, "atdn_lstm_cell: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  lstm_gates_kernel<<<ceil_div(4 * hidden, 8), 256, 0, s>>>(x, h, w_ih, w_hh, b_ih, b_hh, gates, batch, in_f, hidden);
+  ATDN_CUDA(cudaGetLastError());
+  lstm_pointwise_kernel<<<ceil_div(batch * hidden, 256), 256, 0, s>>>(gates, h, c, batch, hidden);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int atdn_keyframe_search(const float* emb, const float* code, float* dist, int32_t* index, int64_t num, int32_t dim,
+                                    void* stream) {
+  if (int e = require_sm100()) return e;
+  ATDN_REQUIRE(emb && code && dist && index && num >= 1, ATDN_ERR_ARG, "atdn_keyframe_search: bad arguments");
+  ATDN_REQUIRE(dim % 4 == 0 && aligned16(emb) && aligned16(code), ATDN_ERR_ALIGN, "atdn_keyframe_search: dim %% 4 and 16-byte alignment required");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  kf_dist_kernel<<<static_cast<unsigned>(num), 256, 0, s>>>(emb, code, dist, dim);
+  ATDN_CUDA(cudaGetLastError());
+  kf_argmin_kernel<<<1, 1024, 0, s>>>(dist, num, index);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}

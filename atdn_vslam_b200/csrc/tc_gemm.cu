@@ -1,0 +1,577 @@
+// Tensor-core implicit GEMM for sm_100a: TMA-staged fp16 operands (128B swizzle), tcgen05.mma with the
+// fp32 accumulator in TMEM, warp-specialised roles, fused epilogues.  See include/atdn_b200.h.
+//
+// CTA = 192 threads: warps 0-3 epilogue (warp w owns TMEM lanes 32w..32w+31 = tile rows), warp 4 = TMA
+// producer (one lane), warp 5 = TMEM allocator + MMA issuer (one lane).  One output tile of
+// 128 x BN per CTA; the K loop runs over (filter tap, 64-channel chunk) pairs through a STAGES-deep
+// mbarrier ring.  Two CTAs per SM are resident for BN <= 128, so one tile's epilogue overlaps the
+// other's MMA phase.
+#include <math.h>
+#include <stdio.h>
+
+#include "common.h"
+#include "tc_ptx.cuh"
+
+namespace atdn {
+
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;                  // fp16 elements per 128-byte swizzled row
+constexpr int kABytes = kTileM * kChunkK * 2;  // 16 KiB
+constexpr int kThreads = 192;
+
+struct alignas(64) TcParams {
+  CUtensorMap tmA, tmA2, tmB;
+  int a_mode, tiles_w, out_h, out_w, m_rows, n_valid;
+  int taps_w, pad_h, pad_w, stride;
+  int chunks_a, chunks_a2, c_a, c_a2, num_k_iters;
+  int b_batched, flags;
+  int corr_h, corr_w, corr_tiles_w;
+  int lvl_pitch[4];
+  float* lvl[3];
+  float alpha;
+  const float* bias;
+  void* out;
+  long long out_pitch, out_ch_off;
+  const __half* resid;
+  long long resid_pitch, resid_ch_off;
+  float* h32;
+  float* z32;
+  __half* rh16;
+  const float* aux32;
+  const float* gamma;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void store8_f16(__half* dst, const float (&y)[8]) {
+  __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+  __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+__device__ __forceinline__ void load8_f16(const __half* src, float (&y)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(src);
+  float2 a = __half22float2(*reinterpret_cast<__half2*>(&u.x));
+  float2 b = __half22float2(*reinterpret_cast<__half2*>(&u.y));
+  float2 c = __half22float2(*reinterpret_cast<__half2*>(&u.z));
+  float2 d = __half22float2(*reinterpret_cast<__half2*>(&u.w));
+  y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y; y[4] = c.x; y[5] = c.y; y[6] = d.x; y[7] = d.y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogues operating on one 32-column chunk of one accumulator row (this thread's pixel / row).
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, bool valid, long long pix, int ncol0,
+                                               const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = ncol0 + g * 8;
+    if (n >= p.n_valid) break;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float b = p.bias ? __ldg(p.bias + n + j) : 0.0f;   // bias arrays are padded to a multiple of 64
+      y[j] = p.alpha * (__uint_as_float(v[g * 8 + j]) + b);
+    }
+    if (!valid) continue;
+    if constexpr (EPI == ATDN_EPI_STORE16) {
+      if (p.flags & ATDN_F_TANH_LO) {
+        if (n < 128) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = tanhf(y[j]);
+          float4* h = reinterpret_cast<float4*>(p.h32 + pix * 128 + n);
+          h[0] = make_float4(y[0], y[1], y[2], y[3]);
+          h[1] = make_float4(y[4], y[5], y[6], y[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.0f);
+        }
+      } else if (p.flags & ATDN_F_RELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.0f);
+      }
+      if (p.flags & ATDN_F_FLOWTAIL) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n + j >= p.n_valid - 2 && n + j < p.n_valid) y[j] = p.aux32[pix * 2 + (n + j - (p.n_valid - 2))];
+      }
+      if (p.flags & ATDN_F_RESID) {
+        float r[8];
+        load8_f16(p.resid + pix * p.resid_pitch + p.resid_ch_off + n, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaxf(r[j] + y[j], 0.0f);
+      }
+      __half* dst = reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n;
+      if (n + 8 <= p.n_valid) {
+        store8_f16(dst, y);
+      } else {
+        for (int j = 0; j < 8 && n + j < p.n_valid; ++j) dst[j] = __float2half_rn(y[j]);
+      }
+    } else if constexpr (EPI == ATDN_EPI_STORE32) {
+      float* dst = reinterpret_cast<float*>(p.out) + pix * p.out_pitch + p.out_ch_off + n;
+      if (n + 8 <= p.n_valid) {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(y[0], y[1], y[2], y[3]);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(y[4], y[5], y[6], y[7]);
+      } else {
+        for (int j = 0; j < 8 && n + j < p.n_valid; ++j) dst[j] = y[j];
+      }
+    } else if constexpr (EPI == ATDN_EPI_GRU_ZR) {
+      if (n < 128) {
+        float4* z = reinterpret_cast<float4*>(p.z32 + pix * 128 + n);
+        z[0] = make_float4(sigmoidf_(y[0]), sigmoidf_(y[1]), sigmoidf_(y[2]), sigmoidf_(y[3]));
+        z[1] = make_float4(sigmoidf_(y[4]), sigmoidf_(y[5]), sigmoidf_(y[6]), sigmoidf_(y[7]));
+      } else {
+        const float4* h = reinterpret_cast<const float4*>(p.h32 + pix * 128 + (n - 128));
+        float4 h0 = h[0], h1 = h[1];
+        float r[8] = {sigmoidf_(y[0]) * h0.x, sigmoidf_(y[1]) * h0.y, sigmoidf_(y[2]) * h0.z, sigmoidf_(y[3]) * h0.w,
+                      sigmoidf_(y[4]) * h1.x, sigmoidf_(y[5]) * h1.y, sigmoidf_(y[6]) * h1.z, sigmoidf_(y[7]) * h1.w};
+        store8_f16(p.rh16 + pix * 128 + (n - 128), r);
+      }
+    } else if constexpr (EPI == ATDN_EPI_GRU_Q) {
+      float4* h = reinterpret_cast<float4*>(p.h32 + pix * 128 + n);
+      const float4* z = reinterpret_cast<const float4*>(p.z32 + pix * 128 + n);
+      float4 h0 = h[0], h1 = h[1], z0 = z[0], z1 = z[1];
+      float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+      float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (1.0f - zv[j]) * hv[j] + zv[j] * tanhf(y[j]);
+      h[0] = make_float4(y[0], y[1], y[2], y[3]);
+      h[1] = make_float4(y[4], y[5], y[6], y[7]);
+      store8_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y);
+    } else if constexpr (EPI == ATDN_EPI_PV) {
+      const float scale = p.aux32[pix] * __ldg(p.gamma);
+      float r[8];
+      load8_f16(p.resid + pix * p.resid_pitch + p.resid_ch_off + n, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = r[j] + scale * y[j];
+      store8_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y);
+    }
+  }
+}
+
+// Corr-volume epilogue: this thread owns query row `pix` of a tile of 8 x 32 target pixels whose 256
+// accumulator columns are ordered (h_local, w_local).  Level 0 is stored as is; levels 1..3 are the
+// hierarchical 2x2 means of corr.py:28-30 (floor semantics: only complete 2x2 blocks exist).
+__device__ __forceinline__ void epilogue_corr(const TcParams& p, bool valid, long long pix, int bh0, int bw0,
+                                              uint32_t tmem_row_base) {
+  const int H0 = p.corr_h, W0 = p.corr_w;
+  const int H1 = H0 / 2, W1 = W0 / 2, H2 = H1 / 2, W2 = W1 / 2, H3 = H2 / 2, W3 = W2 / 2;
+  float hs1[16];   // horizontal pair sums of the previous (even) level-0 row
+  float hs2[8];    // horizontal pair sums of the previous (even) level-1 row
+  float hs3[4];    // horizontal pair sums of the previous (even) level-2 row
+#pragma unroll
+  for (int hl = 0; hl < 8; ++hl) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_row_base + hl * 32, v);
+    tmem_ld_wait();
+    float c[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) c[j] = p.alpha * __uint_as_float(v[j]);
+    const int h = bh0 + hl;
+    if (valid && h < H0) {
+      float* dst = reinterpret_cast<float*>(p.out) + (pix * H0 + h) * (long long)p.lvl_pitch[0] + bw0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        if (bw0 + j < p.lvl_pitch[0]) *reinterpret_cast<float4*>(dst + j) = make_float4(c[j], c[j + 1], c[j + 2], c[j + 3]);
+    }
+    if ((hl & 1) == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) hs1[j] = c[2 * j] + c[2 * j + 1];
+    } else {
+      float l1[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) l1[j] = (hs1[j] + (c[2 * j] + c[2 * j + 1])) * 0.25f;
+      const int r1 = h >> 1, c1 = bw0 >> 1;
+      if (valid && r1 < H1) {
+        float* dst = p.lvl[0] + (pix * H1 + r1) * (long long)p.lvl_pitch[1] + c1;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          if (c1 + j < p.lvl_pitch[1]) *reinterpret_cast<float4*>(dst + j) = make_float4(l1[j], l1[j + 1], l1[j + 2], l1[j + 3]);
+      }
+      if ((hl & 3) == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hs2[j] = l1[2 * j] + l1[2 * j + 1];
+      } else {
+        float l2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) l2[j] = (hs2[j] + (l1[2 * j] + l1[2 * j + 1])) * 0.25f;
+        const int r2 = h >> 2, c2 = bw0 >> 2;
+        if (valid && r2 < H2) {
+          float* dst = p.lvl[1] + (pix * H2 + r2) * (long long)p.lvl_pitch[2] + c2;
+#pragma unroll
+          for (int j = 0; j < 8; j += 4)
+            if (c2 + j < p.lvl_pitch[2]) *reinterpret_cast<float4*>(dst + j) = make_float4(l2[j], l2[j + 1], l2[j + 2], l2[j + 3]);
+        }
+        if (hl == 3) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hs3[j] = l2[2 * j] + l2[2 * j + 1];
+        } else {
+          const int r3 = h >> 3, c3 = bw0 >> 3;
+          if (valid && r3 < H3 && c3 < p.lvl_pitch[3]) {
+            float* dst = p.lvl[2] + (pix * H3 + r3) * (long long)p.lvl_pitch[3] + c3;
+            *reinterpret_cast<float4*>(dst) =
+                make_float4((hs3[0] + (l2[0] + l2[1])) * 0.25f, (hs3[1] + (l2[2] + l2[3])) * 0.25f,
+                            (hs3[2] + (l2[4] + l2[5])) * 0.25f, (hs3[3] + (l2[6] + l2[7])) * 0.25f);
+          }
+        }
+      }
+    }
+  }
+  (void)W1; (void)W2; (void)W3;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant__ TcParams p) {
+  constexpr int kBBytes = BN * kChunkK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t kIdesc = make_idesc_f16(kTileM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int batch = blockIdx.z;
+
+  // tile coordinates
+  int m0 = 0, h0 = 0, w0 = 0;
+  if (p.a_mode == ATDN_MODE_PATCH) {
+    h0 = (blockIdx.x / p.tiles_w) * 8;
+    w0 = (blockIdx.x % p.tiles_w) * 16;
+  } else {
+    m0 = blockIdx.x * kTileM;
+  }
+  const int n0 = blockIdx.y * BN;
+  int bh0 = 0, bw0 = 0;
+  if constexpr (EPI == ATDN_EPI_CORR) {
+    bh0 = (blockIdx.y / p.corr_tiles_w) * 8;
+    bw0 = (blockIdx.y % p.corr_tiles_w) * 32;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    if (p.chunks_a2 > 0) tma_prefetch_desc(&p.tmA2);
+  }
+  if (warp == 5) tmem_alloc(&tmem_base_smem, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int chunks = p.chunks_a + p.chunks_a2;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+        uint8_t* sA = smem + stage * kStageBytes;
+        uint8_t* sB = sA + kABytes;
+        if (p.a_mode == ATDN_MODE_PATCH) {
+          const int tap = it / chunks, chunk = it - tap * chunks;
+          const int dy = tap / p.taps_w, dx = tap - dy * p.taps_w;
+          const int cw = w0 * p.stride + dx - p.pad_w;
+          const int chh = h0 * p.stride + dy - p.pad_h;
+          if (chunk < p.chunks_a) tma_load_4d(sA, &p.tmA, &full_bar[stage], chunk * kChunkK, cw, chh, batch);
+          else tma_load_4d(sA, &p.tmA2, &full_bar[stage], (chunk - p.chunks_a) * kChunkK, cw, chh, batch);
+        } else {
+          tma_load_4d(sA, &p.tmA, &full_bar[stage], it * kChunkK, m0, 0, batch);
+        }
+        if constexpr (EPI == ATDN_EPI_CORR) {
+          tma_load_4d(sB, &p.tmB, &full_bar[stage], it * kChunkK, bw0, bh0, batch);
+        } else {
+          tma_load_4d(sB, &p.tmB, &full_bar[stage], it * kChunkK, n0, 0, p.b_batched ? batch : 0);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        // valid 16-wide K steps in this chunk (zero-padded tails are skipped)
+        int rem;
+        if (p.a_mode == ATDN_MODE_PATCH) {
+          const int chunk = it % chunks;
+          rem = chunk < p.chunks_a ? p.c_a - chunk * kChunkK : p.c_a2 - (chunk - p.chunks_a) * kChunkK;
+        } else {
+          rem = p.c_a - it * kChunkK;
+        }
+        const int ksteps = rem >= kChunkK ? 4 : (rem + 15) >> 4;
+        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+        const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+        const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
+        for (int k = 0; k < ksteps; ++k) {
+          // +32 bytes (>>4 = 2) per 16-element K step inside the 128-byte swizzle atom
+          umma_f16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue warps 0..3 =====
+    const int r = warp * 32 + lane;
+    bool valid;
+    long long pix;
+    if (p.a_mode == ATDN_MODE_PATCH) {
+      const int h = h0 + (r >> 4), w = w0 + (r & 15);
+      valid = (h < p.out_h) && (w < p.out_w);
+      pix = (static_cast<long long>(batch) * p.out_h + h) * p.out_w + w;
+    } else {
+      valid = (m0 + r) < p.m_rows;
+      pix = static_cast<long long>(batch) * p.m_rows + m0 + r;
+    }
+    mbar_wait(&tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    if constexpr (EPI == ATDN_EPI_CORR) {
+      epilogue_corr(p, valid, pix, bh0, bw0, trow);
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(trow + c * 32, v);
+        tmem_ld_wait();
+        epilogue_chunk<EPI>(p, valid, pix, n0 + c * 32, v);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// fp16 tensor, dims innermost first, strides in elements for dims 1..3, 128B swizzle, zero OOB fill.
+static int make_map_f16(CUtensorMap* m, const void* ptr, const int64_t dims[4], const int64_t strides[3],
+                        const uint32_t box[4], const uint32_t estr[4], const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  ATDN_REQUIRE(fn != nullptr, ATDN_ERR_ARCH, "cuTensorMapEncodeTiled is not available from the driver");
+  ATDN_REQUIRE(ptr != nullptr && aligned16(ptr), ATDN_ERR_ALIGN, "%s: pointer must be non-null and 16-byte aligned", what);
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < 4; ++i) {
+    ATDN_REQUIRE(dims[i] >= 1, ATDN_ERR_ARG, "%s: dims[%d] = %lld", what, i, (long long)dims[i]);
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = box[i];
+    es[i] = estr[i];
+  }
+  for (int i = 0; i < 3; ++i) {
+    ATDN_REQUIRE(strides[i] > 0 && strides[i] % 8 == 0, ATDN_ERR_ALIGN,
+                 "%s: strides[%d] = %lld elements is not a positive multiple of 8 (16 bytes)", what, i,
+                 (long long)strides[i]);
+    gs[i] = (cuuint64_t)strides[i] * 2u;
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ATDN_REQUIRE(r == CUDA_SUCCESS, (int)r, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
+template <int BN, int STAGES, int EPI>
+static int launch(const TcParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BN * kChunkK * 2) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    ATDN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  tc_gemm_kernel<BN, STAGES, EPI><<<grid, kThreads, smem, stream>>>(p);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI>
+static int dispatch_bn(int bn, const TcParams& p, dim3 grid, cudaStream_t s) {
+  switch (bn) {
+    case 64:  return launch<64, 4, EPI>(p, grid, s);
+    case 96:  return launch<96, 3, EPI>(p, grid, s);
+    case 128: return launch<128, 3, EPI>(p, grid, s);
+    case 192: return launch<192, 4, EPI>(p, grid, s);
+    default:  return set_error(ATDN_ERR_UNSUP, "atdn_tc_gemm: unsupported bn %d for epilogue %d", bn, EPI);
+  }
+}
+
+}  // namespace atdn
+
+using namespace atdn;
+
+extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ATDN_REQUIRE(d != nullptr, ATDN_ERR_ARG, "atdn_tc_gemm: null descriptor");
+  if (int e = require_sm100()) return e;
+  ATDN_REQUIRE(d->a_mode == ATDN_MODE_ROWS || d->a_mode == ATDN_MODE_PATCH, ATDN_ERR_ARG, "atdn_tc_gemm: bad a_mode");
+  ATDN_REQUIRE(d->n_valid > 0, ATDN_ERR_ARG, "atdn_tc_gemm: n_valid must be positive");
+  const bool corr = d->epi == ATDN_EPI_CORR;
+  ATDN_REQUIRE((d->b_mode == ATDN_MODE_PATCH) == corr, ATDN_ERR_ARG, "atdn_tc_gemm: PATCH B operand is only valid with ATDN_EPI_CORR");
+  ATDN_REQUIRE(!corr || (d->bn == 256 && d->a_mode == ATDN_MODE_ROWS), ATDN_ERR_ARG, "atdn_tc_gemm: CORR needs bn=256 and ROWS A");
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_mode = d->a_mode;
+  p.n_valid = d->n_valid;
+  p.flags = d->flags;
+  p.b_batched = (d->flags & ATDN_F_B_BATCHED) ? 1 : 0;
+  p.alpha = d->alpha;
+  p.bias = d->bias;
+  p.out = d->out;
+  p.out_pitch = d->out_pitch;
+  p.out_ch_off = d->out_ch_off;
+  p.resid = static_cast<const __half*>(d->resid16);
+  p.resid_pitch = d->resid_pitch;
+  p.resid_ch_off = d->resid_ch_off;
+  p.h32 = d->h32;
+  p.z32 = d->z32;
+  p.rh16 = static_cast<__half*>(d->rh16);
+  p.aux32 = d->aux32;
+  p.gamma = d->gamma;
+  ATDN_REQUIRE(p.out != nullptr || d->epi == ATDN_EPI_GRU_ZR, ATDN_ERR_ARG, "atdn_tc_gemm: null output");
+
+  const uint32_t ones[4] = {1, 1, 1, 1};
+  dim3 grid;
+  const int batch = (int)d->a_dims[3];
+  grid.z = batch;
+  const int64_t c_a = d->a_dims[0];
+  if (d->a_mode == ATDN_MODE_PATCH) {
+    ATDN_REQUIRE(d->stride == 1 || d->stride == 2, ATDN_ERR_UNSUP, "atdn_tc_gemm: stride %d", d->stride);
+    ATDN_REQUIRE(d->taps_h >= 1 && d->taps_w >= 1 && d->out_h >= 1 && d->out_w >= 1, ATDN_ERR_ARG, "atdn_tc_gemm: bad conv geometry");
+    const uint32_t s = (uint32_t)d->stride;
+    const uint32_t box[4] = {64, 16 * s, 8 * s, 1};
+    const uint32_t es[4] = {1, s, s, 1};
+    if (int e = make_map_f16(&p.tmA, d->a, d->a_dims, d->a_strides, box, es, "A")) return e;
+    p.chunks_a = (d->a_split_chunk > 0) ? d->a_split_chunk : (int)((c_a + 63) / 64);
+    p.c_a = (int)c_a;
+    if (d->a_split_chunk > 0) {
+      ATDN_REQUIRE(d->a2 != nullptr, ATDN_ERR_ARG, "atdn_tc_gemm: a_split_chunk without a2");
+      ATDN_REQUIRE(c_a == 64LL * d->a_split_chunk, ATDN_ERR_ARG, "atdn_tc_gemm: a must hold exactly a_split_chunk*64 channels");
+      if (int e = make_map_f16(&p.tmA2, d->a2, d->a2_dims, d->a2_strides, box, es, "A2")) return e;
+      p.chunks_a2 = (int)((d->a2_dims[0] + 63) / 64);
+      p.c_a2 = (int)d->a2_dims[0];
+    }
+    p.taps_w = d->taps_w;
+    p.pad_h = d->pad_h;
+    p.pad_w = d->pad_w;
+    p.stride = d->stride;
+    p.out_h = d->out_h;
+    p.out_w = d->out_w;
+    p.tiles_w = ceil_div(d->out_w, 16);
+    p.num_k_iters = d->taps_h * d->taps_w * (p.chunks_a + p.chunks_a2);
+    grid.x = p.tiles_w * ceil_div(d->out_h, 8);
+  } else {
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int e = make_map_f16(&p.tmA, d->a, d->a_dims, d->a_strides, box, ones, "A")) return e;
+    p.c_a = (int)c_a;
+    p.chunks_a = (int)((c_a + 63) / 64);
+    p.num_k_iters = p.chunks_a;
+    p.m_rows = (int)d->a_dims[1];
+    p.taps_w = 1;
+    p.stride = 1;
+    grid.x = ceil_div(p.m_rows, 128);
+  }
+  // the packed K extent of B must cover every K iteration
+  ATDN_REQUIRE(d->b_dims[0] >= (int64_t)(p.num_k_iters - 1) * 64 + 1, ATDN_ERR_ARG,
+               "atdn_tc_gemm: B has K extent %lld but the A side iterates %d chunks of 64", (long long)d->b_dims[0], p.num_k_iters);
+
+  if (corr) {
+    const uint32_t box[4] = {64, 32, 8, 1};
+    if (int e = make_map_f16(&p.tmB, d->b, d->b_dims, d->b_strides, box, ones, "B")) return e;
+    p.corr_h = d->corr_h;
+    p.corr_w = d->corr_w;
+    ATDN_REQUIRE(d->corr_h == d->b_dims[2] && d->corr_w == d->b_dims[1], ATDN_ERR_ARG, "atdn_tc_gemm: corr grid != B image dims");
+    p.corr_tiles_w = ceil_div(d->corr_w, 32);
+    for (int i = 0; i < 4; ++i) {
+      p.lvl_pitch[i] = d->lvl_pitch[i];
+      ATDN_REQUIRE(d->lvl_pitch[i] % 4 == 0 && d->lvl_pitch[i] >= (d->corr_w >> i), ATDN_ERR_ALIGN, "atdn_tc_gemm: lvl_pitch[%d]", i);
+    }
+    for (int i = 0; i < 3; ++i) {
+      p.lvl[i] = d->lvl[i];
+      ATDN_REQUIRE(d->lvl[i] != nullptr && aligned16(d->lvl[i]), ATDN_ERR_ALIGN, "atdn_tc_gemm: lvl[%d]", i);
+    }
+    ATDN_REQUIRE(aligned16(d->out), ATDN_ERR_ALIGN, "atdn_tc_gemm: out");
+    grid.y = p.corr_tiles_w * ceil_div(d->corr_h, 8);
+    return launch<256, 4, ATDN_EPI_CORR>(p, grid, stream);
+  }
+
+  {
+    const uint32_t box[4] = {64, (uint32_t)d->bn, 1, 1};
+    if (int e = make_map_f16(&p.tmB, d->b, d->b_dims, d->b_strides, box, ones, "B")) return e;
+  }
+  grid.y = ceil_div(d->n_valid, d->bn);
+  // vector-store alignment of the epilogue
+  ATDN_REQUIRE(d->out_pitch % 8 == 0 && d->out_ch_off % 8 == 0, ATDN_ERR_ALIGN, "atdn_tc_gemm: out_pitch/out_ch_off must be multiples of 8");
+  switch (d->epi) {
+    case ATDN_EPI_STORE16:
+      ATDN_REQUIRE(!(d->flags & ATDN_F_RESID) || (d->resid16 && d->resid_pitch % 8 == 0 && d->resid_ch_off % 8 == 0), ATDN_ERR_ARG, "atdn_tc_gemm: residual");
+      ATDN_REQUIRE(!(d->flags & ATDN_F_FLOWTAIL) || d->aux32, ATDN_ERR_ARG, "atdn_tc_gemm: FLOWTAIL needs aux32");
+      ATDN_REQUIRE(!(d->flags & ATDN_F_TANH_LO) || d->h32, ATDN_ERR_ARG, "atdn_tc_gemm: TANH_LO needs h32");
+      return dispatch_bn<ATDN_EPI_STORE16>(d->bn, p, grid, stream);
+    case ATDN_EPI_STORE32:
+      return dispatch_bn<ATDN_EPI_STORE32>(d->bn, p, grid, stream);
+    case ATDN_EPI_GRU_ZR:
+      ATDN_REQUIRE(d->bn == 128 && d->n_valid == 256 && d->h32 && d->z32 && d->rh16, ATDN_ERR_ARG, "atdn_tc_gemm: GRU_ZR arguments");
+      return launch<128, 3, ATDN_EPI_GRU_ZR>(p, grid, stream);
+    case ATDN_EPI_GRU_Q:
+      ATDN_REQUIRE(d->n_valid == 128 && d->h32 && d->z32, ATDN_ERR_ARG, "atdn_tc_gemm: GRU_Q arguments");
+      return dispatch_bn<ATDN_EPI_GRU_Q>(d->bn, p, grid, stream);
+    case ATDN_EPI_PV:
+      ATDN_REQUIRE(d->resid16 && d->aux32 && d->gamma && d->resid_pitch % 8 == 0 && d->resid_ch_off % 8 == 0, ATDN_ERR_ARG, "atdn_tc_gemm: PV arguments");
+      return dispatch_bn<ATDN_EPI_PV>(d->bn, p, grid, stream);
+    default:
+      return set_error(ATDN_ERR_UNSUP, "atdn_tc_gemm: unknown epilogue %d", d->epi);
+  }
+}

@@ -1,0 +1,258 @@
+"""Tensor-level wrappers around the C ABI (one Python call = one kernel launch on the current stream).
+
+Activations are NHWC fp16 buffers ``[B, H, W, pitch]``; a :class:`View` names a channel slice of such
+a buffer so that concatenations (``torch.cat`` in the reference) are free: producers write into
+slices of a wider buffer and consumers read the slices through their own TMA tensor maps.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+
+class View:
+    """Channels [c0, c0+c) of an NHWC buffer ``t`` of shape [B, H, W, pitch]."""
+
+    def __init__(self, t, c0=0, c=None):
+        assert t.dim() == 4 and t.is_contiguous()
+        self.t, self.c0 = t, c0
+        self.c = (t.shape[3] - c0) if c is None else c
+        assert 0 <= c0 and c0 + self.c <= t.shape[3]
+
+    B = property(lambda s: s.t.shape[0])
+    H = property(lambda s: s.t.shape[1])
+    W = property(lambda s: s.t.shape[2])
+    pitch = property(lambda s: s.t.shape[3])
+
+    def ptr(self):
+        return L.ptr(self.t, self.c0)
+
+
+def pad_bias(b, n=None):
+    """fp32 bias padded with zeros to a multiple of 64 entries (epilogues read whole 8-groups)."""
+    n = b.numel() if n is None else n
+    out = torch.zeros((n + 63) // 64 * 64, dtype=torch.float32, device=b.device)
+    out[: b.numel()] = b.float()
+    return out
+
+
+def pack_conv_weight(w):
+    """[Cout, Cin, kh, kw] fp32 -> K-major fp16 [Cout, taps * ceil(Cin/64)*64], K = (tap, channel)."""
+    cout, cin, kh, kw = w.shape
+    cpad = (cin + 63) // 64 * 64
+    wp = torch.zeros(cout, kh * kw, cpad, dtype=torch.float32, device=w.device)
+    wp[:, :, :cin] = w.float().permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    return wp.reshape(cout, kh * kw * cpad).half().contiguous()
+
+
+def pack_rows_weight(w2d):
+    """[Cout, K] fp32 -> fp16 [Cout, ceil(K/64)*64] (zero padded)."""
+    cout, k = w2d.shape
+    kp = (k + 63) // 64 * 64
+    wp = torch.zeros(cout, kp, dtype=torch.float32, device=w2d.device)
+    wp[:, :k] = w2d.float()
+    return wp.half().contiguous()
+
+
+def _fill_weight(d, wp):
+    cout, ktot = wp.shape
+    d.b = L.ptr(wp)
+    L._set(d.b_dims, (ktot, cout, 1, 1))
+    L._set(d.b_strides, (ktot, ktot * cout, ktot * cout))
+
+
+def _fill_out(d, out, n_valid, alpha, bias):
+    d.n_valid = n_valid
+    d.alpha = alpha
+    d.bias = L.ptr(bias)
+    if out is not None:
+        d.out = out.ptr()
+        d.out_pitch = out.pitch
+        d.out_ch_off = 0
+
+
+def conv_tc(a, wp, bias, out, *, cout, taps=(1, 1), pad=(0, 0), stride=1, bn=128, epi=L.EPI_STORE16, flags=0,
+            alpha=1.0, a2=None, resid=None, h32=None, z32=None, rh16=None, aux32=None, gamma=None):
+    """Convolution as implicit GEMM on tcgen05.  ``a`` (and optional ``a2``, concatenated after it)
+    are NHWC fp16 Views of the INPUT image; ``out`` is a View of the output buffer."""
+    d = L.TcDesc()
+    d.bn, d.epi, d.flags, d.a_mode, d.b_mode = bn, epi, flags, L.MODE_PATCH, L.MODE_ROWS
+    kh, kw = taps
+    oh = (a.H + 2 * pad[0] - kh) // stride + 1
+    ow = (a.W + 2 * pad[1] - kw) // stride + 1
+    d.out_h, d.out_w = oh, ow
+    d.taps_h, d.taps_w, d.pad_h, d.pad_w, d.stride = kh, kw, pad[0], pad[1], stride
+    d.a = a.ptr()
+    L._set(d.a_dims, (a.c, a.W, a.H, a.B))
+    L._set(d.a_strides, (a.pitch, a.W * a.pitch, a.H * a.W * a.pitch))
+    if a2 is not None:
+        assert a.c % 64 == 0 and (a2.B, a2.H, a2.W) == (a.B, a.H, a.W)
+        d.a_split_chunk = a.c // 64
+        d.a2 = a2.ptr()
+        L._set(d.a2_dims, (a2.c, a2.W, a2.H, a2.B))
+        L._set(d.a2_strides, (a2.pitch, a2.W * a2.pitch, a2.H * a2.W * a2.pitch))
+    _fill_weight(d, wp)
+    _fill_out(d, out, cout, alpha, bias)
+    if resid is not None:
+        d.resid16, d.resid_pitch, d.resid_ch_off = resid.ptr(), resid.pitch, 0
+    d.h32, d.z32, d.rh16, d.aux32, d.gamma = L.ptr(h32), L.ptr(z32), L.ptr(rh16), L.ptr(aux32), L.ptr(gamma)
+    L.tc_gemm(d)
+    return oh, ow
+
+
+def gemm_rows(a, a_k, a_rows, a_pitch, batch, b, b_rows, b_pitch, out_ptr, out_pitch, *, n_valid, a_bstride=None,
+              b_bstride=None, bn=128, epi=L.EPI_STORE16, flags=0, alpha=1.0, bias=None, resid_ptr=None,
+              resid_pitch=0, aux32=None, gamma=None):
+    """Batched D[b] = A[b] (a_rows x a_k) . B[b]^T (b_rows x a_k); pointers are ctypes void pointers,
+    pitches in elements.  ``b_bstride=None`` shares B across the batch."""
+    d = L.TcDesc()
+    d.bn, d.epi, d.a_mode, d.b_mode = bn, epi, L.MODE_ROWS, L.MODE_ROWS
+    d.flags = flags | (L.F_B_BATCHED if b_bstride is not None else 0)
+    a_bstride = a_rows * a_pitch if a_bstride is None else a_bstride
+    d.a = a
+    L._set(d.a_dims, (a_k, a_rows, 1, batch))
+    L._set(d.a_strides, (a_pitch, a_bstride, a_bstride))
+    d.b = b
+    nb = batch if b_bstride is not None else 1
+    bs = b_bstride if b_bstride is not None else b_rows * b_pitch
+    L._set(d.b_dims, (a_k, b_rows, 1, nb))
+    L._set(d.b_strides, (b_pitch, bs, bs))
+    d.n_valid, d.alpha, d.bias = n_valid, alpha, L.ptr(bias)
+    d.out, d.out_pitch, d.out_ch_off = out_ptr, out_pitch, 0
+    if resid_ptr is not None:
+        d.resid16, d.resid_pitch, d.resid_ch_off = resid_ptr, resid_pitch, 0
+    d.aux32, d.gamma = L.ptr(aux32), L.ptr(gamma)
+    L.tc_gemm(d)
+
+
+# ----------------------------------------------------------------------------------------------
+# correlation pyramid
+# ----------------------------------------------------------------------------------------------
+def pyramid_shapes(h8, w8):
+    """[(H_l, W_l, pitch_l)] for the 4 levels; pitch = W_l rounded up to 4 floats (16 bytes)."""
+    out, h, w = [], h8, w8
+    for _ in range(4):
+        out.append((h, w, (w + 3) // 4 * 4))
+        h, w = h // 2, w // 2
+    return out
+
+
+def alloc_pyramid(batch, h8, w8, device):
+    n = h8 * w8
+    return [torch.empty(batch * n, h, p, dtype=torch.float32, device=device) for (h, w, p) in pyramid_shapes(h8, w8)]
+
+
+def corr_pyramid_build(fmap1, fmap2, levels):
+    """fmap1/fmap2: Views [B,H8,W8,256] fp16 -> the 4 fp32 pyramid levels (corr.py:16-30, 55-63)."""
+    d = L.TcDesc()
+    b, h8, w8 = fmap1.B, fmap1.H, fmap1.W
+    n = h8 * w8
+    d.bn, d.epi, d.flags, d.a_mode, d.b_mode = 256, L.EPI_CORR, L.F_B_BATCHED, L.MODE_ROWS, L.MODE_PATCH
+    d.a = fmap1.ptr()
+    L._set(d.a_dims, (fmap1.c, n, 1, b))
+    L._set(d.a_strides, (fmap1.pitch, n * fmap1.pitch, n * fmap1.pitch))
+    d.b = fmap2.ptr()
+    L._set(d.b_dims, (fmap2.c, w8, h8, b))
+    L._set(d.b_strides, (fmap2.pitch, w8 * fmap2.pitch, n * fmap2.pitch))
+    d.n_valid = n
+    d.alpha = 1.0 / math.sqrt(fmap1.c)
+    d.out, d.out_pitch, d.out_ch_off = L.ptr(levels[0]), 8, 0
+    for i in range(3):
+        d.lvl[i] = levels[i + 1].data_ptr()
+    for i in range(4):
+        d.lvl_pitch[i] = levels[i].shape[2]
+    d.corr_h, d.corr_w = h8, w8
+    L.tc_gemm(d)
+
+
+def corr_lookup(levels, coords, out16=None, out32=None):
+    """coords fp32 [B,H8,W8,2] -> out16 View [B,H8,W8,>=324] fp16 and/or out32 [B*H8*W8,324] fp32."""
+    b, h8, w8, _ = coords.shape
+    lv = (C.c_void_p * 4)(*[t.data_ptr() for t in levels])
+    lp = (C.c_int32 * 4)(*[t.shape[2] for t in levels])
+    L.check(L.load().atdn_corr_lookup(lv, lp, L.ptr(coords), out16.ptr() if out16 is not None else None,
+                                      C.c_int64(out16.pitch if out16 is not None else 0), L.ptr(out32),
+                                      b, h8, w8, L.stream_ptr()), "atdn_corr_lookup")
+
+
+# ----------------------------------------------------------------------------------------------
+# element-wise
+# ----------------------------------------------------------------------------------------------
+def stem_im2col(image, rows):
+    b, _, h, w = image.shape
+    L.check(L.load().atdn_stem_im2col(L.ptr(image), L.ptr(rows), C.c_int64(rows.shape[-1]), b, h, w, L.stream_ptr()),
+            "atdn_stem_im2col")
+
+
+def flow_im2col(flow, rows):
+    b, h8, w8, _ = flow.shape
+    L.check(L.load().atdn_flow_im2col(L.ptr(flow), L.ptr(rows), C.c_int64(rows.shape[-1]), b, h8, w8, L.stream_ptr()),
+            "atdn_flow_im2col")
+
+
+def inorm_stats(x, scratch, parts, stats):
+    L.check(L.load().atdn_inorm_stats(x.ptr(), C.c_int64(x.pitch), x.B, x.H * x.W, x.c, L.ptr(scratch), parts,
+                                      L.ptr(stats), L.stream_ptr()), "atdn_inorm_stats")
+
+
+def inorm_apply(x, stats, y, resid=None, relu=True):
+    L.check(L.load().atdn_inorm_apply(x.ptr(), C.c_int64(x.pitch), L.ptr(stats),
+                                      resid.ptr() if resid is not None else None,
+                                      C.c_int64(resid.pitch if resid is not None else 0), y.ptr(), C.c_int64(y.pitch),
+                                      x.B, x.H * x.W, x.c, int(relu), L.stream_ptr()), "atdn_inorm_apply")
+
+
+def softmax_rows(s32, p16, inv_sum, rows, cols):
+    L.check(L.load().atdn_softmax_rows(L.ptr(s32), C.c_int64(s32.shape[-1]), L.ptr(p16), C.c_int64(p16.shape[-1]),
+                                       L.ptr(inv_sum), C.c_int64(rows), cols, L.stream_ptr()), "atdn_softmax_rows")
+
+
+def flow_head_update(x, w, bias, coords1, flow):
+    L.check(L.load().atdn_flow_head_update(x.ptr(), C.c_int64(x.pitch), L.ptr(w), L.ptr(bias), L.ptr(coords1),
+                                           L.ptr(flow), x.B, x.H, x.W, L.stream_ptr()), "atdn_flow_head_update")
+
+
+def convex_upsample(mask32, flow, flow_up, flow_lo=None):
+    b, h8, w8, _ = flow.shape
+    L.check(L.load().atdn_convex_upsample(L.ptr(mask32), C.c_int64(mask32.shape[-1]), L.ptr(flow), L.ptr(flow_up),
+                                          L.ptr(flow_lo), b, h8, w8, L.stream_ptr()), "atdn_convex_upsample")
+
+
+def coords_init(coords1, flow, flow_init=None):
+    b, h8, w8, _ = coords1.shape
+    L.check(L.load().atdn_coords_init(L.ptr(coords1), L.ptr(flow), L.ptr(flow_init), b, h8, w8, L.stream_ptr()),
+            "atdn_coords_init")
+
+
+# ----------------------------------------------------------------------------------------------
+# fp32 small nets
+# ----------------------------------------------------------------------------------------------
+def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shift=None, skip=None, bn_scale=None,
+           bn_shift=None):
+    d = L.Conv32Desc()
+    b, cin, h, wd = x.shape
+    cout, _, k, _ = w.shape
+    d.x, d.y, d.w, d.bias = L.ptr(x), L.ptr(y), L.ptr(w), L.ptr(bias)
+    d.in_scale, d.in_shift, d.skip = L.ptr(in_scale), L.ptr(in_shift), L.ptr(skip)
+    d.bn_scale, d.bn_shift = L.ptr(bn_scale), L.ptr(bn_shift)
+    d.batch, d.cin, d.cout, d.in_h, d.in_w, d.k, d.stride, d.pad, d.mish = b, cin, cout, h, wd, k, stride, pad, int(mish)
+    L.check(L.load().atdn_conv32(C.byref(d), L.stream_ptr()), "atdn_conv32")
+
+
+def linear32(x, w, bias, y, act=0):
+    L.check(L.load().atdn_linear32(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(y), x.shape[0], w.shape[1], w.shape[0], act,
+                                   L.stream_ptr()), "atdn_linear32")
+
+
+def lstm_cell(x, w_ih, w_hh, b_ih, b_hh, h, c, gates):
+    L.check(L.load().atdn_lstm_cell(L.ptr(x), L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih), L.ptr(b_hh), L.ptr(h), L.ptr(c),
+                                    L.ptr(gates), x.shape[0], w_ih.shape[1], h.shape[1], L.stream_ptr()), "atdn_lstm_cell")
+
+
+def keyframe_search(emb, code, dist, index):
+    L.check(L.load().atdn_keyframe_search(L.ptr(emb), L.ptr(code), L.ptr(dist), L.ptr(index), C.c_int64(emb.shape[0]),
+                                          emb.shape[1], L.stream_ptr()), "atdn_keyframe_search")

@@ -1,0 +1,198 @@
+/*
+ * atdn_b200.h -- C ABI of libatdn_b200.so: hand-written sm_100a kernels for the ATDN vSLAM odometry
+ * front end (GMA flow -> CLVO pose -> keyframe search).
+ *
+ * The reference (MILAB-IIT-CV/ATDN_vSLAM) is pure Python/PyTorch and has NO FFI of its own
+ * (SURVEY.md section 2.2); every entry point below therefore cites the reference *Python* call site
+ * whose ATen/cuDNN/cuBLAS dispatch it replaces.  GMA.whl!/ = inside GMA-1.0.0-py3-none-any.whl.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *  - the caller owns all memory (inputs, outputs, workspaces); the library never allocates device
+ *    memory and keeps no reference after the call returns;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises;
+ *  - return value: 0 = ok, < 0 = argument/shape/alignment error detected before launch,
+ *    > 0 = cudaError_t / CUresult of the failed runtime call.  atdn_last_error() returns a
+ *    thread-local, NUL-terminated description of the last non-zero return;
+ *  - there is no CPU fallback: on a device that is not sm_100 every compute call returns
+ *    ATDN_ERR_ARCH.
+ *  - activation tensors are NHWC fp16 ("pixel rows"); `pitch` = elements between consecutive
+ *    pixels; channel slices of a wider buffer are addressed with (pointer + channel offset, pitch).
+ */
+#ifndef ATDN_B200_H_
+#define ATDN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATDN_ERR_ARG   (-1)
+#define ATDN_ERR_ALIGN (-2)
+#define ATDN_ERR_ARCH  (-3)
+#define ATDN_ERR_UNSUP (-4)
+
+const char* atdn_last_error(void);
+int atdn_version(void);
+/* 0 if `device` is an sm_100 part, ATDN_ERR_ARCH otherwise (also primes the driver entry points). */
+int atdn_check_device(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core implicit GEMM (tcgen05.mma kind::f16, fp32 accumulation in TMEM, operands staged by
+ * TMA with 128B swizzle).  D[m, n] = sum_k A[m, k] * B[n, k].
+ *
+ * One kernel family serves every dense contraction on the path:
+ *   convolutions   GMA.whl!/GMA/core/extractor.py:47-55,173-181 (encoders), update.py:76-84 (motion
+ *                  encoder), :48-63 (SepConvGRU), :7-15,120-123 (flow / mask heads), gma.py:59 (to_qk),
+ *                  gma.py:105 (to_v)                                      -- replaces cuDNN conv
+ *   corr volume    GMA.whl!/GMA/core/corr.py:55-63 + pyramid :28-30      -- replaces cuBLAS SGEMM + avg_pool2d
+ *   attention      GMA.whl!/GMA/core/gma.py:72 (q k^T), :107 (attn v)     -- replaces cuBLAS batched GEMM
+ *
+ * Operand addressing ("modes"), all fp16, innermost dimension first:
+ *   ROWS : dims {K, rows, 1, batch}            one tile = 128 (A) or `bn` (B) consecutive rows
+ *   PATCH: dims {C, W, H, batch} (NHWC image)  one A tile = 8 x 16 output pixels, one K step per
+ *          (tap, 64-channel chunk); out-of-image taps are zero-filled by TMA (= conv zero padding).
+ *          For B (corr volume only) one tile = 8 x 32 target pixels.
+ * strides[] are in ELEMENTS for dims 1..3 and must be multiples of 8 (16 bytes); pointers must be
+ * 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+enum { ATDN_MODE_ROWS = 0, ATDN_MODE_PATCH = 1 };
+
+enum {
+  ATDN_EPI_STORE16 = 0, /* out16[pix, ch_off+n] = act(alpha*acc + bias[n]) (+ optional residual / flow tail / tanh split) */
+  ATDN_EPI_STORE32 = 1, /* out32[pix, ch_off+n] = alpha*acc + alpha*bias[n]        (fp32)                                */
+  ATDN_EPI_CORR    = 2, /* corr pyramid: level0 = alpha*acc, levels 1..3 = 2x2 means, fp32 (corr.py:16-30)              */
+  ATDN_EPI_GRU_ZR  = 3, /* n<128: z32 = sigmoid(acc+b); n>=128: rh16 = sigmoid(acc+b) * h32   (update.py:51-53,58-60)   */
+  ATDN_EPI_GRU_Q   = 4, /* q = tanh(acc+b); h32 = (1-z)*h32 + z*q; out16 = h32               (update.py:53-54,60-61)   */
+  ATDN_EPI_PV      = 5  /* out16 = resid16 + gamma * acc * row_scale[pix]                    (gma.py:107-113)           */
+};
+
+enum {
+  ATDN_F_RELU      = 1,  /* STORE16: relu after bias                                                      */
+  ATDN_F_RESID     = 2,  /* STORE16: y = relu(resid16[pix, n] + y)   (extractor.py:55)                     */
+  ATDN_F_FLOWTAIL  = 4,  /* STORE16: columns n >= n_valid-2 take aux32[pix*2 + (n - (n_valid-2))] (update.py:84) */
+  ATDN_F_TANH_LO   = 8,  /* STORE16: n < 128 -> tanh (also written to h32), n >= 128 -> relu (network.py:95-97) */
+  ATDN_F_B_BATCHED = 16  /* B operand has a batch dimension (attention GEMMs, corr volume)               */
+};
+
+typedef struct atdn_tc_desc {
+  int32_t bn;             /* N tile: 64, 96, 128, 192 or 256 (256 only for ATDN_EPI_CORR)           */
+  int32_t epi;            /* ATDN_EPI_*                                                             */
+  int32_t flags;          /* ATDN_F_*                                                               */
+  int32_t a_mode;         /* ATDN_MODE_*                                                            */
+  int32_t b_mode;         /* ATDN_MODE_ROWS, or ATDN_MODE_PATCH for ATDN_EPI_CORR                   */
+  int32_t n_valid;        /* number of valid output columns (Cout / N)                              */
+  /* convolution geometry (PATCH A): out_h x out_w output pixels per image                          */
+  int32_t out_h, out_w;
+  int32_t taps_h, taps_w, pad_h, pad_w, stride;   /* stride 1 or 2                                  */
+  int32_t a_split_chunk;  /* 64-channel chunks [0, split) of each tap come from `a`, the rest from
+                             `a2` (concatenated inputs without a copy); 0 = `a` only                */
+  const void* a;  int64_t a_dims[4];  int64_t a_strides[3];
+  const void* a2; int64_t a2_dims[4]; int64_t a2_strides[3];
+  const void* b;  int64_t b_dims[4];  int64_t b_strides[3];
+  /* epilogue */
+  float alpha;            /* scale applied to the accumulator                                       */
+  const float* bias;      /* [n_valid] fp32 or NULL                                                 */
+  void* out;              /* fp16 (STORE16, GRU_Q, PV) / fp32 (STORE32) / level-0 fp32 (CORR)       */
+  int64_t out_pitch;      /* elements per pixel row                                                 */
+  int64_t out_ch_off;
+  const void* resid16;    /* STORE16|RESID, PV: fp16 [pix, resid_pitch] at resid_ch_off             */
+  int64_t resid_pitch, resid_ch_off;
+  float* h32;             /* GRU_*: fp32 hidden state [pix,128]; STORE16|TANH_LO: written           */
+  float* z32;             /* GRU_ZR writes / GRU_Q reads: fp32 [pix,128]                            */
+  void* rh16;             /* GRU_ZR: fp16 [pix,128] = r*h                                           */
+  const float* aux32;     /* FLOWTAIL: fp32 flow [pix,2]; PV: row_scale [pix]                       */
+  const float* gamma;     /* PV: pointer to the scalar Aggregate.gamma                              */
+  /* CORR: pyramid levels 1..3 (fp32) and their row pitches; level l is [batch*rows, H_l, pitch_l]  */
+  float* lvl[3];
+  int32_t lvl_pitch[4];   /* pitch of levels 0..3 in elements (multiples of 4)                      */
+  int32_t corr_h, corr_w; /* target grid H8 x W8                                                    */
+} atdn_tc_desc;
+
+int atdn_tc_gemm(const atdn_tc_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Correlation lookup -- GMA.whl!/GMA/core/corr.py:32-53 + utils/utils.py:59-73 (grid_sample).
+ * coords: fp32 [B, H8, W8, 2] (x, y); levels as written by ATDN_EPI_CORR;
+ * out: fp16 [B*H8*W8, out_pitch], channel = level*81 + a*9 + b  (a offsets x, b offsets y).
+ * ---------------------------------------------------------------------------------------------- */
+int atdn_corr_lookup(const float* const lvl[4], const int32_t lvl_pitch[4], const float* coords,
+                     void* out16, int64_t out_pitch, float* out32_or_null,
+                     int32_t batch, int32_t h8, int32_t w8, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Element-wise / data-movement kernels of the flow net
+ * ---------------------------------------------------------------------------------------------- */
+/* network.py:75-79 + im2col for the 7x7 stride-2 stem (extractor.py:173): image fp32 NCHW [B,3,H,W]
+ * in 0..255 -> rows fp16 [B*(H/2)*(W/2), pitch] with k = (dy*7+dx)*3 + c of 2*(x/255)-1.            */
+int atdn_stem_im2col(const float* image, void* rows16, int64_t pitch, int32_t batch, int32_t h, int32_t w,
+                     void* stream);
+/* update.py:79 (convf1 7x7 on the 2-channel flow): flow fp32 [B,H8,W8,2] -> rows fp16 [pix, pitch],
+ * k = (dy*7+dx)*2 + c, zero padded.                                                                 */
+int atdn_flow_im2col(const float* flow, void* rows16, int64_t pitch, int32_t batch, int32_t h8, int32_t w8,
+                     void* stream);
+/* nn.InstanceNorm2d (extractor.py:28-32,127) on NHWC fp16: per (image, channel) mean / rstd over H*W
+ * into stats fp32 [B, C, 2]; two-stage, deterministic.  scratch: fp32 [B * parts * C * 2].          */
+int atdn_inorm_stats(const void* x16, int64_t pitch, int32_t batch, int32_t hw, int32_t c,
+                     float* scratch, int32_t parts, float* stats, void* stream);
+/* y = relu((x - mean) * rstd); if resid16: y = relu(resid16 + y) (extractor.py:47-55).  In place ok. */
+int atdn_inorm_apply(const void* x16, int64_t pitch, const float* stats, const void* resid16, int64_t resid_pitch,
+                     void* y16, int64_t y_pitch, int32_t batch, int32_t hw, int32_t c, int32_t relu, void* stream);
+/* softmax over keys of fp32 logits (gma.py:73): p16[row, :] = exp(s - max) (un-normalised, fp16),
+ * inv_sum[row] = 1 / sum(p16).  rows = B*N, cols = N, pitches in elements.                          */
+int atdn_softmax_rows(const float* s32, int64_t s_pitch, void* p16, int64_t p_pitch, float* inv_sum,
+                      int64_t rows, int32_t cols, void* stream);
+/* update.py:14 flow_head.conv2 (3x3, 256 -> 2) + network.py:116: delta = conv(x16) + bias;
+ * coords1 += delta; flow = coords1 - coords0 (coords0 = pixel grid).  x16 NHWC [B,H8,W8,256].       */
+int atdn_flow_head_update(const void* x16, int64_t pitch, const float* w, const float* bias,
+                          float* coords1, float* flow, int32_t batch, int32_t h8, int32_t w8, void* stream);
+/* network.py:59-70 convex upsampling: mask fp32 [pix, 576] (already x0.25), flow fp32 [B,H8,W8,2]
+ * -> flow_up fp32 NCHW [B,2,8*H8,8*W8]; flow_lo NCHW [B,2,H8,W8] is written when non-NULL.          */
+int atdn_convex_upsample(const float* mask32, int64_t mask_pitch, const float* flow, float* flow_up,
+                         float* flow_lo_or_null, int32_t batch, int32_t h8, int32_t w8, void* stream);
+/* coords_grid (utils.py:76-79): coords[b,y,x,:] = (x, y) (+ flow_init NCHW [B,2,H8,W8] when non-NULL) */
+int atdn_coords_init(float* coords1, float* flow, const float* flow_init_or_null, int32_t batch, int32_t h8,
+                     int32_t w8, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 CUDA-core layers of the small-channel networks (CLVO encoder, MappingVAE encoder)
+ * atdn_vslam/layers/conv.py:36-37 (Conv = bn(mish(conv))), :83-90 (ResidualConv),
+ * atdn_vslam/odometry/network.py:63-73,131-134, atdn_vslam/localization/network.py:29-45,57-72.
+ *
+ * y = post( conv(pre(x)) + bias (+ skip) ),  NCHW fp32.
+ *   pre : x * in_scale[c] + in_shift[c] applied to in-bounds inputs (flow/RGB normalisation and the
+ *         depthwise 1x1 of encoder_CNN.0), or NULL
+ *   post: mish then affine bn (scale/shift per channel), each optional.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct atdn_conv32_desc {
+  const float* x; float* y;
+  const float* w;         /* [cout, cin, k, k] (PyTorch layout)                                    */
+  const float* bias;      /* [cout] or NULL                                                         */
+  const float* in_scale;  const float* in_shift;   /* [cin] or NULL                                 */
+  const float* skip;      /* [B, cout, oh, ow] added before the activation, or NULL                 */
+  const float* bn_scale;  const float* bn_shift;   /* [cout] folded eval-mode batch norm, or NULL   */
+  int32_t batch, cin, cout, in_h, in_w, k, stride, pad, mish;
+} atdn_conv32_desc;
+int atdn_conv32(const atdn_conv32_desc* desc, void* stream);
+
+/* y[b, o] = act(sum_i w[o, i] x[b, i] + bias[o]); act: 0 none, 1 mish (layers/linear.py:35-42)     */
+int atdn_linear32(const float* x, const float* w, const float* bias, float* y, int32_t batch, int32_t in_f,
+                  int32_t out_f, int32_t act, void* stream);
+/* torch.nn.LSTMCell (odometry/network.py:137,139): gate order i,f,g,o; h, c updated in place.
+ * gates_scratch: fp32 [batch, 4*hidden].                                                            */
+int atdn_lstm_cell(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                   float* h, float* c, float* gates_scratch, int32_t batch, int32_t in_f, int32_t hidden,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Keyframe search -- atdn_vslam/slam_framework/neural_slam.py:373-384:
+ * dist[k] = || emb[k, :] - code ||_2 ; *index = first arg-min.  emb fp32 [K, dim] (row pitch = dim).
+ * ---------------------------------------------------------------------------------------------- */
+int atdn_keyframe_search(const float* emb, const float* code, float* dist, int32_t* index, int64_t num,
+                         int32_t dim, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATDN_B200_H_ */

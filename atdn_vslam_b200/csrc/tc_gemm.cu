@@ -24,7 +24,7 @@ struct alignas(64) TcParams {
   int a_mode, tiles_w, out_h, out_w, m_rows, n_valid;
   int taps_w, pad_h, pad_w, stride;
   int chunks_a, chunks_a2, c_a, c_a2, num_k_iters;
-  int b_batched, flags;
+  int b_batched, a_shared, flags;
   int corr_h, corr_w, corr_tiles_w;
   int lvl_pitch[4];
   float* lvl[3];
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
           if (chunk < p.chunks_a) tma_load_4d(sA, &p.tmA, &full_bar[stage], chunk * kChunkK, cw, chh, batch);
           else tma_load_4d(sA, &p.tmA2, &full_bar[stage], (chunk - p.chunks_a) * kChunkK, cw, chh, batch);
         } else {
-          tma_load_4d(sA, &p.tmA, &full_bar[stage], it * kChunkK, m0, 0, batch);
+          tma_load_4d(sA, &p.tmA, &full_bar[stage], it * kChunkK, m0, 0, p.a_shared ? 0 : batch);
         }
         if constexpr (EPI == ATDN_EPI_CORR) {
           tma_load_4d(sB, &p.tmB, &full_bar[stage], it * kChunkK, bw0, bh0, batch);
@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 5) {
+    __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -467,6 +468,7 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
   p.n_valid = d->n_valid;
   p.flags = d->flags;
   p.b_batched = (d->flags & ATDN_F_B_BATCHED) ? 1 : 0;
+  p.a_shared = (d->flags & ATDN_F_A_SHARED) ? 1 : 0;
   p.alpha = d->alpha;
   p.bias = d->bias;
   p.out = d->out;
@@ -484,7 +486,8 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
 
   const uint32_t ones[4] = {1, 1, 1, 1};
   dim3 grid;
-  const int batch = (int)d->a_dims[3];
+  const int batch = (d->flags & ATDN_F_A_SHARED) ? (int)d->b_dims[3] : (int)d->a_dims[3];
+  ATDN_REQUIRE(!(d->flags & ATDN_F_A_SHARED) || d->a_mode == ATDN_MODE_ROWS, ATDN_ERR_ARG, "atdn_tc_gemm: A_SHARED needs ROWS A");
   grid.z = batch;
   const int64_t c_a = d->a_dims[0];
   if (d->a_mode == ATDN_MODE_PATCH) {

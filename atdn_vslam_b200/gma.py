@@ -1,0 +1,430 @@
+"""Drop-in for the reference GMA flow network (``GMA.whl!/GMA/core/network.py:26-129``).
+
+``RAFTGMA(args).forward(image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False)``
+keeps the reference signature, parameter names (so the reference state dict loads unchanged, with or
+without the ``module.`` prefix of ``DataParallel``) and return values.  All arithmetic runs in
+hand-written sm_100a kernels through the C ABI; PyTorch only owns the device buffers and the stream.
+
+Data layout in HBM (per batch of B pairs, 1/8-resolution grid H8 x W8, N = H8*W8):
+  activations      NHWC fp16, channel pitch padded to 8
+  HX  [B,H8,W8,512] fp16 : [0:128] GRU hidden state h | [128:256] context inp | [256:384] motion
+                          features | [384:512] globally aggregated motion features  (the reference's
+                          torch.cat([net, inp, mf, mfg]) materialised once, never copied)
+  h32 [B*N,128]    fp32 master copy of the hidden state (recurrent precision)
+  corr pyramid     fp32 [B*N, H_l, pitch_l] for l = 0..3 (pitch = W_l rounded up to 4)
+  P   [B,N,Np]     fp16 un-normalised attention probabilities exp(s - max), Np = N rounded up to 64;
+  inv_sum [B*N]    fp32 1/sum(P) applied in the P.V epilogue
+  coords1, flow    fp32 [B,H8,W8,2]
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops, schema
+from .ops import View
+
+
+def _build_module_tree(root: nn.Module, sch):
+    """Create nested containers so that ``root.state_dict()`` has exactly the schema's names."""
+    for name, (shape, kind) in sch.items():
+        parts = name.split(".")
+        mod = root
+        for p in parts[:-1]:
+            if p not in mod._modules:
+                mod.add_module(p, nn.Module())
+            mod = mod._modules[p]
+        if kind in ("bn_mean", "bn_var"):
+            mod.register_buffer(parts[-1], torch.zeros(shape) if kind == "bn_mean" else torch.ones(shape))
+        elif kind == "bn_count":
+            mod.register_buffer(parts[-1], torch.tensor(0, dtype=torch.long))
+        elif kind == "index":
+            n = shape[0]
+            mod.register_buffer(parts[-1], torch.arange(n).view(1, -1) - torch.arange(n).view(-1, 1) + n - 1)
+        else:
+            if kind == "conv_w":
+                fan = shape[1] * shape[2] * shape[3]
+                t = torch.randn(shape) / math.sqrt(fan)
+            elif kind == "lin_w":
+                t = torch.randn(shape) / math.sqrt(shape[1])
+            elif kind == "bn_w":
+                t = torch.ones(shape)
+            elif kind == "emb":
+                t = torch.randn(shape)
+            else:
+                t = torch.zeros(shape)
+            mod.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
+
+
+def _fold_bn(w, b, sd, name):
+    """conv -> eval-mode batch norm folded into the conv (extractor.py:21-26, norm after conv)."""
+    s = sd[name + ".weight"].float() / torch.sqrt(sd[name + ".running_var"].float() + 1e-5)
+    return w.float() * s.view(-1, 1, 1, 1), (b.float() - sd[name + ".running_mean"].float()) * s + sd[name + ".bias"].float()
+
+
+def _pick_bn(cout, m_tiles):
+    """Largest N tile that still yields >= ~1 wave of the 148 SMs."""
+    for bn in (192, 128, 96, 64):
+        if cout % bn == 0 and m_tiles * (cout // bn) >= 140:
+            return bn
+    for bn in (64, 96, 128, 192):
+        if cout % bn == 0:
+            return bn
+    return 64 if cout <= 64 else 128
+
+
+class _Conv:
+    """Packed weights of one convolution (K-major fp16 for the tcgen05 kernel, padded fp32 bias)."""
+
+    def __init__(self, w, b, taps=None, rows=False):
+        self.cout = w.shape[0]
+        self.cin = w.shape[1]
+        self.taps = (w.shape[2], w.shape[3])
+        self.pad = (w.shape[2] // 2, w.shape[3] // 2)
+        if rows:   # im2col layers: K = (tap, channel) flattened
+            self.wp = ops.pack_rows_weight(w.float().permute(0, 2, 3, 1).reshape(self.cout, -1))
+        else:
+            self.wp = ops.pack_conv_weight(w)
+        self.bias = ops.pad_bias(b, self.cout) if b is not None else None
+
+
+class _EncoderWeights:
+    def __init__(self, sd, p, norm):
+        self.norm = norm
+
+        def conv(name, bn_name=None):
+            w, b = sd[name + ".weight"], sd[name + ".bias"]
+            if norm == "batch" and bn_name is not None:
+                w, b = _fold_bn(w, b, sd, bn_name)
+            return w, b
+
+        w, b = conv(p + "conv1", p + "norm1")
+        self.stem = _Conv(w, b, rows=True)
+        self.blocks = []
+        for li, (planes, stride) in enumerate(schema.ENCODER_STAGES, start=1):
+            for bi in range(2):
+                q = f"{p}layer{li}.{bi}."
+                st = stride if bi == 0 else 1
+                blk = {"stride": st, "planes": planes,
+                       "conv1": _Conv(*conv(q + "conv1", q + "norm1")),
+                       "conv2": _Conv(*conv(q + "conv2", q + "norm2"))}
+                if st != 1:
+                    blk["down"] = _Conv(*conv(q + "downsample.0", q + "downsample.1"))
+                self.blocks.append(blk)
+        self.out = _Conv(sd[p + "conv2.weight"], sd[p + "conv2.bias"])
+
+
+class _Packed:
+    """All GMA weights in kernel layouts (built once per device from the module's state dict)."""
+
+    def __init__(self, sd):
+        self.fnet = _EncoderWeights(sd, "fnet.", "instance")
+        self.cnet = _EncoderWeights(sd, "cnet.", "batch")
+        u = "update_block."
+        g = lambda n: (sd[u + n + ".weight"], sd[u + n + ".bias"])
+        self.convc1 = _Conv(*g("encoder.convc1"))
+        self.convc2 = _Conv(*g("encoder.convc2"))
+        self.convf1 = _Conv(*g("encoder.convf1"), rows=True)
+        self.convf2 = _Conv(*g("encoder.convf2"))
+        w, b = g("encoder.conv")                       # 126 outputs + 2 raw flow channels (update.py:84)
+        self.conv = _Conv(w, torch.cat([b.float(), torch.zeros(2, device=b.device)]))
+        self.gru = []
+        for n in ("1", "2"):
+            wz, bz = g("gru.convz" + n)
+            wr, br = g("gru.convr" + n)
+            wq, bq = g("gru.convq" + n)
+            self.gru.append((_Conv(torch.cat([wz, wr], 0), torch.cat([bz, br], 0)), _Conv(wq, bq)))
+        self.fh1 = _Conv(*g("flow_head.conv1"))
+        self.fh2_w = sd[u + "flow_head.conv2.weight"].float().contiguous()
+        self.fh2_b = sd[u + "flow_head.conv2.bias"].float().contiguous()
+        self.mask0 = _Conv(*g("mask.0"))
+        self.mask2 = _Conv(*g("mask.2"))
+        self.gamma = sd[u + "aggregator.gamma"].float().contiguous()
+        # to_v runs with the weight as the A operand (output stored transposed for the P.V GEMM)
+        self.to_v = ops.pack_rows_weight(sd[u + "aggregator.to_v.weight"].float().reshape(128, 128))
+        self.to_qk = _Conv(sd["att.to_qk.weight"], None)
+
+
+class _Plan:
+    """Device buffers for a batch of ``b`` pairs at image size h x w (allocated once, reused)."""
+
+    def __init__(self, b, h, w, dev):
+        assert h % 8 == 0 and w % 8 == 0, "image sides must be multiples of 8 (use InputPadder as the reference does)"
+        self.b, self.h, self.w = b, h, w
+        self.h8, self.w8 = h // 8, w // 8
+        self.n = n = self.h8 * self.w8
+        assert self.h8 >= 16 and self.w8 >= 16, "1/8-resolution grid must be at least 16x16 (4-level pyramid)"
+        self.np_ = (n + 63) // 64 * 64
+        f16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        self.enc = {}          # encoder scratch keyed by number of images
+        h8, w8 = self.h8, self.w8
+        self.hx = f16(b, h8, w8, 512)
+        self.h32 = f32(b * n, 128)
+        self.z32 = f32(b * n, 128)
+        self.rh = f16(b, h8, w8, 128)
+        self.pyr = ops.alloc_pyramid(b, h8, w8, dev)
+        self.qk = f16(b, h8, w8, 256)
+        self.s32 = f32(b, n, self.np_)
+        self.p16 = f16(b, n, self.np_)
+        self.inv_sum = f32(b * n)
+        self.vt = f16(b, 128, self.np_)
+        self.coords1 = f32(b, h8, w8, 2)
+        self.flow = f32(b, h8, w8, 2)
+        self.corrfeat = f16(b, h8, w8, 328)
+        self.c1 = f16(b, h8, w8, 256)
+        self.corflo = f16(b, h8, w8, 256)
+        self.frows = f16(b * n, 104)
+        self.f1 = f16(b, h8, w8, 128)
+        self.fh = f16(b, h8, w8, 256)
+        self.mh = f16(b, h8, w8, 256)
+        self.mask32 = f32(b * n, 576)
+
+    def encoder_scratch(self, nimg, dev):
+        if nimg not in self.enc:
+            f16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
+            h2, w2, h4, w4, h8, w8 = self.h // 2, self.w // 2, self.h // 4, self.w // 4, self.h8, self.w8
+            self.enc[nimg] = {
+                "rows": f16(nimg * h2 * w2, 152),
+                "r2": [f16(nimg, h2, w2, 64) for _ in range(4)],
+                "r4": [f16(nimg, h4, w4, 96) for _ in range(4)],
+                "r8": [f16(nimg, h8, w8, 128) for _ in range(4)],
+                "stats": torch.empty(nimg, 128, 2, dtype=torch.float32, device=dev),
+                "scratch": torch.empty(nimg * 296 * 128 * 2, dtype=torch.float32, device=dev),
+            }
+        return self.enc[nimg]
+
+
+class RAFTGMA(nn.Module):
+    """B200-native GMA.  Same constructor contract as the reference (``network.py:27-43``): ``args`` is
+    duck-typed (``mixed_precision``, ``num_heads``, ``position_only``, ``position_and_content``,
+    ``__contains__``) and gets ``corr_levels``, ``corr_radius`` and ``dropout`` set on it."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.hidden_dim = self.context_dim = 128
+        args.corr_levels = 4
+        args.corr_radius = 4
+        if "dropout" not in self.args:
+            self.args.dropout = 0
+        if getattr(args, "num_heads", 1) != 1 or getattr(args, "position_only", False) or \
+                getattr(args, "position_and_content", False):
+            raise NotImplementedError("only the configuration the SLAM uses is built: num_heads=1, content-only "
+                                      "attention (atdn_vslam/utils/gma_parameters.py:8-10)")
+        _build_module_tree(self, schema.gma_schema())
+        self._packed = None
+        self._plans = {}
+
+    # -- weight handling --------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._packed = None
+        return super().load_state_dict(schema.strip_module_prefix(state_dict), strict=strict, **kw)
+
+    def _apply(self, fn, *a, **kw):
+        self._packed = None
+        self._plans = {}
+        return super()._apply(fn, *a, **kw)
+
+    def freeze_bn(self):   # network.py:45-48: eval-mode BN is the only mode implemented
+        return self
+
+    def _weights(self, dev):
+        if self._packed is None:
+            sd = {k: v.detach().to(dev) for k, v in self.state_dict().items()}
+            self._packed = _Packed(sd)
+        return self._packed
+
+    def _plan(self, b, h, w, dev):
+        key = (b, h, w, str(dev))
+        if key not in self._plans:
+            self._plans[key] = _Plan(b, h, w, dev)
+        return self._plans[key]
+
+    # -- encoders -----------------------------------------------------------------------------------
+    def _encoder(self, plan, ew, images, out_view, final_flags=0, h32=None):
+        """BasicEncoder (extractor.py:165-189) on ``images`` [n,3,H,W] fp32 -> out_view [n,H8,W8,256]."""
+        n = images.shape[0]
+        sc = plan.encoder_scratch(n, images.device)
+        inst = ew.norm == "instance"
+        relu = 0 if inst else L.F_RELU
+        h2, w2 = plan.h // 2, plan.w // 2
+
+        def norm_apply(x, y, resid=None, act=True):
+            ops.inorm_stats(x, sc["scratch"], 296, sc["stats"])
+            ops.inorm_apply(x, sc["stats"], y, resid=resid, relu=act)
+
+        ops.stem_im2col(images, sc["rows"])
+        r2 = sc["r2"]
+        ops.gemm_rows(L.ptr(sc["rows"]), 147, n * h2 * w2, 152, 1, L.ptr(ew.stem.wp), 64, ew.stem.wp.shape[1],
+                      L.ptr(r2[0]), 64, n_valid=64, bn=64, flags=relu, bias=ew.stem.bias)
+        x = View(r2[0])
+        if inst:
+            norm_apply(x, x)
+        pools = {64: sc["r2"], 96: sc["r4"], 128: sc["r8"]}
+        for blk in ew.blocks:
+            planes, st = blk["planes"], blk["stride"]
+            free = [t for t in pools[planes] if t is not x.t]
+            t1, t2, t3 = View(free[0]), View(free[1]), View(free[2])
+            m_tiles = n * math.ceil(t1.H / 8) * math.ceil(t1.W / 16)
+            bn = _pick_bn(planes, m_tiles)
+            c1, c2 = blk["conv1"], blk["conv2"]
+            ops.conv_tc(x, c1.wp, c1.bias, t1, cout=planes, taps=(3, 3), pad=(1, 1), stride=st, bn=bn, flags=relu)
+            if inst:
+                norm_apply(t1, t1)
+            if st != 1:
+                dn = blk["down"]
+                ops.conv_tc(x, dn.wp, dn.bias, t3, cout=planes, taps=(1, 1), pad=(0, 0), stride=st, bn=bn)
+                if inst:
+                    norm_apply(t3, t3, act=False)
+                skip = t3
+            else:
+                skip = x
+            if inst:
+                ops.conv_tc(t1, c2.wp, c2.bias, t2, cout=planes, taps=(3, 3), pad=(1, 1), bn=bn)
+                norm_apply(t2, t2, resid=skip)
+            else:   # y = relu(bn(conv)); out = relu(skip + y) fused in the epilogue
+                ops.conv_tc(t1, c2.wp, c2.bias, t2, cout=planes, taps=(3, 3), pad=(1, 1), bn=bn,
+                            flags=L.F_RELU | L.F_RESID, resid=skip)
+            x = t2
+        m_tiles = n * math.ceil(plan.h8 / 8) * math.ceil(plan.w8 / 16)
+        ops.conv_tc(x, ew.out.wp, ew.out.bias, out_view, cout=256, bn=128 if m_tiles * 2 >= 140 else 64,
+                    flags=final_flags, h32=h32)
+
+    # -- forward ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
+        """Estimate optical flow between a pair (or batch of pairs) of frames -- network.py:72-129."""
+        L.require_cuda(image1, image2)
+        dev = image1.device
+        L.check(L.load().atdn_check_device(dev.index if dev.index is not None else torch.cuda.current_device()),
+                "atdn_check_device")
+        b, _, h, w = image1.shape
+        image1 = image1.float().contiguous()
+        image2 = image2.float().contiguous()
+        wts = self._weights(dev)
+        plan = self._plan(b, h, w, dev)
+        h8, w8, n, np_ = plan.h8, plan.w8, plan.n, plan.np_
+        m_tiles = b * math.ceil(h8 / 8) * math.ceil(w8 / 16)
+
+        # feature network on both frames (batch of 2B, extractor.py:168-171), then the fp32-accumulated
+        # all-pairs correlation pyramid
+        fmap = getattr(plan, "fmap", None)
+        if fmap is None:
+            fmap = plan.fmap = torch.empty(2 * b, h8, w8, 256, dtype=torch.float16, device=dev)
+        self._encoder(plan, wts.fnet, torch.cat([image1, image2], 0), View(fmap))
+        ops.corr_pyramid_build(View(fmap[:b]), View(fmap[b:]), plan.pyr)
+
+        # context network: net = tanh(.) -> HX[0:128] + h32, inp = relu(.) -> HX[128:256]
+        hx = plan.hx
+        self._encoder(plan, wts.cnet, image1, View(hx, 0, 256), final_flags=L.F_TANH_LO, h32=plan.h32)
+
+        # attention (gma.py:54-76): q.k^T * scale -> softmax
+        ops.conv_tc(View(hx, 128, 128), wts.to_qk.wp, None, View(plan.qk), cout=256, bn=_pick_bn(256, m_tiles))
+        ops.gemm_rows(L.ptr(plan.qk), 128, n, 256, b, L.ptr(plan.qk, 128), n, 256, L.ptr(plan.s32), np_, n_valid=n,
+                      b_bstride=n * 256, bn=128, epi=L.EPI_STORE32, alpha=128 ** -0.5)
+        ops.softmax_rows(plan.s32, plan.p16, plan.inv_sum, b * n, n)
+
+        if flow_init is not None:
+            flow_init = flow_init.float().contiguous()
+        ops.coords_init(plan.coords1, plan.flow, flow_init)
+
+        preds = []
+        flow_up = flow_lo = None
+        for itr in range(iters):
+            need_up = (not test_mode) or itr == iters - 1
+            self._update(plan, wts, m_tiles)
+            if need_up:
+                c = wts.mask0
+                ops.conv_tc(View(hx, 0, 128), c.wp, c.bias, View(plan.mh), cout=256, taps=(3, 3), pad=(1, 1),
+                            bn=_pick_bn(256, m_tiles), flags=L.F_RELU)
+                c = wts.mask2
+                d_out = View(plan.mask32.view(b, h8, w8, 576))
+                ops.conv_tc(View(plan.mh), c.wp, c.bias, d_out, cout=576, bn=192, epi=L.EPI_STORE32, alpha=0.25)
+                flow_up = torch.empty(b, 2, h, w, dtype=torch.float32, device=dev)
+                flow_lo = torch.empty(b, 2, h8, w8, dtype=torch.float32, device=dev)
+                ops.convex_upsample(plan.mask32, plan.flow, flow_up, flow_lo)
+                preds.append(flow_up)
+        if test_mode:
+            return flow_lo, flow_up
+        return preds
+
+    def _update(self, plan, wts, m_tiles):
+        """One refinement iteration: lookup + GMAUpdateBlock (update.py:127-139) + coords update."""
+        b, h8, w8, n, np_ = plan.b, plan.h8, plan.w8, plan.n, plan.np_
+        hx = plan.hx
+        R = L.F_RELU
+        ops.corr_lookup(plan.pyr, plan.coords1, out16=View(plan.corrfeat))
+        c = wts.convc1
+        ops.conv_tc(View(plan.corrfeat, 0, 324), c.wp, c.bias, View(plan.c1), cout=256, bn=_pick_bn(256, m_tiles), flags=R)
+        c = wts.convc2
+        ops.conv_tc(View(plan.c1), c.wp, c.bias, View(plan.corflo, 0, 192), cout=192, taps=(3, 3), pad=(1, 1),
+                    bn=_pick_bn(192, m_tiles), flags=R)
+        ops.flow_im2col(plan.flow, plan.frows)
+        c = wts.convf1
+        ops.gemm_rows(L.ptr(plan.frows), 98, b * n, 104, 1, L.ptr(c.wp), 128, c.wp.shape[1], L.ptr(plan.f1), 128,
+                      n_valid=128, bn=_pick_bn(128, m_tiles), flags=R, bias=c.bias)
+        c = wts.convf2
+        ops.conv_tc(View(plan.f1), c.wp, c.bias, View(plan.corflo, 192, 64), cout=64, taps=(3, 3), pad=(1, 1), bn=64, flags=R)
+        c = wts.conv
+        ops.conv_tc(View(plan.corflo), c.wp, c.bias, View(hx, 256, 128), cout=128, taps=(3, 3), pad=(1, 1),
+                    bn=_pick_bn(128, m_tiles), flags=R | L.F_FLOWTAIL, aux32=plan.flow)
+        # aggregation: v^T = W_v . mf^T (stored [B,128,Np]); mfg = mf + gamma * (P . v) / rowsum
+        d = L.TcDesc()
+        d.bn, d.epi, d.flags, d.a_mode, d.b_mode = 128, L.EPI_STORE16, L.F_B_BATCHED | L.F_A_SHARED, L.MODE_ROWS, L.MODE_ROWS
+        d.a = L.ptr(wts.to_v)
+        L._set(d.a_dims, (128, 128, 1, 1))
+        L._set(d.a_strides, (128, 128 * 128, 128 * 128))
+        d.b = L.ptr(hx, 256)
+        L._set(d.b_dims, (128, n, 1, b))
+        L._set(d.b_strides, (512, n * 512, n * 512))
+        d.n_valid, d.alpha = n, 1.0
+        d.out, d.out_pitch = L.ptr(plan.vt), np_
+        L.tc_gemm(d)
+        ops.gemm_rows(L.ptr(plan.p16), n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
+                      b_bstride=128 * np_, bn=64, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
+                      aux32=plan.inv_sum, gamma=wts.gamma)
+        for (zr, q), taps, pad in ((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0))):
+            ops.conv_tc(View(hx), zr.wp, zr.bias, None, cout=256, taps=taps, pad=pad, bn=128, epi=L.EPI_GRU_ZR,
+                        h32=plan.h32, z32=plan.z32, rh16=plan.rh)
+            ops.conv_tc(View(plan.rh), q.wp, q.bias, View(hx, 0, 128), cout=128, taps=taps, pad=pad,
+                        bn=_pick_bn(128, m_tiles), epi=L.EPI_GRU_Q, a2=View(hx, 128, 384), h32=plan.h32, z32=plan.z32)
+        c = wts.fh1
+        ops.conv_tc(View(hx, 0, 128), c.wp, c.bias, View(plan.fh), cout=256, taps=(3, 3), pad=(1, 1),
+                    bn=_pick_bn(256, m_tiles), flags=R)
+        ops.flow_head_update(View(plan.fh), wts.fh2_w, wts.fh2_b, plan.coords1, plan.flow)
+
+
+class CorrBlock:
+    """Drop-in for ``GMA.whl!/GMA/core/corr.py:15-63``: ``CorrBlock(fmap1, fmap2, num_levels=4, radius=4)``
+    builds the pyramid on the tensor cores; ``corr_fn(coords) -> [B, 324, H8, W8]`` fp32."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        if num_levels != 4 or radius != 4:
+            raise NotImplementedError("the SLAM configuration is num_levels=4, radius=4 (network.py:33-34)")
+        L.require_cuda(fmap1, fmap2)
+        self.num_levels, self.radius = num_levels, radius
+        b, c, h, w = fmap1.shape
+        f1 = fmap1.permute(0, 2, 3, 1).contiguous().half()
+        f2 = fmap2.permute(0, 2, 3, 1).contiguous().half()
+        self.levels = ops.alloc_pyramid(b, h, w, fmap1.device)
+        ops.corr_pyramid_build(View(f1), View(f2), self.levels)
+        self.shape = (b, h, w)
+
+    @property
+    def corr_pyramid(self):
+        """The reference attribute: list of [B*N, 1, H_l, W_l] fp32 tensors."""
+        out = []
+        for t, (hl, wl, _) in zip(self.levels, ops.pyramid_shapes(self.shape[1], self.shape[2])):
+            out.append(t[:, :, :wl].unsqueeze(1))
+        return out
+
+    def __call__(self, coords):
+        b, h, w = self.shape
+        c = coords.float().permute(0, 2, 3, 1).contiguous()
+        out32 = torch.empty(b * h * w, 324, dtype=torch.float32, device=coords.device)
+        ops.corr_lookup(self.levels, c, out32=out32)
+        return out32.view(b, h, w, 324).permute(0, 3, 1, 2).contiguous()

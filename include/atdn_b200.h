@@ -73,7 +73,8 @@ enum {
   ATDN_F_RESID     = 2,  /* STORE16: y = relu(resid16[pix, n] + y)   (extractor.py:55)                     */
   ATDN_F_FLOWTAIL  = 4,  /* STORE16: columns n >= n_valid-2 take aux32[pix*2 + (n - (n_valid-2))] (update.py:84) */
   ATDN_F_TANH_LO   = 8,  /* STORE16: n < 128 -> tanh (also written to h32), n >= 128 -> relu (network.py:95-97) */
-  ATDN_F_B_BATCHED = 16  /* B operand has a batch dimension (attention GEMMs, corr volume)               */
+  ATDN_F_B_BATCHED = 16, /* B operand has a batch dimension (attention GEMMs, corr volume)               */
+  ATDN_F_A_SHARED  = 32  /* ROWS A is shared by all batches (weights as the A operand: transposed output); batch = b_dims[3] */
 };
 
 typedef struct atdn_tc_desc {

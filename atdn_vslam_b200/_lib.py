@@ -41,8 +41,9 @@ class TcDesc(C.Structure):
 class Conv32Desc(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("y", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
-        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("skip", C.c_void_p),
-        ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p),
+        ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p), ("skip", C.c_void_p),
+        ("bn2_scale", C.c_void_p), ("bn2_shift", C.c_void_p),
         ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
         ("k", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("mish", C.c_int32),
     ]

@@ -20,7 +20,7 @@ __device__ __forceinline__ float mishf(float x) {
 constexpr int kCoT = 16, kCiT = 4, kTile = 16;
 
 struct Conv32Params {
-  const float *x, *w, *bias, *in_scale, *in_shift, *skip, *bn_scale, *bn_shift;
+  const float *x, *w, *bias, *in_scale, *in_shift, *skip, *bn_scale, *bn_shift, *bn2_scale, *bn2_shift;
   float* y;
   int B, Cin, Cout, H, W, OH, OW, K, stride, pad, mish, tiles_x, in_tile;
 };
@@ -87,9 +87,12 @@ __global__ void __launch_bounds__(256) conv32_kernel(Conv32Params p) {
     if (co >= p.Cout) break;
     const long long o = ((static_cast<long long>(b) * p.Cout + co) * p.OH + oy) * p.OW + ox;
     float v = acc[i] + (p.bias ? __ldg(p.bias + co) : 0.0f);
-    if (p.skip) v += p.skip[o];
     if (p.mish) v = mishf(v);
     if (p.bn_scale) v = v * __ldg(p.bn_scale + co) + __ldg(p.bn_shift + co);
+    if (p.skip) {
+      v = mishf(v + p.skip[o]);
+      if (p.bn2_scale) v = v * __ldg(p.bn2_scale + co) + __ldg(p.bn2_shift + co);
+    }
     p.y[o] = v;
   }
 }
@@ -211,11 +214,12 @@ extern "C" int atdn_conv32(const atdn_conv32_desc* d, void* stream) {
   if (int e = require_sm100()) return e;
   ATDN_REQUIRE(d && d->x && d->y && d->w, ATDN_ERR_ARG, "atdn_conv32: null argument");
   ATDN_REQUIRE(d->k >= 1 && d->k <= 7 && d->stride >= 1 && d->stride <= 3, ATDN_ERR_UNSUP, "atdn_conv32: k=%d stride=%d", d->k, d->stride);
-  ATDN_REQUIRE((d->in_scale == nullptr) == (d->in_shift == nullptr) && (d->bn_scale == nullptr) == (d->bn_shift == nullptr), ATDN_ERR_ARG,
+  ATDN_REQUIRE((d->in_scale == nullptr) == (d->in_shift == nullptr) && (d->bn_scale == nullptr) == (d->bn_shift == nullptr) &&
+                   (d->bn2_scale == nullptr) == (d->bn2_shift == nullptr), ATDN_ERR_ARG,
                "atdn_conv32: scale/shift must come in pairs");
   Conv32Params p;
   p.x = d->x; p.w = d->w; p.bias = d->bias; p.in_scale = d->in_scale; p.in_shift = d->in_shift; p.skip = d->skip;
-  p.bn_scale = d->bn_scale; p.bn_shift = d->bn_shift; p.y = d->y;
+  p.bn_scale = d->bn_scale; p.bn_shift = d->bn_shift; p.bn2_scale = d->bn2_scale; p.bn2_shift = d->bn2_shift; p.y = d->y;
   p.B = d->batch; p.Cin = d->cin; p.Cout = d->cout; p.H = d->in_h; p.W = d->in_w; p.K = d->k; p.stride = d->stride;
   p.pad = d->pad; p.mish = d->mish;
   p.OH = (d->in_h + 2 * d->pad - d->k) / d->stride + 1;

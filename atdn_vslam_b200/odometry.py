@@ -1,0 +1,209 @@
+"""Drop-in for the reference CLVO pose network (``atdn_vslam/odometry/network.py:11-162``).
+
+``ATDNVO(batch_size=1, in_channels=2, compressor=True, use_dropout=False, use_layernorm=False)``,
+``.forward(flows) -> (rot [B,3], tr [B,3])``, ``.reset_lstm()``, ``.to(device)`` (resets the LSTM
+state and returns self) and the externally read attributes ``suffix``, ``batch_size``, ``device``,
+``lstm{1,2}_{h,c}`` keep the reference semantics; the reference state dict (127 tensors, including
+the unused ``polar_norm``) loads unchanged.  The whole network runs in fp32 CUDA-core kernels:
+16-channel maps are memory-bound, and the 1e-4 relative pose tolerance leaves no room for fp16.
+
+Two extra entry points serve the multi-GPU path: ``encode(flows)`` is the
+stateless CNN (pair-parallel, -> [B,512]) and ``recurrent_scan(features)`` runs the LSTM + heads
+serially over a gathered [T,512] feature sequence.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops, schema
+from .gma import _build_module_tree
+
+FLOW_STD = (58.1837, 17.7647)   # atdn_vslam/utils/normalizations.py:8-10
+
+
+def _bn_affine(sd, name):
+    s = sd[name + ".weight"].float() / torch.sqrt(sd[name + ".running_var"].float() + 1e-5)
+    return s.contiguous(), (sd[name + ".bias"].float() - sd[name + ".running_mean"].float() * s).contiguous()
+
+
+class _ConvBlock:
+    """layers/conv.py:36-37: bn(mish(conv(x)))."""
+
+    def __init__(self, sd, p):
+        self.w = sd[p + "conv.weight"].float().contiguous()
+        self.b = sd[p + "conv.bias"].float().contiguous()
+        self.bn_s, self.bn_b = _bn_affine(sd, p + "bn")
+
+
+class _ResidualBlock:
+    """layers/conv.py:83-90."""
+
+    def __init__(self, sd, p):
+        self.c0 = _ConvBlock(sd, p + "conv.0.")
+        self.c1 = _ConvBlock(sd, p + "conv.1.")
+        self.skip_w = sd[p + "skip_layer.weight"].float().contiguous()
+        self.skip_b = sd[p + "skip_layer.bias"].float().contiguous()
+        self.bn_s, self.bn_b = _bn_affine(sd, p + "out_block.1")
+
+
+def conv_out(n, k, s, p):
+    return (n + 2 * p - k) // s + 1
+
+
+def run_conv_block(x, blk, stride, pad, in_scale=None, in_shift=None, skip=None, bn2=None):
+    b, _, h, w = x.shape
+    k = blk.w.shape[2]
+    y = torch.empty(b, blk.w.shape[0], conv_out(h, k, stride, pad), conv_out(w, k, stride, pad),
+                    dtype=torch.float32, device=x.device)
+    ops.conv32(x, blk.w, blk.b, y, stride=stride, pad=pad, mish=True, in_scale=in_scale, in_shift=in_shift,
+               bn_scale=blk.bn_s, bn_shift=blk.bn_b, skip=skip, bn2_scale=bn2[0] if bn2 else None,
+               bn2_shift=bn2[1] if bn2 else None)
+    return y
+
+
+def run_residual_block(x, blk, stride):
+    """bn(mish(conv.1(conv.0(x)) + skip_layer(x))) with conv.i = bn(mish(conv)) -- layers/conv.py:83-90."""
+    y = run_conv_block(x, blk.c0, 1, 1)
+    b, _, h, w = x.shape
+    skip = torch.empty(b, blk.skip_w.shape[0], conv_out(h, 1, stride, 0), conv_out(w, 1, stride, 0),
+                       dtype=torch.float32, device=x.device)
+    ops.conv32(x, blk.skip_w, blk.skip_b, skip, stride=stride, pad=0)
+    return run_conv_block(y, blk.c1, stride, 1, skip=skip, bn2=(blk.bn_s, blk.bn_b))
+
+
+class _Packed:
+    def __init__(self, sd, dev):
+        sd = {k: v.detach().to(dev) for k, v in sd.items()}
+        std = torch.tensor(FLOW_STD, dtype=torch.float32, device=dev)
+        # flow / std (network.py:131) then the depthwise 1x1 encoder_CNN.0 (groups=2): one affine per channel,
+        # applied to in-bounds inputs only (the 7x7 conv zero-pads AFTER both)
+        dw = sd["encoder_CNN.0.weight"].float().view(2)
+        self.in_scale = (dw / std).contiguous()
+        self.in_shift = sd["encoder_CNN.0.bias"].float().contiguous()
+        self.stem = _ConvBlock(sd, "encoder_CNN.1.")
+        self.res = [_ResidualBlock(sd, f"encoder_CNN.{i}.") for i in range(2, 6)]
+        self.tail = _ConvBlock(sd, "encoder_CNN.6.")
+        g = lambda n: sd[n].float().contiguous()
+        self.fc_w, self.fc_b = g("encoder_CNN.8.linear.weight"), g("encoder_CNN.8.linear.bias")
+        self.lstm = [tuple(g(f"{n}.{k}") for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")) for n in ("lstm1", "lstm2")]
+        self.ll_w, self.ll_b = g("lstm_linear.linear.weight"), g("lstm_linear.linear.bias")
+        self.heads = {}
+        for h in ("rotation_regressor", "translation_regressor"):
+            self.heads[h] = (g(h + ".0.linear.weight"), g(h + ".0.linear.bias"), g(h + ".1.linear.weight"),
+                             g(h + ".1.linear.bias"), g(h + ".2.weight"))
+
+
+class ATDNVO(nn.Module):
+    def __init__(self, batch_size: int = 1, in_channels: int = 2, compressor=True, use_dropout=False, use_layernorm=False):
+        super().__init__()
+        if not compressor or in_channels != 2 or use_layernorm:
+            raise NotImplementedError("only the configuration the SLAM loads is built: compressor=True, in_channels=2, "
+                                      "use_layernorm=False (atdn_vslam/slam_framework/neural_slam.py:57)")
+        self.batch_size = batch_size
+        self.in_channels = in_channels
+        self.device = "cpu"
+        self.suffix = "_c" + ("d" if use_dropout else "")     # network.py:52-60; dropout is inactive in eval
+        self.lstm_out_size = 512
+        _build_module_tree(self, schema.atdnvo_schema())
+        self._packed = None
+        self.reset_lstm()
+
+    # -- state ------------------------------------------------------------------------------------------
+    def reset_lstm(self):
+        """network.py:149-153"""
+        z = lambda: torch.zeros(self.batch_size, self.lstm_out_size, device=self.device)
+        self.lstm1_h, self.lstm1_c, self.lstm2_h, self.lstm2_c = z(), z(), z(), z()
+
+    def to(self, device):
+        """network.py:156-162: moves the parameters, resets the LSTM state, returns self."""
+        super().to(device)
+        self.device = device
+        self._packed = None
+        self.reset_lstm()
+        return self
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._packed = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _weights(self, dev):
+        if self._packed is None:
+            self._packed = _Packed(self.state_dict(), dev)
+        return self._packed
+
+    # -- compute ----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, flows):
+        """network.py:131-134: normalise -> CNN -> [B,512] feature (stateless, pair-parallel)."""
+        L.require_cuda(flows)
+        p = self._weights(flows.device)
+        x = flows.float().contiguous()
+        x = run_conv_block(x, p.stem, 2, 3, in_scale=p.in_scale, in_shift=p.in_shift)
+        for blk in p.res:
+            x = run_residual_block(x, blk, 2)
+        x = run_conv_block(x, p.tail, 3, 0)
+        x = x.flatten(1).contiguous()
+        feat = torch.empty(x.shape[0], 512, dtype=torch.float32, device=x.device)
+        ops.linear32(x, p.fc_w, p.fc_b, feat, act=1)
+        return feat
+
+    def _step(self, p, feat, state, gates, tmp):
+        h1, c1, h2, c2 = state
+        ops.lstm_cell(feat, *p.lstm[0], h1, c1, gates)
+        ops.linear32(h1, p.ll_w, p.ll_b, tmp["x2"], act=1)
+        ops.lstm_cell(tmp["x2"], *p.lstm[1], h2, c2, gates)
+        outs = []
+        for h in ("rotation_regressor", "translation_regressor"):
+            w0, b0, w1, b1, w2 = p.heads[h]
+            ops.linear32(h2, w0, b0, tmp["a"], act=1)
+            ops.linear32(tmp["a"], w1, b1, tmp["b"], act=1)
+            o = torch.empty(feat.shape[0], 3, dtype=torch.float32, device=feat.device)
+            ops.linear32(tmp["b"], w2, None, o, act=0)
+            outs.append(o)
+        return outs
+
+    @staticmethod
+    def _tmp(b, dev):
+        f = lambda n: torch.empty(b, n, dtype=torch.float32, device=dev)
+        return f(2048), {"x2": f(512), "a": f(128), "b": f(64)}
+
+    @torch.no_grad()
+    def forward(self, flows: torch.Tensor):
+        """network.py:122-146 (the LSTM state persists across calls exactly like the reference)."""
+        feat = self.encode(flows)
+        p = self._weights(flows.device)
+        b = feat.shape[0]
+        state = []
+        for name in ("lstm1_h", "lstm1_c", "lstm2_h", "lstm2_c"):
+            t = getattr(self, name)
+            if t.device != feat.device or t.shape[0] != b:
+                t = t.to(feat.device).expand(b, -1) if t.shape[0] == 1 else t.to(feat.device)
+            state.append(t.contiguous().clone())     # LSTMCell returns new tensors; never alias the caller's
+        gates, tmp = self._tmp(b, feat.device)
+        rot, tr = self._step(p, feat, state, gates, tmp)
+        self.lstm1_h, self.lstm1_c, self.lstm2_h, self.lstm2_c = state
+        return rot, tr
+
+    @torch.no_grad()
+    def recurrent_scan(self, features):
+        """Serial LSTM + heads over a [T,512] (or [T,B,512]) feature sequence, continuing from and
+        updating the module state -> (rot [T,(B,)3], tr [T,(B,)3]).  Equivalent to T forward calls."""
+        L.require_cuda(features)
+        p = self._weights(features.device)
+        squeeze = features.dim() == 2
+        f = features.unsqueeze(1) if squeeze else features
+        t_steps, b = f.shape[0], f.shape[1]
+        state = [getattr(self, n).to(f.device).expand(b, -1).contiguous().clone()
+                 for n in ("lstm1_h", "lstm1_c", "lstm2_h", "lstm2_c")]
+        gates, tmp = self._tmp(b, f.device)
+        rots, trs = [], []
+        f = f.contiguous()
+        for t in range(t_steps):
+            r, tr = self._step(p, f[t], state, gates, tmp)
+            rots.append(r)
+            trs.append(tr)
+        self.lstm1_h, self.lstm1_c, self.lstm2_h, self.lstm2_c = state
+        rot, tr = torch.stack(rots), torch.stack(trs)
+        return (rot[:, 0], tr[:, 0]) if squeeze else (rot, tr)

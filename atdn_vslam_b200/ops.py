@@ -232,13 +232,14 @@ def coords_init(coords1, flow, flow_init=None):
 # fp32 small nets
 # ----------------------------------------------------------------------------------------------
 def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shift=None, skip=None, bn_scale=None,
-           bn_shift=None):
+           bn_shift=None, bn2_scale=None, bn2_shift=None):
     d = L.Conv32Desc()
     b, cin, h, wd = x.shape
     cout, _, k, _ = w.shape
     d.x, d.y, d.w, d.bias = L.ptr(x), L.ptr(y), L.ptr(w), L.ptr(bias)
     d.in_scale, d.in_shift, d.skip = L.ptr(in_scale), L.ptr(in_shift), L.ptr(skip)
     d.bn_scale, d.bn_shift = L.ptr(bn_scale), L.ptr(bn_shift)
+    d.bn2_scale, d.bn2_shift = L.ptr(bn2_scale), L.ptr(bn2_shift)
     d.batch, d.cin, d.cout, d.in_h, d.in_w, d.k, d.stride, d.pad, d.mish = b, cin, cout, h, wd, k, stride, pad, int(mish)
     L.check(L.load().atdn_conv32(C.byref(d), L.stream_ptr()), "atdn_conv32")
 

@@ -161,18 +161,20 @@ int atdn_coords_init(float* coords1, float* flow, const float* flow_init_or_null
  * atdn_vslam/layers/conv.py:36-37 (Conv = bn(mish(conv))), :83-90 (ResidualConv),
  * atdn_vslam/odometry/network.py:63-73,131-134, atdn_vslam/localization/network.py:29-45,57-72.
  *
- * y = post( conv(pre(x)) + bias (+ skip) ),  NCHW fp32.
- *   pre : x * in_scale[c] + in_shift[c] applied to in-bounds inputs (flow/RGB normalisation and the
- *         depthwise 1x1 of encoder_CNN.0), or NULL
- *   post: mish then affine bn (scale/shift per channel), each optional.
+ * y = post2( post( conv(pre(x)) + bias ) ),  NCHW fp32.
+ *   pre  : x * in_scale[c] + in_shift[c] applied to in-bounds inputs (flow/RGB normalisation and the
+ *          depthwise 1x1 of encoder_CNN.0), or NULL
+ *   post : mish then affine bn (scale/shift per channel), each optional            (Conv block)
+ *   post2: when skip != NULL: v = bn2(mish(v + skip))                               (ResidualConv tail)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct atdn_conv32_desc {
   const float* x; float* y;
   const float* w;         /* [cout, cin, k, k] (PyTorch layout)                                    */
   const float* bias;      /* [cout] or NULL                                                         */
   const float* in_scale;  const float* in_shift;   /* [cin] or NULL                                 */
-  const float* skip;      /* [B, cout, oh, ow] added before the activation, or NULL                 */
   const float* bn_scale;  const float* bn_shift;   /* [cout] folded eval-mode batch norm, or NULL   */
+  const float* skip;      /* [B, cout, oh, ow] or NULL: enables post2                               */
+  const float* bn2_scale; const float* bn2_shift;  /* [cout] batch norm of post2, or NULL           */
   int32_t batch, cin, cout, in_h, in_w, k, stride, pad, mish;
 } atdn_conv32_desc;
 int atdn_conv32(const atdn_conv32_desc* desc, void* stream);

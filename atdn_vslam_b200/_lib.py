@@ -72,7 +72,13 @@ def load():
     return lib
 
 
-def check(code, what):
+LAUNCHES = 0          # kernels launched through the C ABI by this process (bench.py reports it)
+PROFILER = None       # optional callable(label, flops, bytes) -> context manager, installed by bench.py
+
+
+def check(code, what, launches=1):
+    global LAUNCHES
+    LAUNCHES += launches
     if code != 0:
         raise RuntimeError(f"{what} failed with code {code}: {load().atdn_last_error().decode(errors='replace')}")
 
@@ -93,7 +99,26 @@ def require_cuda(*tensors):
             raise RuntimeError("atdn_vslam_b200 kernels need CUDA tensors on an sm_100 device (no CPU fallback)")
 
 
+def tc_label(d: TcDesc):
+    """(label, flops) of one tensor-core launch, derived from its descriptor (profiling only)."""
+    if d.a_mode == MODE_PATCH:
+        cin = d.a_dims[0] + (d.a2_dims[0] if d.a_split_chunk else 0)
+        flops = 2.0 * d.out_h * d.out_w * d.a_dims[3] * d.n_valid * d.taps_h * d.taps_w * cin
+        name = {EPI_GRU_ZR: "gru_zr", EPI_GRU_Q: "gru_q"}.get(d.epi, f"conv{d.taps_h}x{d.taps_w}_{cin}to{d.n_valid}_s{d.stride}")
+    else:
+        batch = d.b_dims[3] if (d.flags & F_A_SHARED) else d.a_dims[3]
+        flops = 2.0 * d.a_dims[1] * d.n_valid * d.a_dims[0] * batch
+        name = {EPI_CORR: "corr_gemm", EPI_PV: "attn_pv", EPI_STORE32: "attn_qk"}.get(
+            d.epi, "to_v" if (d.flags & F_A_SHARED) else f"rows_k{d.a_dims[0]}to{d.n_valid}")
+    return name, flops
+
+
 def tc_gemm(desc: TcDesc):
+    if PROFILER is not None:
+        name, flops = tc_label(desc)
+        with PROFILER(name, flops, 0.0):
+            check(load().atdn_tc_gemm(C.byref(desc), stream_ptr()), "atdn_tc_gemm")
+        return
     check(load().atdn_tc_gemm(C.byref(desc), stream_ptr()), "atdn_tc_gemm")
 
 

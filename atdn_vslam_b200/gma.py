@@ -183,6 +183,13 @@ class _Plan:
         self.mh = f16(b, h8, w8, 256)
         self.mask32 = f32(b * n, 576)
 
+    def buffer(self, name, shape, dtype):
+        t = self.__dict__.get("_buf_" + name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(*shape, dtype=dtype, device=self.hx.device)
+            self.__dict__["_buf_" + name] = t
+        return t
+
     def encoder_scratch(self, nimg, dev):
         if nimg not in self.enc:
             f16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
@@ -307,16 +314,34 @@ class RAFTGMA(nn.Module):
         image2 = image2.float().contiguous()
         wts = self._weights(dev)
         plan = self._plan(b, h, w, dev)
+        # feature network on both frames as one batch of 2B (extractor.py:168-171)
+        fmap = plan.buffer("fmap", (2 * b, plan.h8, plan.w8, 256), torch.float16)
+        self._encoder(plan, wts.fnet, torch.cat([image1, image2], 0), View(fmap))
+        return self._flow(plan, wts, image1, View(fmap[:b]), View(fmap[b:]), iters, flow_init, test_mode)
+
+    @torch.no_grad()
+    def forward_frames(self, frames, iters=12, test_mode=True):
+        """Flow for the B consecutive pairs (t, t+1) of ``frames`` [B+1,3,H,W]: the feature network
+        runs once per FRAME (instance norm is per image, so the result equals B separate ``forward``
+        calls) and fmap[t+1] doubles as fmap2 of pair t and fmap1 of pair t+1."""
+        L.require_cuda(frames)
+        dev = frames.device
+        nb, _, h, w = frames.shape
+        b = nb - 1
+        frames = frames.float().contiguous()
+        wts = self._weights(dev)
+        plan = self._plan(b, h, w, dev)
+        fmap = plan.buffer("fmap_seq", (nb, plan.h8, plan.w8, 256), torch.float16)
+        self._encoder(plan, wts.fnet, frames, View(fmap))
+        return self._flow(plan, wts, frames[:b], View(fmap[:b]), View(fmap[1:]), iters, None, test_mode)
+
+    def _flow(self, plan, wts, image1, fmap1, fmap2, iters, flow_init, test_mode):
+        dev = image1.device
+        b, h, w = plan.b, plan.h, plan.w
         h8, w8, n, np_ = plan.h8, plan.w8, plan.n, plan.np_
         m_tiles = b * math.ceil(h8 / 8) * math.ceil(w8 / 16)
-
-        # feature network on both frames (batch of 2B, extractor.py:168-171), then the fp32-accumulated
-        # all-pairs correlation pyramid
-        fmap = getattr(plan, "fmap", None)
-        if fmap is None:
-            fmap = plan.fmap = torch.empty(2 * b, h8, w8, 256, dtype=torch.float16, device=dev)
-        self._encoder(plan, wts.fnet, torch.cat([image1, image2], 0), View(fmap))
-        ops.corr_pyramid_build(View(fmap[:b]), View(fmap[b:]), plan.pyr)
+        # fp32-accumulated all-pairs correlation pyramid (corr.py:16-30)
+        ops.corr_pyramid_build(fmap1, fmap2, plan.pyr)
 
         # context network: net = tanh(.) -> HX[0:128] + h32, inp = relu(.) -> HX[128:256]
         hx = plan.hx

@@ -174,6 +174,15 @@ def corr_lookup(levels, coords, out16=None, out32=None):
     b, h8, w8, _ = coords.shape
     lv = (C.c_void_p * 4)(*[t.data_ptr() for t in levels])
     lp = (C.c_int32 * 4)(*[t.shape[2] for t in levels])
+    if L.PROFILER is not None:
+        # algorithmic bytes: <= 4 levels x 10x10 texels x 4 B read + coords + 324 outputs written per query
+        q = b * h8 * w8
+        nbytes = q * (4 * 100 * 4 + 8 + 324 * (2 if out16 is not None else 4))
+        with L.PROFILER("corr_lookup", 0.0, float(nbytes)):
+            L.check(L.load().atdn_corr_lookup(lv, lp, L.ptr(coords), out16.ptr() if out16 is not None else None,
+                                              C.c_int64(out16.pitch if out16 is not None else 0), L.ptr(out32),
+                                              b, h8, w8, L.stream_ptr()), "atdn_corr_lookup")
+        return
     L.check(L.load().atdn_corr_lookup(lv, lp, L.ptr(coords), out16.ptr() if out16 is not None else None,
                                       C.c_int64(out16.pitch if out16 is not None else 0), L.ptr(out32),
                                       b, h8, w8, L.stream_ptr()), "atdn_corr_lookup")
@@ -196,7 +205,7 @@ def flow_im2col(flow, rows):
 
 def inorm_stats(x, scratch, parts, stats):
     L.check(L.load().atdn_inorm_stats(x.ptr(), C.c_int64(x.pitch), x.B, x.H * x.W, x.c, L.ptr(scratch), parts,
-                                      L.ptr(stats), L.stream_ptr()), "atdn_inorm_stats")
+                                      L.ptr(stats), L.stream_ptr()), "atdn_inorm_stats", 2)
 
 
 def inorm_apply(x, stats, y, resid=None, relu=True):
@@ -251,9 +260,9 @@ def linear32(x, w, bias, y, act=0):
 
 def lstm_cell(x, w_ih, w_hh, b_ih, b_hh, h, c, gates):
     L.check(L.load().atdn_lstm_cell(L.ptr(x), L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih), L.ptr(b_hh), L.ptr(h), L.ptr(c),
-                                    L.ptr(gates), x.shape[0], w_ih.shape[1], h.shape[1], L.stream_ptr()), "atdn_lstm_cell")
+                                    L.ptr(gates), x.shape[0], w_ih.shape[1], h.shape[1], L.stream_ptr()), "atdn_lstm_cell", 2)
 
 
 def keyframe_search(emb, code, dist, index):
     L.check(L.load().atdn_keyframe_search(L.ptr(emb), L.ptr(code), L.ptr(dist), L.ptr(index), C.c_int64(emb.shape[0]),
-                                          emb.shape[1], L.stream_ptr()), "atdn_keyframe_search")
+                                          emb.shape[1], L.stream_ptr()), "atdn_keyframe_search", 2)

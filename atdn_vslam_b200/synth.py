@@ -75,7 +75,7 @@ def state_dict_digest(sd):
     for k in sorted(sd):
         v = sd[k]
         if v.is_floating_point():
-            h.update(k.encode())
+            h.update((k[7:] if k.startswith("module.") else k).encode())
             h.update(v.detach().cpu().float().contiguous().numpy().tobytes())
     return h.hexdigest()
 

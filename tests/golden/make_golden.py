@@ -89,7 +89,7 @@ def main():
     assert err(up, o_up) < 5e-3
     np.savez_compressed(os.path.join(OUT, "gma_full.npz"), digest=np.array(synth.state_dict_digest(gsd)),
                         flow_lo=lo.numpy(), flow_up_s4=up[:, :, ::4, ::4].numpy().astype(np.float32),
-                        frame_sum=np.array([float(frames[0].sum()), float(frames[1].sum())]))
+                        frame_sum=np.array([float(frames[0].double().sum()), float(frames[1].double().sum())]))
 
     # ---- ATDNVO: 3 consecutive calls (stateful LSTM) ---------------------------------------------
     vsd = synth.atdnvo_state_dict()

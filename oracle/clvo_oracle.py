@@ -94,9 +94,10 @@ def atdnvo_forward(sd, flows, state):
 # pose assembly -- utils/transforms.py:25-51, 54-94, 97-119; slam_framework/neural_slam.py:288-302
 # ----------------------------------------------------------------------------------------------
 def euler2matrix(r):
-    """'yxz' convention, utils/transforms.py:68-81 (fp32 like the reference)."""
-    c1, c2, c3 = (math.cos(float(v)) for v in r)
-    s1, s2, s3 = (math.sin(float(v)) for v in r)
+    """'yxz' convention, utils/transforms.py:68-81: fp32 torch trig, products formed in fp32."""
+    r = r.detach().float()
+    c1, c2, c3 = torch.cos(r[0]), torch.cos(r[1]), torch.cos(r[2])
+    s1, s2, s3 = torch.sin(r[0]), torch.sin(r[1]), torch.sin(r[2])
     return torch.tensor([[c1 * c3 + s1 * s2 * s3, c3 * s1 * s2 - c1 * s3, c2 * s1],
                          [c2 * s3, c2 * c3, -s2],
                          [c1 * s2 * s3 - c3 * s1, c1 * c3 * s2 + s1 * s3, c1 * c2]], dtype=torch.float32)
@@ -107,7 +108,7 @@ def matrix2euler(R):
     a = torch.atan2(R[0, 2], R[2, 2])
     b = torch.atan2(-R[1, 2], torch.sqrt(1 - R[1, 2] ** 2))
     g = torch.atan2(R[1, 0], R[1, 1])
-    return torch.stack([a, b, g])
+    return torch.tensor([a, b, g])
 
 
 def transform(rot, tr):

@@ -111,8 +111,8 @@ def main():
                         flow_seed=np.array(3))
     # pose assembly
     m = ref_transform(rots[0].squeeze(), trs[0].squeeze())
-    assert err(m, clvo_oracle.transform(rots[0].squeeze(), trs[0].squeeze())) < 1e-6
-    assert err(ref_m2e(m[:3, :3]), clvo_oracle.matrix2euler(m[:3, :3])) < 1e-6
+    assert torch.equal(m, clvo_oracle.transform(rots[0].squeeze(), trs[0].squeeze()))
+    assert torch.equal(ref_m2e(m[:3, :3]), clvo_oracle.matrix2euler(m[:3, :3]))
 
     # ---- MappingVAE encoder -----------------------------------------------------------------------
     esd = synth.vae_state_dict()

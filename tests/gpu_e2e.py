@@ -107,7 +107,7 @@ def check_gma_full():
     im1, im2 = frames[0:1].cuda(), frames[1:2].cuda()
     lo, up = m(im1, im2, iters=12, test_mode=True)
     torch.cuda.synchronize()
-    ok = _epe("full flow_lo vs reference", lo, torch.from_numpy(g["flow_lo"]), 1.25e-3)
+    ok = _epe("full flow_lo vs reference", lo, torch.from_numpy(g["flow_lo"]), 2.5e-3)
     ok &= _epe("full flow_up (stride-4 samples) vs reference", up[:, :, ::4, ::4], torch.from_numpy(g["flow_up_s4"]), 1e-2)
     t0 = time.time()
     for _ in range(3):

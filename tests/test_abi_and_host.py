@@ -1,0 +1,140 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/atdn_b200.h declares,
+descriptor structs match the header, the drop-in modules accept the reference state dicts, packing
+and the host pose / sharding logic behave (no compute kernels are called here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from atdn_vslam_b200 import _lib as L
+from atdn_vslam_b200 import ops, schema, synth
+from atdn_vslam_b200.poses import PoseChain, transform
+from atdn_vslam_b200.sequence import shard_ranges
+from atdn_vslam_b200.localization import merge_shard_minima
+from oracle import clvo_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Args:
+    mixed_precision, num_heads, position_only, position_and_content = True, 1, False, False
+
+    def __contains__(self, k):
+        return hasattr(self, k)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "atdn_b200.h")).read()
+    declared = set(re.findall(r"\b(atdn_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.atdn_version() == 100
+
+
+def test_struct_layouts_match_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "atdn_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
+                   'sizeof(atdn_tc_desc), offsetof(atdn_tc_desc, corr_w), sizeof(atdn_conv32_desc), offsetof(atdn_conv32_desc, mish));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    a, b, c, d = map(int, subprocess.check_output([str(exe)]).split())
+    assert (a, b) == (C.sizeof(L.TcDesc), L.TcDesc.corr_w.offset)
+    assert (c, d) == (C.sizeof(L.Conv32Desc), L.Conv32Desc.mish.offset)
+
+
+def test_no_cpu_fallback():
+    from atdn_vslam_b200.gma import RAFTGMA
+    m = RAFTGMA(Args())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 128, 160), torch.zeros(1, 3, 128, 160), iters=1, test_mode=True)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "atdn_vslam_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            txt = open(os.path.join(pkg, f)).read()
+            assert "oracle" not in re.sub(r"#.*", "", txt).replace("oracle port", ""), f
+
+
+def test_reference_state_dicts_load_unchanged():
+    from atdn_vslam_b200.gma import RAFTGMA
+    from atdn_vslam_b200.odometry import ATDNVO
+    from atdn_vslam_b200.localization import MappingEncoder
+    g = RAFTGMA(Args())
+    assert len(g.state_dict()) == 185
+    assert g.load_state_dict(synth.gma_state_dict(module_prefix=True)).missing_keys == []
+    assert g.load_state_dict(synth.gma_state_dict()).unexpected_keys == []
+    assert g.args.corr_levels == 4 and g.args.corr_radius == 4 and g.args.dropout == 0
+    vo = ATDNVO()
+    assert len(vo.state_dict()) == 127 and sum(p.numel() for p in vo.parameters()) > 5_000_000
+    vo.load_state_dict(synth.atdnvo_state_dict())
+    assert vo.suffix == "_c" and vo.batch_size == 1 and tuple(vo.lstm1_h.shape) == (1, 512)
+    enc = MappingEncoder()
+    sd = dict(synth.vae_state_dict())
+    sd["decoder.0.skip_layer.weight"] = torch.zeros(128, 128, 1, 1)     # decoder tensors are ignored
+    enc.load_state_dict(sd)
+
+
+def test_weight_packing_layout():
+    w = torch.arange(2 * 3 * 1 * 5, dtype=torch.float32).reshape(2, 3, 1, 5)
+    wp = ops.pack_conv_weight(w)
+    assert tuple(wp.shape) == (2, 5 * 64)
+    # K index = tap * 64 + channel
+    assert wp[1, 2 * 64 + 1] == w[1, 1, 0, 2] and wp[0, 3] == 0
+    assert tuple(ops.pack_rows_weight(torch.ones(4, 147)).shape) == (4, 192)
+    assert ops.pad_bias(torch.ones(126)).numel() == 128
+    assert ops.pyramid_shapes(47, 154) == [(47, 154, 156), (23, 77, 80), (11, 38, 40), (5, 19, 20)]
+
+
+def test_pose_chain_matches_oracle():
+    g = torch.Generator().manual_seed(0)
+    rots = torch.randn(40, 3, generator=g) * 0.03
+    trs = torch.randn(40, 3, generator=g) * 2.0
+    poses, keys = PoseChain().extend(rots, trs)
+    o_poses, o_keys = clvo_oracle.chain_and_keyframes(rots, trs)
+    assert keys == o_keys and len(keys) > 2
+    assert torch.equal(poses, o_poses)
+    assert torch.equal(transform(rots[0], trs[0]), clvo_oracle.transform(rots[0], trs[0]))
+
+
+def test_shard_ranges_and_minima_merge():
+    assert shard_ranges(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard_ranges(4540, 8)[-1][1] == 4540
+    assert merge_shard_minima([(2.0, 7), (1.0, 20), (1.0, 12), (float("inf"), -1)]) == (12, 1.0)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from atdn_vslam_b200.sequence import gather_features, shard_ranges
+    total = 7
+    s, e = shard_ranges(total, world)[rank]
+    local = torch.arange(s, e, dtype=torch.float32).view(-1, 1).repeat(1, 4)
+    full = gather_features(local, total)
+    q.put((rank, full[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_feature_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, vals in res:
+        assert vals == [float(i) for i in range(7)]

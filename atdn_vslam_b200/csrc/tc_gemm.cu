@@ -280,6 +280,9 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const bool dbg = (p.flags & 512) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+  long long* dbuf = reinterpret_cast<long long*>(p.lvl[2]);
+  if (dbg && threadIdx.x == 0) dbuf[0] = clock64();
 
   const int chunks = p.chunks_a + p.chunks_a2;
 
@@ -288,16 +291,22 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int chunk = 0, dx = 0, dy = 0;
       for (int it = 0; it < p.num_k_iters; ++it) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (dbg && it < 48) dbuf[8 + it] = clock64();
+        if (p.flags & ATDN_F_DEBUG_NO_TMA) {          // timing experiment: barrier handshake without loads
+          mbar_arrive(&full_bar[stage]);
+          if (++chunk == chunks) { chunk = 0; if (++dx == p.taps_w) { dx = 0; ++dy; } }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          continue;
+        }
         mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
         uint8_t* sA = smem + stage * kStageBytes;
         uint8_t* sB = sA + kABytes;
         if (p.a_mode == ATDN_MODE_PATCH) {
-          const int tap = it / chunks, chunk = it - tap * chunks;
-          const int dy = tap / p.taps_w, dx = tap - dy * p.taps_w;
-          const int cw = w0 * p.stride + dx - p.pad_w;
-          const int chh = h0 * p.stride + dy - p.pad_h;
+          const int cw = w0 * p.stride + dx - p.pad_w;      // (chunk, dx, dy) advance incrementally: no
+          const int chh = h0 * p.stride + dy - p.pad_h;     // integer division inside the K loop
           if (chunk < p.chunks_a) tma_load_4d(sA, &p.tmA, &full_bar[stage], chunk * kChunkK, cw, chh, batch);
           else tma_load_4d(sA, &p.tmA2, &full_bar[stage], (chunk - p.chunks_a) * kChunkK, cw, chh, batch);
         } else {
@@ -308,22 +317,25 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
         } else {
           tma_load_4d(sB, &p.tmB, &full_bar[stage], it * kChunkK, n0, 0, p.b_batched ? batch : 0);
         }
+        if (++chunk == chunks) { chunk = 0; if (++dx == p.taps_w) { dx = 0; ++dy; } }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (dbg) dbuf[1] = clock64();
     }
   } else if (warp == 5) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, mchunk = 0;
       uint32_t phase = 0;
       for (int it = 0; it < p.num_k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
+        if (dbg && it < 48) dbuf[64 + it] = clock64();
         tcgen05_fence_after();
         // valid 16-wide K steps in this chunk (zero-padded tails are skipped)
         int rem;
         if (p.a_mode == ATDN_MODE_PATCH) {
-          const int chunk = it % chunks;
-          rem = chunk < p.chunks_a ? p.c_a - chunk * kChunkK : p.c_a2 - (chunk - p.chunks_a) * kChunkK;
+          rem = mchunk < p.chunks_a ? p.c_a - mchunk * kChunkK : p.c_a2 - (mchunk - p.chunks_a) * kChunkK;
+          if (++mchunk == chunks) mchunk = 0;
         } else {
           rem = p.c_a - it * kChunkK;
         }
@@ -331,6 +343,11 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
         const uint64_t a_desc = make_smem_desc_sw128(a_addr);
         const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
+        if (p.flags & ATDN_F_DEBUG_NO_MMA) {          // timing experiment: loads without tensor work
+          mbar_arrive(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          continue;
+        }
         for (int k = 0; k < ksteps; ++k) {
           // +32 bytes (>>4 = 2) per 16-element K step inside the 128-byte swizzle atom
           umma_f16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
@@ -338,7 +355,9 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
         umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (p.flags & ATDN_F_DEBUG_NO_MMA) mbar_arrive(&tmem_full_bar); else
       umma_commit(&tmem_full_bar);
+      if (dbg) dbuf[2] = clock64();
     }
   } else {
     // ===== epilogue warps 0..3 =====
@@ -353,7 +372,163 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
       valid = (m0 + r) < p.m_rows;
       pix = static_cast<long long>(batch) * p.m_rows + m0 + r;
     }
-    mbar_wait(&tmem_full_bar, 0);
+    mbar_wait_group128(&tmem_full_bar, 0, threadIdx.x);
+    tcgen05_fence_after();
+    if (dbg && threadIdx.x == 0) dbuf[3] = clock64();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    if constexpr (EPI == ATDN_EPI_CORR) {
+      epilogue_corr(p, valid, pix, bh0, bw0, trow);
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(trow + c * 32, v);
+        tmem_ld_wait();
+        epilogue_chunk<EPI>(p, valid, pix, n0 + c * 32, v);
+      }
+    }
+    if (dbg && threadIdx.x == 0) dbuf[4] = clock64();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+  if (dbg && threadIdx.x == 0) dbuf[5] = clock64();
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel: one cluster of two CTAs computes a 256 x BN tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 A rows and BN/2 of the B rows, so the operand bytes fetched from L2 per
+// FLOP drop by 2x (BN = 256) relative to the single-CTA 128 x 128 tile -- the single-CTA kernel runs at
+// the chip's L2->SM throughput cap (profiles/r01_prof_gru_zr_details.txt).  Only the leader CTA
+// issues MMAs; its commits are multicast to the mbarriers of both CTAs.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_kernel(const __grid_constant__ TcParams p) {
+  constexpr int kBHalfBytes = (BN / 2) * kChunkK * 2;
+  constexpr int kStageBytes = kABytes + kBHalfBytes;
+  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t kIdesc = make_idesc_f16(2 * kTileM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int batch = blockIdx.z;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int pair = blockIdx.x >> 1;
+
+  int m0 = 0, h0 = 0, w0 = 0;
+  if (p.a_mode == ATDN_MODE_PATCH) {
+    h0 = (pair / p.tiles_w) * 16 + rank * 8;
+    w0 = (pair % p.tiles_w) * 16;
+  } else {
+    m0 = pair * (2 * kTileM) + rank * kTileM;
+  }
+  const int n0 = blockIdx.y * BN;
+  int bh0 = 0, bw0 = 0;
+  if constexpr (EPI == ATDN_EPI_CORR) {
+    bh0 = (blockIdx.y / p.corr_tiles_w) * 8;
+    bw0 = (blockIdx.y % p.corr_tiles_w) * 32;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    if (p.chunks_a2 > 0) tma_prefetch_desc(&p.tmA2);
+  }
+  if (warp == 5) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised before any remote arrive / complete_tx
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int chunks = p.chunks_a + p.chunks_a2;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int chunk = 0, dx = 0, dy = 0;
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);   // both CTAs' bytes land here
+        uint8_t* sA = smem + stage * kStageBytes;
+        uint8_t* sB = sA + kABytes;
+        if (p.a_mode == ATDN_MODE_PATCH) {
+          const int cw = w0 * p.stride + dx - p.pad_w;      // (chunk, dx, dy) advance incrementally: no
+          const int chh = h0 * p.stride + dy - p.pad_h;     // integer division inside the K loop
+          if (chunk < p.chunks_a) tma_load_4d_pair(sA, &p.tmA, &full_bar[stage], chunk * kChunkK, cw, chh, batch);
+          else tma_load_4d_pair(sA, &p.tmA2, &full_bar[stage], (chunk - p.chunks_a) * kChunkK, cw, chh, batch);
+        } else {
+          tma_load_4d_pair(sA, &p.tmA, &full_bar[stage], it * kChunkK, m0, 0, p.a_shared ? 0 : batch);
+        }
+        if constexpr (EPI == ATDN_EPI_CORR) {
+          tma_load_4d_pair(sB, &p.tmB, &full_bar[stage], it * kChunkK, bw0, bh0 + rank * 4, batch);
+        } else {
+          tma_load_4d_pair(sB, &p.tmB, &full_bar[stage], it * kChunkK, n0 + rank * (BN / 2), 0, p.b_batched ? batch : 0);
+        }
+        if (++chunk == chunks) { chunk = 0; if (++dx == p.taps_w) { dx = 0; ++dy; } }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0, mchunk = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        int rem;
+        if (p.a_mode == ATDN_MODE_PATCH) {
+          rem = mchunk < p.chunks_a ? p.c_a - mchunk * kChunkK : p.c_a2 - (mchunk - p.chunks_a) * kChunkK;
+          if (++mchunk == chunks) mchunk = 0;
+        } else {
+          rem = p.c_a - it * kChunkK;
+        }
+        const int ksteps = rem >= kChunkK ? 4 : (rem + 15) >> 4;
+        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+        const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+        const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
+        for (int k = 0; k < ksteps; ++k)
+          umma_f16_pair(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit_pair(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit_pair(&tmem_full_bar);
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    bool valid;
+    long long pix;
+    if (p.a_mode == ATDN_MODE_PATCH) {
+      const int h = h0 + (r >> 4), w = w0 + (r & 15);
+      valid = (h < p.out_h) && (w < p.out_w);
+      pix = (static_cast<long long>(batch) * p.out_h + h) * p.out_w + w;
+    } else {
+      valid = (m0 + r) < p.m_rows;
+      pix = static_cast<long long>(batch) * p.m_rows + m0 + r;
+    }
+    mbar_wait_group128(&tmem_full_bar, 0, threadIdx.x);
     tcgen05_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     if constexpr (EPI == ATDN_EPI_CORR) {
@@ -371,10 +546,11 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
+  cluster_sync_all();          // neither CTA frees TMEM / exits while the pair's MMAs or epilogues are in flight
   if (warp == 5) {
     __syncwarp();
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 
@@ -437,6 +613,31 @@ static int launch(const TcParams& p, dim3 grid, cudaStream_t stream) {
   return 0;
 }
 
+template <int BN, int STAGES, int EPI>
+static int launch2(const TcParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + (BN / 2) * kChunkK * 2) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    ATDN_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  tc_gemm2_kernel<BN, STAGES, EPI><<<grid, kThreads, smem, stream>>>(p);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI>
+static int dispatch_bn2(int bn, const TcParams& p, dim3 grid, cudaStream_t s) {
+  switch (bn) {
+    case 64:  return launch2<64, 4, EPI>(p, grid, s);
+    case 96:  return launch2<96, 4, EPI>(p, grid, s);
+    case 128: return launch2<128, 4, EPI>(p, grid, s);
+    case 192: return launch2<192, 3, EPI>(p, grid, s);
+    case 256: return launch2<256, 3, EPI>(p, grid, s);
+    default:  return set_error(ATDN_ERR_UNSUP, "atdn_tc_gemm: unsupported bn %d for pair epilogue %d", bn, EPI);
+  }
+}
+
 template <int EPI>
 static int dispatch_bn(int bn, const TcParams& p, dim3 grid, cudaStream_t s) {
   switch (bn) {
@@ -460,6 +661,7 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
   ATDN_REQUIRE(d->n_valid > 0, ATDN_ERR_ARG, "atdn_tc_gemm: n_valid must be positive");
   const bool corr = d->epi == ATDN_EPI_CORR;
   ATDN_REQUIRE((d->b_mode == ATDN_MODE_PATCH) == corr, ATDN_ERR_ARG, "atdn_tc_gemm: PATCH B operand is only valid with ATDN_EPI_CORR");
+  ATDN_REQUIRE(!(d->flags & ATDN_F_PAIR) || d->bn % 32 == 0, ATDN_ERR_ARG, "atdn_tc_gemm: pair kernel needs bn %% 32 == 0");
   ATDN_REQUIRE(!corr || (d->bn == 256 && d->a_mode == ATDN_MODE_ROWS), ATDN_ERR_ARG, "atdn_tc_gemm: CORR needs bn=256 and ROWS A");
 
   TcParams p;
@@ -482,10 +684,12 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
   p.rh16 = static_cast<__half*>(d->rh16);
   p.aux32 = d->aux32;
   p.gamma = d->gamma;
+  if (d->flags & 512) p.lvl[2] = d->lvl[2];   // timing experiment: clock64 stamps of one CTA
   ATDN_REQUIRE(p.out != nullptr || d->epi == ATDN_EPI_GRU_ZR, ATDN_ERR_ARG, "atdn_tc_gemm: null output");
 
   const uint32_t ones[4] = {1, 1, 1, 1};
   dim3 grid;
+  const bool pair = (d->flags & ATDN_F_PAIR) != 0;    // CTA-pair kernel: 256-row tiles, grid.x = 2 * pairs
   const int batch = (d->flags & ATDN_F_A_SHARED) ? (int)d->b_dims[3] : (int)d->a_dims[3];
   ATDN_REQUIRE(!(d->flags & ATDN_F_A_SHARED) || d->a_mode == ATDN_MODE_ROWS, ATDN_ERR_ARG, "atdn_tc_gemm: A_SHARED needs ROWS A");
   grid.z = batch;
@@ -514,7 +718,7 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
     p.out_w = d->out_w;
     p.tiles_w = ceil_div(d->out_w, 16);
     p.num_k_iters = d->taps_h * d->taps_w * (p.chunks_a + p.chunks_a2);
-    grid.x = p.tiles_w * ceil_div(d->out_h, 8);
+    grid.x = pair ? 2 * p.tiles_w * ceil_div(d->out_h, 16) : p.tiles_w * ceil_div(d->out_h, 8);
   } else {
     const uint32_t box[4] = {64, 128, 1, 1};
     if (int e = make_map_f16(&p.tmA, d->a, d->a_dims, d->a_strides, box, ones, "A")) return e;
@@ -524,14 +728,14 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
     p.m_rows = (int)d->a_dims[1];
     p.taps_w = 1;
     p.stride = 1;
-    grid.x = ceil_div(p.m_rows, 128);
+    grid.x = pair ? 2 * ceil_div(p.m_rows, 256) : ceil_div(p.m_rows, 128);
   }
   // the packed K extent of B must cover every K iteration
   ATDN_REQUIRE(d->b_dims[0] >= (int64_t)(p.num_k_iters - 1) * 64 + 1, ATDN_ERR_ARG,
                "atdn_tc_gemm: B has K extent %lld but the A side iterates %d chunks of 64", (long long)d->b_dims[0], p.num_k_iters);
 
   if (corr) {
-    const uint32_t box[4] = {64, 32, 8, 1};
+    const uint32_t box[4] = {64, 32, pair ? 4u : 8u, 1};
     if (int e = make_map_f16(&p.tmB, d->b, d->b_dims, d->b_strides, box, ones, "B")) return e;
     p.corr_h = d->corr_h;
     p.corr_w = d->corr_w;
@@ -547,11 +751,11 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
     }
     ATDN_REQUIRE(aligned16(d->out), ATDN_ERR_ALIGN, "atdn_tc_gemm: out");
     grid.y = p.corr_tiles_w * ceil_div(d->corr_h, 8);
-    return launch<256, 4, ATDN_EPI_CORR>(p, grid, stream);
+    return pair ? launch2<256, 3, ATDN_EPI_CORR>(p, grid, stream) : launch<256, 4, ATDN_EPI_CORR>(p, grid, stream);
   }
 
   {
-    const uint32_t box[4] = {64, (uint32_t)d->bn, 1, 1};
+    const uint32_t box[4] = {64, (uint32_t)(pair ? d->bn / 2 : d->bn), 1, 1};
     if (int e = make_map_f16(&p.tmB, d->b, d->b_dims, d->b_strides, box, ones, "B")) return e;
   }
   grid.y = ceil_div(d->n_valid, d->bn);
@@ -562,17 +766,30 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
       ATDN_REQUIRE(!(d->flags & ATDN_F_RESID) || (d->resid16 && d->resid_pitch % 8 == 0 && d->resid_ch_off % 8 == 0), ATDN_ERR_ARG, "atdn_tc_gemm: residual");
       ATDN_REQUIRE(!(d->flags & ATDN_F_FLOWTAIL) || d->aux32, ATDN_ERR_ARG, "atdn_tc_gemm: FLOWTAIL needs aux32");
       ATDN_REQUIRE(!(d->flags & ATDN_F_TANH_LO) || d->h32, ATDN_ERR_ARG, "atdn_tc_gemm: TANH_LO needs h32");
-      return dispatch_bn<ATDN_EPI_STORE16>(d->bn, p, grid, stream);
+      return pair ? dispatch_bn2<ATDN_EPI_STORE16>(d->bn, p, grid, stream) : dispatch_bn<ATDN_EPI_STORE16>(d->bn, p, grid, stream);
     case ATDN_EPI_STORE32:
-      return dispatch_bn<ATDN_EPI_STORE32>(d->bn, p, grid, stream);
+      return pair ? dispatch_bn2<ATDN_EPI_STORE32>(d->bn, p, grid, stream) : dispatch_bn<ATDN_EPI_STORE32>(d->bn, p, grid, stream);
     case ATDN_EPI_GRU_ZR:
-      ATDN_REQUIRE(d->bn == 128 && d->n_valid == 256 && d->h32 && d->z32 && d->rh16, ATDN_ERR_ARG, "atdn_tc_gemm: GRU_ZR arguments");
+      ATDN_REQUIRE(d->n_valid == 256 && d->h32 && d->z32 && d->rh16, ATDN_ERR_ARG, "atdn_tc_gemm: GRU_ZR arguments");
+      if (pair) {
+        ATDN_REQUIRE(d->bn == 256 || d->bn == 128, ATDN_ERR_ARG, "atdn_tc_gemm: GRU_ZR pair kernel needs bn 128 or 256");
+        return d->bn == 256 ? launch2<256, 3, ATDN_EPI_GRU_ZR>(p, grid, stream) : launch2<128, 4, ATDN_EPI_GRU_ZR>(p, grid, stream);
+      }
+      ATDN_REQUIRE(d->bn == 128, ATDN_ERR_ARG, "atdn_tc_gemm: GRU_ZR needs bn 128");
       return launch<128, 3, ATDN_EPI_GRU_ZR>(p, grid, stream);
     case ATDN_EPI_GRU_Q:
       ATDN_REQUIRE(d->n_valid == 128 && d->h32 && d->z32, ATDN_ERR_ARG, "atdn_tc_gemm: GRU_Q arguments");
+      if (pair) {
+        ATDN_REQUIRE(d->bn == 128 || d->bn == 64, ATDN_ERR_ARG, "atdn_tc_gemm: GRU_Q pair kernel needs bn 64 or 128");
+        return d->bn == 128 ? launch2<128, 4, ATDN_EPI_GRU_Q>(p, grid, stream) : launch2<64, 4, ATDN_EPI_GRU_Q>(p, grid, stream);
+      }
       return dispatch_bn<ATDN_EPI_GRU_Q>(d->bn, p, grid, stream);
     case ATDN_EPI_PV:
       ATDN_REQUIRE(d->resid16 && d->aux32 && d->gamma && d->resid_pitch % 8 == 0 && d->resid_ch_off % 8 == 0, ATDN_ERR_ARG, "atdn_tc_gemm: PV arguments");
+      if (pair) {
+        ATDN_REQUIRE(d->bn == 128 || d->bn == 64, ATDN_ERR_ARG, "atdn_tc_gemm: PV pair kernel needs bn 64 or 128");
+        return d->bn == 128 ? launch2<128, 4, ATDN_EPI_PV>(p, grid, stream) : launch2<64, 4, ATDN_EPI_PV>(p, grid, stream);
+      }
       return dispatch_bn<ATDN_EPI_PV>(d->bn, p, grid, stream);
     default:
       return set_error(ATDN_ERR_UNSUP, "atdn_tc_gemm: unknown epilogue %d", d->epi);

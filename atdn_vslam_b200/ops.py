@@ -146,12 +146,13 @@ def alloc_pyramid(batch, h8, w8, device):
     return [torch.empty(batch * n, h, p, dtype=torch.float32, device=device) for (h, w, p) in pyramid_shapes(h8, w8)]
 
 
-def corr_pyramid_build(fmap1, fmap2, levels):
+def corr_pyramid_build(fmap1, fmap2, levels, pair=False):
     """fmap1/fmap2: Views [B,H8,W8,256] fp16 -> the 4 fp32 pyramid levels (corr.py:16-30, 55-63)."""
     d = L.TcDesc()
     b, h8, w8 = fmap1.B, fmap1.H, fmap1.W
     n = h8 * w8
-    d.bn, d.epi, d.flags, d.a_mode, d.b_mode = 256, L.EPI_CORR, L.F_B_BATCHED, L.MODE_ROWS, L.MODE_PATCH
+    d.bn, d.epi, d.a_mode, d.b_mode = 256, L.EPI_CORR, L.MODE_ROWS, L.MODE_PATCH
+    d.flags = L.F_B_BATCHED | (L.F_PAIR if pair else 0)
     d.a = fmap1.ptr()
     L._set(d.a_dims, (fmap1.c, n, 1, b))
     L._set(d.a_strides, (fmap1.pitch, n * fmap1.pitch, n * fmap1.pitch))

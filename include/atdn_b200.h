@@ -74,7 +74,9 @@ enum {
   ATDN_F_FLOWTAIL  = 4,  /* STORE16: columns n >= n_valid-2 take aux32[pix*2 + (n - (n_valid-2))] (update.py:84) */
   ATDN_F_TANH_LO   = 8,  /* STORE16: n < 128 -> tanh (also written to h32), n >= 128 -> relu (network.py:95-97) */
   ATDN_F_B_BATCHED = 16, /* B operand has a batch dimension (attention GEMMs, corr volume)               */
-  ATDN_F_A_SHARED  = 32  /* ROWS A is shared by all batches (weights as the A operand: transposed output); batch = b_dims[3] */
+  ATDN_F_A_SHARED  = 32, /* ROWS A is shared by all batches (weights as the A operand: transposed output); batch = b_dims[3] */
+  ATDN_F_DEBUG_NO_MMA = 128, ATDN_F_DEBUG_NO_TMA = 256, /* timing experiments only (single-CTA kernel): results are garbage */
+  ATDN_F_PAIR      = 64  /* CTA-pair kernel (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages bn/2 B rows; bn up to 256 */
 };
 
 typedef struct atdn_tc_desc {

@@ -23,7 +23,7 @@ def _cmp(name, got, ref, tol):
     return rel <= tol
 
 
-def check_rows(m=300, n=200, k=256, bn=128, batch=1):
+def check_rows(m=300, n=200, k=256, bn=128, batch=1, pair=False):
     import torch
     from atdn_vslam_b200 import ops, _lib as L
     g = torch.Generator().manual_seed(1)
@@ -36,13 +36,13 @@ def check_rows(m=300, n=200, k=256, bn=128, batch=1):
     npitch = (n + 7) // 8 * 8
     out = torch.full((batch, m, npitch), float("nan"), dtype=torch.float32, device="cuda")
     ops.gemm_rows(L.ptr(ap), k, m, kp, batch, L.ptr(bp), n, bp.shape[1], L.ptr(out), npitch, n_valid=n, bn=bn,
-                  epi=L.EPI_STORE32, alpha=0.5)
+                  epi=L.EPI_STORE32, alpha=0.5, flags=L.F_PAIR if pair else 0)
     torch.cuda.synchronize()
     ref = 0.5 * torch.matmul(a.float().cpu(), b.float().cpu().t())
-    return _cmp(f"rows m={m} n={n} k={k} bn={bn} batch={batch}", out[:, :, :n], ref, 2e-5)
+    return _cmp(f"rows m={m} n={n} k={k} bn={bn} batch={batch} pair={pair}", out[:, :, :n], ref, 2e-5)
 
 
-def check_conv(cin=64, cout=64, kh=3, kw=3, stride=1, h=20, w=37, batch=2, bn=64, relu=False, resid=False, split=0):
+def check_conv(cin=64, cout=64, kh=3, kw=3, stride=1, h=20, w=37, batch=2, bn=64, relu=False, resid=False, split=0, pair=False):
     import torch
     import torch.nn.functional as F
     from atdn_vslam_b200 import ops, _lib as L
@@ -61,7 +61,7 @@ def check_conv(cin=64, cout=64, kh=3, kw=3, stride=1, h=20, w=37, batch=2, bn=64
     bp = ops.pad_bias(bias.cuda())
     op = (cout + 7) // 8 * 8
     out = torch.full((batch, oh, ow, op), float("nan"), dtype=torch.half, device="cuda")
-    flags = (L.F_RELU if relu else 0) | (L.F_RESID if resid else 0)
+    flags = (L.F_RELU if relu else 0) | (L.F_RESID if resid else 0) | (L.F_PAIR if pair else 0)
     rs = None
     if resid:
         r = torch.randn(batch, oh, ow, op, generator=g).half()
@@ -80,11 +80,11 @@ def check_conv(cin=64, cout=64, kh=3, kw=3, stride=1, h=20, w=37, batch=2, bn=64
                     bn=bn, flags=flags, resid=rs)
     torch.cuda.synchronize()
     got = out[..., :cout].permute(0, 3, 1, 2)
-    return _cmp(f"conv cin={cin} cout={cout} k={kh}x{kw} s={stride} {h}x{w} b={batch} bn={bn} relu={relu} resid={resid} split={split}",
+    return _cmp(f"conv cin={cin} cout={cout} k={kh}x{kw} s={stride} {h}x{w} b={batch} bn={bn} relu={relu} resid={resid} split={split} pair={pair}",
                 got, ref, 2e-3)
 
 
-def check_corr(h8=16, w8=20, batch=2):
+def check_corr(h8=16, w8=20, batch=2, pair=False):
     import torch
     from atdn_vslam_b200 import ops
     from oracle import gma_oracle
@@ -97,12 +97,12 @@ def check_corr(h8=16, w8=20, batch=2):
     lv = ops.alloc_pyramid(batch, h8, w8, "cuda")
     for t in lv:
         t.fill_(float("nan"))
-    ops.corr_pyramid_build(v1, v2, lv)
+    ops.corr_pyramid_build(v1, v2, lv, pair=pair)
     torch.cuda.synchronize()
     ok = True
     for l, (t, r) in enumerate(zip(lv, pyr)):
         hl, wl = r.shape[-2:]
-        ok &= _cmp(f"corr level {l} grid {h8}x{w8} b={batch}", t[:, :, :wl].reshape(batch, h8 * w8, hl, wl), r, 1e-5)
+        ok &= _cmp(f"corr level {l} grid {h8}x{w8} b={batch} pair={pair}", t[:, :, :wl].reshape(batch, h8 * w8, hl, wl), r, 1e-5)
     # lookup against the oracle on the oracle's pyramid layout
     coords = gma_oracle.coords_grid(batch, h8, w8) + 2.5 * torch.randn(batch, 2, h8, w8, generator=g)
     coords[0, :, 0, 0] = torch.tensor([-7.3, 2.2])
@@ -116,7 +116,58 @@ def check_corr(h8=16, w8=20, batch=2):
     return ok
 
 
+def bench_gru(pair, bn, kind="zr", batch=6, h=47, w=154, reps=20):
+    """Timing of the SepConvGRU z|r (Cout 256) or q (Cout 128) 1x5 conv at the benchmark shape."""
+    import torch
+    from atdn_vslam_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(0)
+    cout = 256 if kind == "zr" else 128
+    hx = torch.randn(batch, h, w, 512, generator=g).half().cuda()
+    wp = ops.pack_conv_weight((torch.randn(cout, 512, 1, 5, generator=g) / 50).cuda())
+    bias = ops.pad_bias(torch.zeros(cout).cuda())
+    h32 = torch.randn(batch * h * w, 128, generator=g).cuda()
+    z32 = torch.rand(batch * h * w, 128, generator=g).cuda()
+    rh = torch.empty(batch, h, w, 128, dtype=torch.half, device="cuda")
+    out = torch.empty(batch, h, w, 128, dtype=torch.half, device="cuda")
+    fl = L.F_PAIR if pair else 0
+
+    def run():
+        if kind == "zr":
+            ops.conv_tc(ops.View(hx), wp, bias, None, cout=256, taps=(1, 5), pad=(0, 2), bn=bn, epi=L.EPI_GRU_ZR, flags=fl,
+                        h32=h32, z32=z32, rh16=rh)
+        else:
+            ops.conv_tc(ops.View(rh), wp, bias, ops.View(out), cout=128, taps=(1, 5), pad=(0, 2), bn=bn, epi=L.EPI_GRU_Q,
+                        flags=fl, a2=ops.View(hx, 128, 384), h32=h32, z32=z32)
+    for _ in range(3):
+        run()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(reps):
+        run()
+    e.record()
+    torch.cuda.synchronize()
+    us = s.elapsed_time(e) / reps * 1e3
+    flops = 2.0 * batch * h * w * cout * 5 * 512
+    print(f"PASS timing gru_{kind} pair={pair} bn={bn}: {us:.1f} us/launch  {flops / us / 1e6:.0f} TFLOP/s", flush=True)
+    return True
+
+
 CHECKS = {
+    "pair_rows_basic": lambda: check_rows(pair=True),
+    "pair_rows_bn256": lambda: check_rows(m=700, n=512, k=256, bn=256, pair=True),
+    "pair_rows_bn64_batch": lambda: check_rows(m=130, n=70, k=128, bn=64, batch=3, pair=True),
+    "pair_rows_longk": lambda: check_rows(m=200, n=128, k=7238, bn=64, pair=True),
+    "pair_conv3x3": lambda: check_conv(pair=True),
+    "pair_conv3x3_c96": lambda: check_conv(cin=96, cout=96, bn=96, pair=True),
+    "pair_conv1x5_split_bn128": lambda: check_conv(cin=512, cout=128, kh=1, kw=5, bn=128, split=128, pair=True),
+    "pair_conv5x1_bn256": lambda: check_conv(cin=512, cout=256, kh=5, kw=1, bn=256, relu=True, pair=True),
+    "pair_conv3x3_bn192": lambda: check_conv(cin=256, cout=192, bn=192, relu=True, pair=True),
+    "pair_conv_s2_3x3": lambda: check_conv(cin=64, cout=96, stride=2, h=22, w=40, bn=96, pair=True),
+    "pair_corr_small": lambda: check_corr(pair=True),
+    "pair_corr_odd": lambda: check_corr(h8=23, w8=39, batch=1, pair=True),
+    "time_gru": lambda: all([bench_gru(False, 128, "zr"), bench_gru(True, 128, "zr"), bench_gru(True, 256, "zr"),
+                             bench_gru(False, 128, "q"), bench_gru(True, 128, "q"), bench_gru(False, 64, "q"), bench_gru(True, 64, "q")]),
     "rows_basic": lambda: check_rows(),
     "rows_k147": lambda: check_rows(m=1000, n=64, k=147, bn=64),
     "rows_bn64_batch": lambda: check_rows(m=130, n=70, k=128, bn=64, batch=3),
@@ -157,5 +208,66 @@ def main():
     print("SUMMARY", results)
 
 
+
+
+def experiment_pipeline():
+    """Where does a K step go?  zr-conv shape, single-CTA kernel, with loads and/or MMAs disabled."""
+    import torch
+    from atdn_vslam_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(0)
+    for batch in (1, 2, 3, 6, 12):
+        h, w = 47, 154
+        hx = torch.randn(batch, h, w, 512, generator=g).half().cuda()
+        hxc = torch.randn(batch, h, w, 64, generator=g).half().cuda()
+        wp = ops.pack_conv_weight((torch.randn(256, 512, 1, 5, generator=g) / 50).cuda())
+        wpc = ops.pack_conv_weight((torch.randn(256, 64, 1, 5, generator=g) / 50).cuda())
+        bias = ops.pad_bias(torch.zeros(256).cuda())
+        out = torch.empty(batch, h, w, 256, dtype=torch.half, device="cuda")
+        for name, fl in (("full", 0), ("no_mma", 128), ("no_tma", 256), ("neither", 384)):
+            def run():
+                ops.conv_tc(ops.View(hx), wp, bias, ops.View(out), cout=256, taps=(1, 5), pad=(0, 2), bn=128, flags=fl)
+            for _ in range(3):
+                run()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(10):
+                run()
+            e.record()
+            torch.cuda.synchronize()
+            print(f"PASS exp batch={batch} ctas={batch * 120} {name}: {s.elapsed_time(e) / 10 * 1e3:.1f} us", flush=True)
+    return True
+
+
+def experiment_stamps():
+    import torch
+    from atdn_vslam_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(0)
+    batch, h, w = 6, 47, 154
+    hx = torch.randn(batch, h, w, 512, generator=g).half().cuda()
+    wp = ops.pack_conv_weight((torch.randn(256, 512, 1, 5, generator=g) / 50).cuda())
+    bias = ops.pad_bias(torch.zeros(256).cuda())
+    out = torch.empty(batch, h, w, 256, dtype=torch.half, device="cuda")
+    dbuf = torch.zeros(128, dtype=torch.int64, device="cuda")
+    for name, fl in (("full", 0), ("no_mma", 128), ("no_tma", 256), ("neither", 384)):
+        for rep in range(3):
+            d = L.TcDesc()
+            a = ops.View(hx)
+            d.bn, d.epi, d.flags, d.a_mode, d.b_mode = 128, L.EPI_STORE16, fl | 512, L.MODE_PATCH, L.MODE_ROWS
+            d.out_h, d.out_w, d.taps_h, d.taps_w, d.pad_h, d.pad_w, d.stride = h, w, 1, 5, 0, 2, 1
+            d.a = a.ptr(); L._set(d.a_dims, (512, w, h, batch)); L._set(d.a_strides, (512, w * 512, h * w * 512))
+            ops._fill_weight(d, wp); ops._fill_out(d, ops.View(out), 256, 1.0, bias)
+            d.lvl[2] = dbuf.data_ptr()
+            L.tc_gemm(d)
+            torch.cuda.synchronize()
+        t = dbuf.cpu().tolist()
+        print("    prod:", [t[8 + i] - t[0] for i in range(0, 40, 3)], flush=True)
+        print("    cons:", [t[64 + i] - t[0] for i in range(0, 40, 3)], flush=True)
+        print(f"PASS stamps {name}: setup->prod_end {t[1]-t[0]} mma_end {t[2]-t[0]} epi_start {t[3]-t[0]} epi_end {t[4]-t[0]} exit {t[5]-t[0]} cycles", flush=True)
+    return True
+
+
+CHECKS["exp_stamps"] = experiment_stamps
+CHECKS["exp_pipeline"] = experiment_pipeline
 if __name__ == "__main__":
     main()

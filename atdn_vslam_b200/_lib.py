@@ -35,6 +35,7 @@ class TcDesc(C.Structure):
         ("out_ch_off", C.c_int64), ("resid16", C.c_void_p), ("resid_pitch", C.c_int64), ("resid_ch_off", C.c_int64),
         ("h32", C.c_void_p), ("z32", C.c_void_p), ("rh16", C.c_void_p), ("aux32", C.c_void_p), ("gamma", C.c_void_p),
         ("lvl", C.c_void_p * 3), ("lvl_pitch", C.c_int32 * 4), ("corr_h", C.c_int32), ("corr_w", C.c_int32),
+        ("mt", C.c_int32),
     ]
 
 

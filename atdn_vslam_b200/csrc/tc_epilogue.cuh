@@ -1,0 +1,205 @@
+// Fused epilogues shared by the tensor-core kernels (tc_gemm.cu, tc_conv.cu).  One call handles 32
+// consecutive accumulator columns of ONE accumulator row (= one output pixel / GEMM row) held by one thread
+// after tcgen05.ld.32x32b.x32.  Every global load of the chunk (bias, residual, recurrent state) is issued
+// before the first store: the output may alias the inputs as far as the compiler knows, so interleaving
+// loads and stores serialises one L2 round trip per 8 columns (measured: 15K cycles per 128x128 tile).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/atdn_b200.h"
+
+namespace atdn {
+
+struct EpiParams {
+  int n_valid, flags;
+  float alpha;
+  const float* bias;
+  void* out;
+  long long out_pitch, out_ch_off;
+  const __half* resid;
+  long long resid_pitch, resid_ch_off;
+  float* h32;
+  float* z32;
+  __half* rh16;
+  const float* aux32;
+  const float* gamma;
+};
+
+// 1/(1+e^-x) and tanh through MUFU.EX2 + MUFU.RCP: ~1e-6 relative, far below the fp16 operand rounding (5e-4)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float xc = fminf(fmaxf(x, -15.0f), 15.0f);
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * xc));
+}
+
+__device__ __forceinline__ uint4 pack8_f16(const float* y) {
+  __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+  __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2);
+  u.w = *reinterpret_cast<uint32_t*>(&h3);
+  return u;
+}
+__device__ __forceinline__ void unpack8_f16(const uint4& u, float* y) {
+  float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
+  float2 d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+  y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y; y[4] = c.x; y[5] = c.y; y[6] = d.x; y[7] = d.y;
+}
+
+// fp16 store of `ng` complete 8-column groups followed by `tail` (< 8) single columns
+__device__ __forceinline__ void store_row_f16(__half* dst, const float (&y)[32], int ng, int tail) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    if (g < ng) reinterpret_cast<uint4*>(dst)[g] = pack8_f16(&y[g * 8]);
+  if (tail > 0) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g == ng) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < tail) dst[g * 8 + j] = __float2half_rn(y[g * 8 + j]);
+      }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, long long pix, int n,
+                                               const uint32_t (&v)[32]) {
+  if (n >= p.n_valid) return;
+  const int nv = min(32, p.n_valid - n);   // valid columns of this chunk
+  const int ng = nv >> 3, tail = nv & 7;
+  float y[32];
+  if (p.bias) {   // bias arrays are padded to a multiple of 64 floats
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(b4 + i);
+      y[4 * i + 0] = p.alpha * (__uint_as_float(v[4 * i + 0]) + b.x);
+      y[4 * i + 1] = p.alpha * (__uint_as_float(v[4 * i + 1]) + b.y);
+      y[4 * i + 2] = p.alpha * (__uint_as_float(v[4 * i + 2]) + b.z);
+      y[4 * i + 3] = p.alpha * (__uint_as_float(v[4 * i + 3]) + b.w);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = p.alpha * __uint_as_float(v[j]);
+  }
+  if (!valid) return;
+
+  if constexpr (EPI == ATDN_EPI_STORE16) {
+    uint4 r4[4];
+    const bool has_resid = (p.flags & ATDN_F_RESID) != 0;
+    if (has_resid) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.resid_pitch + p.resid_ch_off + n);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) r4[g] = (g < ng) ? rp[g] : make_uint4(0, 0, 0, 0);
+    }
+    float2 fl = make_float2(0.f, 0.f);
+    if (p.flags & ATDN_F_FLOWTAIL) fl = *reinterpret_cast<const float2*>(p.aux32 + pix * 2);
+    if (p.flags & ATDN_F_TANH_LO) {
+      if (n < 128) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = tanh_fast(y[j]);
+        float4* h = reinterpret_cast<float4*>(p.h32 + pix * 128 + n);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
+      }
+    } else if (p.flags & ATDN_F_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
+    }
+    if (p.flags & ATDN_F_FLOWTAIL) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (n + j == p.n_valid - 2) y[j] = fl.x;
+        if (n + j == p.n_valid - 1) y[j] = fl.y;
+      }
+    }
+    if (has_resid) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float r[8];
+        unpack8_f16(r4[g], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[g * 8 + j] = fmaxf(r[j] + y[g * 8 + j], 0.0f);
+      }
+    }
+    store_row_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y, ng, tail);
+  } else if constexpr (EPI == ATDN_EPI_STORE32) {
+    float* dst = reinterpret_cast<float*>(p.out) + pix * p.out_pitch + p.out_ch_off + n;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g < ng) {
+        reinterpret_cast<float4*>(dst)[2 * g] = make_float4(y[g * 8], y[g * 8 + 1], y[g * 8 + 2], y[g * 8 + 3]);
+        reinterpret_cast<float4*>(dst)[2 * g + 1] = make_float4(y[g * 8 + 4], y[g * 8 + 5], y[g * 8 + 6], y[g * 8 + 7]);
+      } else if (g == ng) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < tail) dst[g * 8 + j] = y[g * 8 + j];
+      }
+    }
+  } else if constexpr (EPI == ATDN_EPI_GRU_ZR) {
+    if (n < 128) {
+      float4* z = reinterpret_cast<float4*>(p.z32 + pix * 128 + n);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        z[i] = make_float4(sigmoid_fast(y[4 * i]), sigmoid_fast(y[4 * i + 1]), sigmoid_fast(y[4 * i + 2]), sigmoid_fast(y[4 * i + 3]));
+    } else {
+      const float4* h = reinterpret_cast<const float4*>(p.h32 + pix * 128 + (n - 128));
+      float4 hv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hv[i] = h[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        y[4 * i + 0] = sigmoid_fast(y[4 * i + 0]) * hv[i].x;
+        y[4 * i + 1] = sigmoid_fast(y[4 * i + 1]) * hv[i].y;
+        y[4 * i + 2] = sigmoid_fast(y[4 * i + 2]) * hv[i].z;
+        y[4 * i + 3] = sigmoid_fast(y[4 * i + 3]) * hv[i].w;
+      }
+      uint4* dst = reinterpret_cast<uint4*>(p.rh16 + pix * 128 + (n - 128));
+#pragma unroll
+      for (int g = 0; g < 4; ++g) dst[g] = pack8_f16(&y[g * 8]);
+    }
+  } else if constexpr (EPI == ATDN_EPI_GRU_Q) {
+    float4* h = reinterpret_cast<float4*>(p.h32 + pix * 128 + n);
+    const float4* z = reinterpret_cast<const float4*>(p.z32 + pix * 128 + n);
+    float4 hv[8], zv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { hv[i] = h[i]; zv[i] = z[i]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      y[4 * i + 0] = (1.0f - zv[i].x) * hv[i].x + zv[i].x * tanh_fast(y[4 * i + 0]);
+      y[4 * i + 1] = (1.0f - zv[i].y) * hv[i].y + zv[i].y * tanh_fast(y[4 * i + 1]);
+      y[4 * i + 2] = (1.0f - zv[i].z) * hv[i].z + zv[i].z * tanh_fast(y[4 * i + 2]);
+      y[4 * i + 3] = (1.0f - zv[i].w) * hv[i].w + zv[i].w * tanh_fast(y[4 * i + 3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) dst[g] = pack8_f16(&y[g * 8]);
+  } else if constexpr (EPI == ATDN_EPI_PV) {
+    const float scale = p.aux32[pix] * __ldg(p.gamma);
+    const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.resid_pitch + p.resid_ch_off + n);
+    uint4 r4[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) r4[g] = (g < ng) ? rp[g] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float r[8];
+      unpack8_f16(r4[g], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[g * 8 + j] = r[j] + scale * y[g * 8 + j];
+    }
+    store_row_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y, ng, tail);
+  }
+}
+
+}  // namespace atdn

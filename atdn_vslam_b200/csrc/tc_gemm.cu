@@ -11,6 +11,8 @@
 
 #include "common.h"
 #include "tc_ptx.cuh"
+#include "tc_epilogue.cuh"
+#include "tc_host.cuh"
 
 namespace atdn {
 
@@ -21,138 +23,15 @@ constexpr int kThreads = 192;
 
 struct alignas(64) TcParams {
   CUtensorMap tmA, tmA2, tmB;
-  int a_mode, tiles_w, out_h, out_w, m_rows, n_valid;
+  int a_mode, tiles_w, out_h, out_w, m_rows;
   int taps_w, pad_h, pad_w, stride;
   int chunks_a, chunks_a2, c_a, c_a2, num_k_iters;
-  int b_batched, a_shared, flags;
+  int b_batched, a_shared;
   int corr_h, corr_w, corr_tiles_w;
   int lvl_pitch[4];
   float* lvl[3];
-  float alpha;
-  const float* bias;
-  void* out;
-  long long out_pitch, out_ch_off;
-  const __half* resid;
-  long long resid_pitch, resid_ch_off;
-  float* h32;
-  float* z32;
-  __half* rh16;
-  const float* aux32;
-  const float* gamma;
+  EpiParams e;
 };
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-__device__ __forceinline__ void store8_f16(__half* dst, const float (&y)[8]) {
-  __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
-  __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
-  uint4 u;
-  u.x = *reinterpret_cast<uint32_t*>(&h0);
-  u.y = *reinterpret_cast<uint32_t*>(&h1);
-  u.z = *reinterpret_cast<uint32_t*>(&h2);
-  u.w = *reinterpret_cast<uint32_t*>(&h3);
-  *reinterpret_cast<uint4*>(dst) = u;
-}
-__device__ __forceinline__ void load8_f16(const __half* src, float (&y)[8]) {
-  uint4 u = *reinterpret_cast<const uint4*>(src);
-  float2 a = __half22float2(*reinterpret_cast<__half2*>(&u.x));
-  float2 b = __half22float2(*reinterpret_cast<__half2*>(&u.y));
-  float2 c = __half22float2(*reinterpret_cast<__half2*>(&u.z));
-  float2 d = __half22float2(*reinterpret_cast<__half2*>(&u.w));
-  y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y; y[4] = c.x; y[5] = c.y; y[6] = d.x; y[7] = d.y;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Epilogues operating on one 32-column chunk of one accumulator row (this thread's pixel / row).
-// ------------------------------------------------------------------------------------------------
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, bool valid, long long pix, int ncol0,
-                                               const uint32_t (&v)[32]) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int n = ncol0 + g * 8;
-    if (n >= p.n_valid) break;
-    float y[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float b = p.bias ? __ldg(p.bias + n + j) : 0.0f;   // bias arrays are padded to a multiple of 64
-      y[j] = p.alpha * (__uint_as_float(v[g * 8 + j]) + b);
-    }
-    if (!valid) continue;
-    if constexpr (EPI == ATDN_EPI_STORE16) {
-      if (p.flags & ATDN_F_TANH_LO) {
-        if (n < 128) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = tanhf(y[j]);
-          float4* h = reinterpret_cast<float4*>(p.h32 + pix * 128 + n);
-          h[0] = make_float4(y[0], y[1], y[2], y[3]);
-          h[1] = make_float4(y[4], y[5], y[6], y[7]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.0f);
-        }
-      } else if (p.flags & ATDN_F_RELU) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.0f);
-      }
-      if (p.flags & ATDN_F_FLOWTAIL) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (n + j >= p.n_valid - 2 && n + j < p.n_valid) y[j] = p.aux32[pix * 2 + (n + j - (p.n_valid - 2))];
-      }
-      if (p.flags & ATDN_F_RESID) {
-        float r[8];
-        load8_f16(p.resid + pix * p.resid_pitch + p.resid_ch_off + n, r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = fmaxf(r[j] + y[j], 0.0f);
-      }
-      __half* dst = reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n;
-      if (n + 8 <= p.n_valid) {
-        store8_f16(dst, y);
-      } else {
-        for (int j = 0; j < 8 && n + j < p.n_valid; ++j) dst[j] = __float2half_rn(y[j]);
-      }
-    } else if constexpr (EPI == ATDN_EPI_STORE32) {
-      float* dst = reinterpret_cast<float*>(p.out) + pix * p.out_pitch + p.out_ch_off + n;
-      if (n + 8 <= p.n_valid) {
-        reinterpret_cast<float4*>(dst)[0] = make_float4(y[0], y[1], y[2], y[3]);
-        reinterpret_cast<float4*>(dst)[1] = make_float4(y[4], y[5], y[6], y[7]);
-      } else {
-        for (int j = 0; j < 8 && n + j < p.n_valid; ++j) dst[j] = y[j];
-      }
-    } else if constexpr (EPI == ATDN_EPI_GRU_ZR) {
-      if (n < 128) {
-        float4* z = reinterpret_cast<float4*>(p.z32 + pix * 128 + n);
-        z[0] = make_float4(sigmoidf_(y[0]), sigmoidf_(y[1]), sigmoidf_(y[2]), sigmoidf_(y[3]));
-        z[1] = make_float4(sigmoidf_(y[4]), sigmoidf_(y[5]), sigmoidf_(y[6]), sigmoidf_(y[7]));
-      } else {
-        const float4* h = reinterpret_cast<const float4*>(p.h32 + pix * 128 + (n - 128));
-        float4 h0 = h[0], h1 = h[1];
-        float r[8] = {sigmoidf_(y[0]) * h0.x, sigmoidf_(y[1]) * h0.y, sigmoidf_(y[2]) * h0.z, sigmoidf_(y[3]) * h0.w,
-                      sigmoidf_(y[4]) * h1.x, sigmoidf_(y[5]) * h1.y, sigmoidf_(y[6]) * h1.z, sigmoidf_(y[7]) * h1.w};
-        store8_f16(p.rh16 + pix * 128 + (n - 128), r);
-      }
-    } else if constexpr (EPI == ATDN_EPI_GRU_Q) {
-      float4* h = reinterpret_cast<float4*>(p.h32 + pix * 128 + n);
-      const float4* z = reinterpret_cast<const float4*>(p.z32 + pix * 128 + n);
-      float4 h0 = h[0], h1 = h[1], z0 = z[0], z1 = z[1];
-      float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-      float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = (1.0f - zv[j]) * hv[j] + zv[j] * tanhf(y[j]);
-      h[0] = make_float4(y[0], y[1], y[2], y[3]);
-      h[1] = make_float4(y[4], y[5], y[6], y[7]);
-      store8_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y);
-    } else if constexpr (EPI == ATDN_EPI_PV) {
-      const float scale = p.aux32[pix] * __ldg(p.gamma);
-      float r[8];
-      load8_f16(p.resid + pix * p.resid_pitch + p.resid_ch_off + n, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = r[j] + scale * y[j];
-      store8_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y);
-    }
-  }
-}
 
 // Corr-volume epilogue: this thread owns query row `pix` of a tile of 8 x 32 target pixels whose 256
 // accumulator columns are ordered (h_local, w_local).  Level 0 is stored as is; levels 1..3 are the
@@ -171,10 +50,10 @@ __device__ __forceinline__ void epilogue_corr(const TcParams& p, bool valid, lon
     tmem_ld_wait();
     float c[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) c[j] = p.alpha * __uint_as_float(v[j]);
+    for (int j = 0; j < 32; ++j) c[j] = p.e.alpha * __uint_as_float(v[j]);
     const int h = bh0 + hl;
     if (valid && h < H0) {
-      float* dst = reinterpret_cast<float*>(p.out) + (pix * H0 + h) * (long long)p.lvl_pitch[0] + bw0;
+      float* dst = reinterpret_cast<float*>(p.e.out) + (pix * H0 + h) * (long long)p.lvl_pitch[0] + bw0;
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         if (bw0 + j < p.lvl_pitch[0]) *reinterpret_cast<float4*>(dst + j) = make_float4(c[j], c[j + 1], c[j + 2], c[j + 3]);
@@ -243,7 +122,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler as well
   const int lane = threadIdx.x & 31;
   const int batch = blockIdx.z;
 
@@ -280,27 +159,17 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const bool dbg = (p.flags & 512) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
-  long long* dbuf = reinterpret_cast<long long*>(p.lvl[2]);
-  if (dbg && threadIdx.x == 0) dbuf[0] = clock64();
 
   const int chunks = p.chunks_a + p.chunks_a2;
 
   if (warp == 4) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int chunk = 0, dx = 0, dy = 0;
-      for (int it = 0; it < p.num_k_iters; ++it) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (dbg && it < 48) dbuf[8 + it] = clock64();
-        if (p.flags & ATDN_F_DEBUG_NO_TMA) {          // timing experiment: barrier handshake without loads
-          mbar_arrive(&full_bar[stage]);
-          if (++chunk == chunks) { chunk = 0; if (++dx == p.taps_w) { dx = 0; ++dy; } }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          continue;
-        }
+    // ===== TMA producer: the whole warp runs the loop, one elected lane issues (see elect_one_sync) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int chunk = 0, dx = 0, dy = 0;
+    for (int it = 0; it < p.num_k_iters; ++it) {
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
         uint8_t* sA = smem + stage * kStageBytes;
         uint8_t* sB = sA + kABytes;
@@ -317,47 +186,46 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
         } else {
           tma_load_4d(sB, &p.tmB, &full_bar[stage], it * kChunkK, n0, 0, p.b_batched ? batch : 0);
         }
-        if (++chunk == chunks) { chunk = 0; if (++dx == p.taps_w) { dx = 0; ++dy; } }
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (dbg) dbuf[1] = clock64();
+      __syncwarp();
+      if (++chunk == chunks) { chunk = 0; if (++dx == p.taps_w) { dx = 0; ++dy; } }
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 5) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      int stage = 0, mchunk = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < p.num_k_iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
-        if (dbg && it < 48) dbuf[64 + it] = clock64();
-        tcgen05_fence_after();
-        // valid 16-wide K steps in this chunk (zero-padded tails are skipped)
-        int rem;
-        if (p.a_mode == ATDN_MODE_PATCH) {
-          rem = mchunk < p.chunks_a ? p.c_a - mchunk * kChunkK : p.c_a2 - (mchunk - p.chunks_a) * kChunkK;
-          if (++mchunk == chunks) mchunk = 0;
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+    int stage = 0, mchunk = 0;
+    uint32_t phase = 0;
+    const uint32_t smem_base_u32 = smem_u32(smem);
+    for (int it = 0; it < p.num_k_iters; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      // valid 16-wide K steps in this chunk (zero-padded tails are skipped)
+      int rem;
+      if (p.a_mode == ATDN_MODE_PATCH) {
+        rem = mchunk < p.chunks_a ? p.c_a - mchunk * kChunkK : p.c_a2 - (mchunk - p.chunks_a) * kChunkK;
+        if (++mchunk == chunks) mchunk = 0;
+      } else {
+        rem = p.c_a - it * kChunkK;
+      }
+      const int ksteps = rem >= kChunkK ? 4 : (rem + 15) >> 4;
+      const uint32_t a_addr = smem_base_u32 + stage * kStageBytes;
+      const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+      const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
+      const uint32_t acc0 = it > 0 ? 1u : 0u;
+      if (elect_one_sync()) {
+        if (ksteps == 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // +32 bytes (>>4 = 2) per 16-element K step inside the 128-byte swizzle atom
+            umma_f16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, k == 0 ? acc0 : 1u);
         } else {
-          rem = p.c_a - it * kChunkK;
-        }
-        const int ksteps = rem >= kChunkK ? 4 : (rem + 15) >> 4;
-        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-        const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-        const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
-        if (p.flags & ATDN_F_DEBUG_NO_MMA) {          // timing experiment: loads without tensor work
-          mbar_arrive(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          continue;
-        }
-        for (int k = 0; k < ksteps; ++k) {
-          // +32 bytes (>>4 = 2) per 16-element K step inside the 128-byte swizzle atom
-          umma_f16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, k == 0 ? acc0 : 1u);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (it == p.num_k_iters - 1) umma_commit(&tmem_full_bar);
       }
-      if (p.flags & ATDN_F_DEBUG_NO_MMA) mbar_arrive(&tmem_full_bar); else
-      umma_commit(&tmem_full_bar);
-      if (dbg) dbuf[2] = clock64();
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else {
     // ===== epilogue warps 0..3 =====
@@ -374,7 +242,6 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     }
     mbar_wait_group128(&tmem_full_bar, 0, threadIdx.x);
     tcgen05_fence_after();
-    if (dbg && threadIdx.x == 0) dbuf[3] = clock64();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     if constexpr (EPI == ATDN_EPI_CORR) {
       epilogue_corr(p, valid, pix, bh0, bw0, trow);
@@ -384,10 +251,9 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
         uint32_t v[32];
         tmem_ld_32x32(trow + c * 32, v);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, valid, pix, n0 + c * 32, v);
+        epilogue_chunk<EPI>(p.e, valid, pix, n0 + c * 32, v);
       }
     }
-    if (dbg && threadIdx.x == 0) dbuf[4] = clock64();
   }
 
   tcgen05_fence_before();
@@ -397,7 +263,6 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
-  if (dbg && threadIdx.x == 0) dbuf[5] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -422,7 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler as well
   const int lane = threadIdx.x & 31;
   const int batch = blockIdx.z;
   const int rank = static_cast<int>(cluster_ctarank());
@@ -465,18 +330,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
   const int chunks = p.chunks_a + p.chunks_a2;
 
   if (warp == 4) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int chunk = 0, dx = 0, dy = 0;
-      for (int it = 0; it < p.num_k_iters; ++it) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+    int stage = 0;
+    uint32_t phase = 0;
+    int chunk = 0, dx = 0, dy = 0;
+    for (int it = 0; it < p.num_k_iters; ++it) {
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (elect_one_sync()) {
         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);   // both CTAs' bytes land here
         uint8_t* sA = smem + stage * kStageBytes;
         uint8_t* sB = sA + kABytes;
         if (p.a_mode == ATDN_MODE_PATCH) {
-          const int cw = w0 * p.stride + dx - p.pad_w;      // (chunk, dx, dy) advance incrementally: no
-          const int chh = h0 * p.stride + dy - p.pad_h;     // integer division inside the K loop
+          const int cw = w0 * p.stride + dx - p.pad_w;
+          const int chh = h0 * p.stride + dy - p.pad_h;
           if (chunk < p.chunks_a) tma_load_4d_pair(sA, &p.tmA, &full_bar[stage], chunk * kChunkK, cw, chh, batch);
           else tma_load_4d_pair(sA, &p.tmA2, &full_bar[stage], (chunk - p.chunks_a) * kChunkK, cw, chh, batch);
         } else {
@@ -487,14 +352,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
         } else {
           tma_load_4d_pair(sB, &p.tmB, &full_bar[stage], it * kChunkK, n0 + rank * (BN / 2), 0, p.b_batched ? batch : 0);
         }
-        if (++chunk == chunks) { chunk = 0; if (++dx == p.taps_w) { dx = 0; ++dy; } }
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      if (++chunk == chunks) { chunk = 0; if (++dx == p.taps_w) { dx = 0; ++dy; } }
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 5) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       int stage = 0, mchunk = 0;
       uint32_t phase = 0;
+      const uint32_t smem_base_u32 = smem_u32(smem);
       for (int it = 0; it < p.num_k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
@@ -506,15 +373,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
           rem = p.c_a - it * kChunkK;
         }
         const int ksteps = rem >= kChunkK ? 4 : (rem + 15) >> 4;
-        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+        const uint32_t a_addr = smem_base_u32 + stage * kStageBytes;
         const uint64_t a_desc = make_smem_desc_sw128(a_addr);
         const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
-        for (int k = 0; k < ksteps; ++k)
-          umma_f16_pair(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit_pair(&empty_bar[stage]);
+        const uint32_t acc0 = it > 0 ? 1u : 0u;
+        if (elect_one_sync()) {
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_pair(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, k == 0 ? acc0 : 1u);
+          } else {
+            for (int k = 0; k < ksteps; ++k) umma_f16_pair(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, k == 0 ? acc0 : 1u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (it == p.num_k_iters - 1) umma_commit_pair(&tmem_full_bar);
+        }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      umma_commit_pair(&tmem_full_bar);
     }
   } else {
     const int r = warp * 32 + lane;
@@ -539,7 +414,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
         uint32_t v[32];
         tmem_ld_32x32(trow + c * 32, v);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, valid, pix, n0 + c * 32, v);
+        epilogue_chunk<EPI>(p.e, valid, pix, n0 + c * 32, v);
       }
     }
   }
@@ -557,49 +432,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-// fp16 tensor, dims innermost first, strides in elements for dims 1..3, 128B swizzle, zero OOB fill.
-static int make_map_f16(CUtensorMap* m, const void* ptr, const int64_t dims[4], const int64_t strides[3],
-                        const uint32_t box[4], const uint32_t estr[4], const char* what) {
-  EncodeTiledFn fn = get_encode_fn();
-  ATDN_REQUIRE(fn != nullptr, ATDN_ERR_ARCH, "cuTensorMapEncodeTiled is not available from the driver");
-  ATDN_REQUIRE(ptr != nullptr && aligned16(ptr), ATDN_ERR_ALIGN, "%s: pointer must be non-null and 16-byte aligned", what);
-  cuuint64_t gd[4], gs[3];
-  cuuint32_t bx[4], es[4];
-  for (int i = 0; i < 4; ++i) {
-    ATDN_REQUIRE(dims[i] >= 1, ATDN_ERR_ARG, "%s: dims[%d] = %lld", what, i, (long long)dims[i]);
-    gd[i] = (cuuint64_t)dims[i];
-    bx[i] = box[i];
-    es[i] = estr[i];
-  }
-  for (int i = 0; i < 3; ++i) {
-    ATDN_REQUIRE(strides[i] > 0 && strides[i] % 8 == 0, ATDN_ERR_ALIGN,
-                 "%s: strides[%d] = %lld elements is not a positive multiple of 8 (16 bytes)", what, i,
-                 (long long)strides[i]);
-    gs[i] = (cuuint64_t)strides[i] * 2u;
-  }
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  ATDN_REQUIRE(r == CUDA_SUCCESS, (int)r, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);
-  return 0;
-}
-
 template <int BN, int STAGES, int EPI>
 static int launch(const TcParams& p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + BN * kChunkK * 2) + 1024;
@@ -659,6 +491,7 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
   if (int e = require_sm100()) return e;
   ATDN_REQUIRE(d->a_mode == ATDN_MODE_ROWS || d->a_mode == ATDN_MODE_PATCH, ATDN_ERR_ARG, "atdn_tc_gemm: bad a_mode");
   ATDN_REQUIRE(d->n_valid > 0, ATDN_ERR_ARG, "atdn_tc_gemm: n_valid must be positive");
+  if (d->mt > 0) return launch_conv_halo(d, stream);
   const bool corr = d->epi == ATDN_EPI_CORR;
   ATDN_REQUIRE((d->b_mode == ATDN_MODE_PATCH) == corr, ATDN_ERR_ARG, "atdn_tc_gemm: PATCH B operand is only valid with ATDN_EPI_CORR");
   ATDN_REQUIRE(!(d->flags & ATDN_F_PAIR) || d->bn % 32 == 0, ATDN_ERR_ARG, "atdn_tc_gemm: pair kernel needs bn %% 32 == 0");
@@ -667,25 +500,24 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.a_mode = d->a_mode;
-  p.n_valid = d->n_valid;
-  p.flags = d->flags;
+  p.e.n_valid = d->n_valid;
+  p.e.flags = d->flags;
   p.b_batched = (d->flags & ATDN_F_B_BATCHED) ? 1 : 0;
   p.a_shared = (d->flags & ATDN_F_A_SHARED) ? 1 : 0;
-  p.alpha = d->alpha;
-  p.bias = d->bias;
-  p.out = d->out;
-  p.out_pitch = d->out_pitch;
-  p.out_ch_off = d->out_ch_off;
-  p.resid = static_cast<const __half*>(d->resid16);
-  p.resid_pitch = d->resid_pitch;
-  p.resid_ch_off = d->resid_ch_off;
-  p.h32 = d->h32;
-  p.z32 = d->z32;
-  p.rh16 = static_cast<__half*>(d->rh16);
-  p.aux32 = d->aux32;
-  p.gamma = d->gamma;
-  if (d->flags & 512) p.lvl[2] = d->lvl[2];   // timing experiment: clock64 stamps of one CTA
-  ATDN_REQUIRE(p.out != nullptr || d->epi == ATDN_EPI_GRU_ZR, ATDN_ERR_ARG, "atdn_tc_gemm: null output");
+  p.e.alpha = d->alpha;
+  p.e.bias = d->bias;
+  p.e.out = d->out;
+  p.e.out_pitch = d->out_pitch;
+  p.e.out_ch_off = d->out_ch_off;
+  p.e.resid = static_cast<const __half*>(d->resid16);
+  p.e.resid_pitch = d->resid_pitch;
+  p.e.resid_ch_off = d->resid_ch_off;
+  p.e.h32 = d->h32;
+  p.e.z32 = d->z32;
+  p.e.rh16 = static_cast<__half*>(d->rh16);
+  p.e.aux32 = d->aux32;
+  p.e.gamma = d->gamma;
+  ATDN_REQUIRE(p.e.out != nullptr || d->epi == ATDN_EPI_GRU_ZR, ATDN_ERR_ARG, "atdn_tc_gemm: null output");
 
   const uint32_t ones[4] = {1, 1, 1, 1};
   dim3 grid;

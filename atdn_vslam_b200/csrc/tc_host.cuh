@@ -1,0 +1,54 @@
+// Host-side helpers shared by the tensor-core translation units: TMA tensor-map construction.
+#pragma once
+#include "common.h"
+
+namespace atdn {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// fp16 tensor, dims innermost first, strides in elements for dims 1..3, 128B swizzle, zero OOB fill.
+inline int make_map_f16(CUtensorMap* m, const void* ptr, const int64_t dims[4], const int64_t strides[3],
+                        const uint32_t box[4], const uint32_t estr[4], const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  ATDN_REQUIRE(fn != nullptr, ATDN_ERR_ARCH, "cuTensorMapEncodeTiled is not available from the driver");
+  ATDN_REQUIRE(ptr != nullptr && aligned16(ptr), ATDN_ERR_ALIGN, "%s: pointer must be non-null and 16-byte aligned", what);
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < 4; ++i) {
+    ATDN_REQUIRE(dims[i] >= 1, ATDN_ERR_ARG, "%s: dims[%d] = %lld", what, i, (long long)dims[i]);
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = box[i];
+    es[i] = estr[i];
+  }
+  for (int i = 0; i < 3; ++i) {
+    ATDN_REQUIRE(strides[i] > 0 && strides[i] % 8 == 0, ATDN_ERR_ALIGN,
+                 "%s: strides[%d] = %lld elements is not a positive multiple of 8 (16 bytes)", what, i,
+                 (long long)strides[i]);
+    gs[i] = (cuuint64_t)strides[i] * 2u;
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ATDN_REQUIRE(r == CUDA_SUCCESS, (int)r, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
+
+// CTA-pair / persistent conv kernel entry (tc_conv.cu); called by atdn_tc_gemm when desc->mt > 0
+int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream);
+
+}  // namespace atdn

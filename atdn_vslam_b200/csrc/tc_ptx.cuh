@@ -12,6 +12,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp.  The single-thread roles (TMA producer, MMA issuer) run their loops with the
+// WHOLE warp and predicate only the issuing instructions with this: control flow and operands stay
+// warp-uniform, so descriptors live in uniform registers.  A loop entered under `if (lane == 0)` instead makes
+// ptxas wrap every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST waterfall loop: ~115 cycles per MMA issue,
+// i.e. 2x the 64..128 cycles a 128 x N x 16 MMA takes to execute (measured, profiles/r02_halo_timings.txt).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -189,6 +200,13 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
       : "memory");
+}
+
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta_rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta_rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 // K-major operand tile in shared memory, 128-byte rows (64 fp16), SWIZZLE_128B, 8-row groups 1024 B

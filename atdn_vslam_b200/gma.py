@@ -65,6 +65,26 @@ def _fold_bn(w, b, sd, name):
     return w.float() * s.view(-1, 1, 1, 1), (b.float() - sd[name + ".running_mean"].float()) * s + sd[name + ".bias"].float()
 
 
+# (mt, bn, CTA pair) of the persistent halo-reuse kernel per output width (stride-1 convs); measured on B200 at
+# 47x154 x 24 pairs / encoder resolutions (profiles/r01b_halo_conv_timings.log)
+_HALO_CFG = {64: (4, 64, False), 96: (2, 96, True), 128: (2, 128, True), 192: (1, 192, True), 256: (1, 256, True),
+             576: (1, 192, False)}
+
+
+def _halo(cout, taps=(3, 3)):
+    mt, bn, pair = _HALO_CFG[cout]
+    if taps == (1, 1) and cout == 256:
+        pair = False
+    return {"mt": mt, "bn": bn, "flags": L.F_PAIR if pair else 0}
+
+
+def _conv_s1(x, c, out, *, cout, taps, flags=0, **kw):
+    """Stride-1 convolution on the halo kernel; `c` is a _Conv."""
+    cfg = _halo(cout, taps)
+    return ops.conv_tc(x, c.wp, c.bias, out, cout=cout, taps=taps, pad=(taps[0] // 2, taps[1] // 2), bn=cfg["bn"],
+                       mt=cfg["mt"], flags=flags | cfg["flags"], **kw)
+
+
 def _pick_bn(cout, m_tiles):
     """Largest N tile that still yields >= ~1 wave of the 148 SMs."""
     for bn in (192, 128, 96, 64):
@@ -279,7 +299,10 @@ class RAFTGMA(nn.Module):
             m_tiles = n * math.ceil(t1.H / 8) * math.ceil(t1.W / 16)
             bn = _pick_bn(planes, m_tiles)
             c1, c2 = blk["conv1"], blk["conv2"]
-            ops.conv_tc(x, c1.wp, c1.bias, t1, cout=planes, taps=(3, 3), pad=(1, 1), stride=st, bn=bn, flags=relu)
+            if st == 1:
+                _conv_s1(x, c1, t1, cout=planes, taps=(3, 3), flags=relu)
+            else:
+                ops.conv_tc(x, c1.wp, c1.bias, t1, cout=planes, taps=(3, 3), pad=(1, 1), stride=st, bn=bn, flags=relu)
             if inst:
                 norm_apply(t1, t1)
             if st != 1:
@@ -291,15 +314,12 @@ class RAFTGMA(nn.Module):
             else:
                 skip = x
             if inst:
-                ops.conv_tc(t1, c2.wp, c2.bias, t2, cout=planes, taps=(3, 3), pad=(1, 1), bn=bn)
+                _conv_s1(t1, c2, t2, cout=planes, taps=(3, 3))
                 norm_apply(t2, t2, resid=skip)
             else:   # y = relu(bn(conv)); out = relu(skip + y) fused in the epilogue
-                ops.conv_tc(t1, c2.wp, c2.bias, t2, cout=planes, taps=(3, 3), pad=(1, 1), bn=bn,
-                            flags=L.F_RELU | L.F_RESID, resid=skip)
+                _conv_s1(t1, c2, t2, cout=planes, taps=(3, 3), flags=L.F_RELU | L.F_RESID, resid=skip)
             x = t2
-        m_tiles = n * math.ceil(plan.h8 / 8) * math.ceil(plan.w8 / 16)
-        ops.conv_tc(x, ew.out.wp, ew.out.bias, out_view, cout=256, bn=128 if m_tiles * 2 >= 140 else 64,
-                    flags=final_flags, h32=h32)
+        _conv_s1(x, ew.out, out_view, cout=256, taps=(1, 1), flags=final_flags, h32=h32)
 
     # -- forward ------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -348,7 +368,7 @@ class RAFTGMA(nn.Module):
         self._encoder(plan, wts.cnet, image1, View(hx, 0, 256), final_flags=L.F_TANH_LO, h32=plan.h32)
 
         # attention (gma.py:54-76): q.k^T * scale -> softmax
-        ops.conv_tc(View(hx, 128, 128), wts.to_qk.wp, None, View(plan.qk), cout=256, bn=_pick_bn(256, m_tiles))
+        _conv_s1(View(hx, 128, 128), wts.to_qk, View(plan.qk), cout=256, taps=(1, 1))
         ops.gemm_rows(L.ptr(plan.qk), 128, n, 256, b, L.ptr(plan.qk, 128), n, 256, L.ptr(plan.s32), np_, n_valid=n,
                       b_bstride=n * 256, bn=128, epi=L.EPI_STORE32, alpha=128 ** -0.5)
         ops.softmax_rows(plan.s32, plan.p16, plan.inv_sum, b * n, n)
@@ -364,11 +384,10 @@ class RAFTGMA(nn.Module):
             self._update(plan, wts, m_tiles)
             if need_up:
                 c = wts.mask0
-                ops.conv_tc(View(hx, 0, 128), c.wp, c.bias, View(plan.mh), cout=256, taps=(3, 3), pad=(1, 1),
-                            bn=_pick_bn(256, m_tiles), flags=L.F_RELU)
+                _conv_s1(View(hx, 0, 128), c, View(plan.mh), cout=256, taps=(3, 3), flags=L.F_RELU)
                 c = wts.mask2
                 d_out = View(plan.mask32.view(b, h8, w8, 576))
-                ops.conv_tc(View(plan.mh), c.wp, c.bias, d_out, cout=576, bn=192, epi=L.EPI_STORE32, alpha=0.25)
+                _conv_s1(View(plan.mh), c, d_out, cout=576, taps=(1, 1), epi=L.EPI_STORE32, alpha=0.25)
                 flow_up = torch.empty(b, 2, h, w, dtype=torch.float32, device=dev)
                 flow_lo = torch.empty(b, 2, h8, w8, dtype=torch.float32, device=dev)
                 ops.convex_upsample(plan.mask32, plan.flow, flow_up, flow_lo)
@@ -384,19 +403,18 @@ class RAFTGMA(nn.Module):
         R = L.F_RELU
         ops.corr_lookup(plan.pyr, plan.coords1, out16=View(plan.corrfeat))
         c = wts.convc1
-        ops.conv_tc(View(plan.corrfeat, 0, 324), c.wp, c.bias, View(plan.c1), cout=256, bn=_pick_bn(256, m_tiles), flags=R)
+        _conv_s1(View(plan.corrfeat, 0, 324), c, View(plan.c1), cout=256, taps=(1, 1), flags=R)
         c = wts.convc2
-        ops.conv_tc(View(plan.c1), c.wp, c.bias, View(plan.corflo, 0, 192), cout=192, taps=(3, 3), pad=(1, 1),
-                    bn=_pick_bn(192, m_tiles), flags=R)
+        _conv_s1(View(plan.c1), c, View(plan.corflo, 0, 192), cout=192, taps=(3, 3), flags=R)
         ops.flow_im2col(plan.flow, plan.frows)
         c = wts.convf1
         ops.gemm_rows(L.ptr(plan.frows), 98, b * n, 104, 1, L.ptr(c.wp), 128, c.wp.shape[1], L.ptr(plan.f1), 128,
                       n_valid=128, bn=_pick_bn(128, m_tiles), flags=R, bias=c.bias)
         c = wts.convf2
-        ops.conv_tc(View(plan.f1), c.wp, c.bias, View(plan.corflo, 192, 64), cout=64, taps=(3, 3), pad=(1, 1), bn=64, flags=R)
+        ops.conv_tc(View(plan.f1), c.wp, c.bias, View(plan.corflo, 192, 64), cout=64, taps=(3, 3), pad=(1, 1), bn=64, mt=2,
+                    flags=R | L.F_PAIR)
         c = wts.conv
-        ops.conv_tc(View(plan.corflo), c.wp, c.bias, View(hx, 256, 128), cout=128, taps=(3, 3), pad=(1, 1),
-                    bn=_pick_bn(128, m_tiles), flags=R | L.F_FLOWTAIL, aux32=plan.flow)
+        _conv_s1(View(plan.corflo), c, View(hx, 256, 128), cout=128, taps=(3, 3), flags=R | L.F_FLOWTAIL, aux32=plan.flow)
         # aggregation: v^T = W_v . mf^T (stored [B,128,Np]); mfg = mf + gamma * (P . v) / rowsum
         d = L.TcDesc()
         d.bn, d.epi, d.flags, d.a_mode, d.b_mode = 128, L.EPI_STORE16, L.F_B_BATCHED | L.F_A_SHARED, L.MODE_ROWS, L.MODE_ROWS
@@ -413,13 +431,11 @@ class RAFTGMA(nn.Module):
                       b_bstride=128 * np_, bn=64, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
                       aux32=plan.inv_sum, gamma=wts.gamma)
         for (zr, q), taps, pad in ((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0))):
-            ops.conv_tc(View(hx), zr.wp, zr.bias, None, cout=256, taps=taps, pad=pad, bn=128, epi=L.EPI_GRU_ZR,
-                        h32=plan.h32, z32=plan.z32, rh16=plan.rh)
-            ops.conv_tc(View(plan.rh), q.wp, q.bias, View(hx, 0, 128), cout=128, taps=taps, pad=pad,
-                        bn=_pick_bn(128, m_tiles), epi=L.EPI_GRU_Q, a2=View(hx, 128, 384), h32=plan.h32, z32=plan.z32)
+            _conv_s1(View(hx), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, h32=plan.h32, z32=plan.z32, rh16=plan.rh)
+            _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 128, 384),
+                     h32=plan.h32, z32=plan.z32)
         c = wts.fh1
-        ops.conv_tc(View(hx, 0, 128), c.wp, c.bias, View(plan.fh), cout=256, taps=(3, 3), pad=(1, 1),
-                    bn=_pick_bn(256, m_tiles), flags=R)
+        _conv_s1(View(hx, 0, 128), c, View(plan.fh), cout=256, taps=(3, 3), flags=R)
         ops.flow_head_update(View(plan.fh), wts.fh2_w, wts.fh2_b, plan.coords1, plan.flow)
 
 

@@ -76,11 +76,14 @@ def _fill_out(d, out, n_valid, alpha, bias):
 
 
 def conv_tc(a, wp, bias, out, *, cout, taps=(1, 1), pad=(0, 0), stride=1, bn=128, epi=L.EPI_STORE16, flags=0,
-            alpha=1.0, a2=None, resid=None, h32=None, z32=None, rh16=None, aux32=None, gamma=None):
+            alpha=1.0, a2=None, resid=None, h32=None, z32=None, rh16=None, aux32=None, gamma=None, mt=0, stamps=None):
     """Convolution as implicit GEMM on tcgen05.  ``a`` (and optional ``a2``, concatenated after it)
     are NHWC fp16 Views of the INPUT image; ``out`` is a View of the output buffer."""
     d = L.TcDesc()
     d.bn, d.epi, d.flags, d.a_mode, d.b_mode = bn, epi, flags, L.MODE_PATCH, L.MODE_ROWS
+    d.mt = mt
+    if stamps is not None:
+        d.lvl[2] = stamps.data_ptr()
     kh, kw = taps
     oh = (a.H + 2 * pad[0] - kh) // stride + 1
     ow = (a.W + 2 * pad[1] - kw) // stride + 1

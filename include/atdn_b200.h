@@ -75,7 +75,6 @@ enum {
   ATDN_F_TANH_LO   = 8,  /* STORE16: n < 128 -> tanh (also written to h32), n >= 128 -> relu (network.py:95-97) */
   ATDN_F_B_BATCHED = 16, /* B operand has a batch dimension (attention GEMMs, corr volume)               */
   ATDN_F_A_SHARED  = 32, /* ROWS A is shared by all batches (weights as the A operand: transposed output); batch = b_dims[3] */
-  ATDN_F_DEBUG_NO_MMA = 128, ATDN_F_DEBUG_NO_TMA = 256, /* timing experiments only (single-CTA kernel): results are garbage */
   ATDN_F_PAIR      = 64  /* CTA-pair kernel (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages bn/2 B rows; bn up to 256 */
 };
 
@@ -111,6 +110,12 @@ typedef struct atdn_tc_desc {
   float* lvl[3];
   int32_t lvl_pitch[4];   /* pitch of levels 0..3 in elements (multiples of 4)                      */
   int32_t corr_h, corr_w; /* target grid H8 x W8                                                    */
+  /* mt > 0 selects the persistent halo-reuse convolution kernel (PATCH A, stride 1): one CTA owns
+   * `mt` side-by-side sub-tiles of 16 x 8 output pixels, stages one (16+kh-1) x (8*mt+kw-1) input box per
+   * 64-channel chunk and reads every filter tap as a shifted view of it; mt * bn <= 256 (two TMEM
+   * accumulator buffers).  Instances: (mt, bn) = (1,256) (1,192) (1,128) (2,128) (2,96) (2,64) (4,64);
+   * epilogues STORE16, STORE32, GRU_ZR (bn 128), GRU_Q.  mt = 0: one 8 x 16 pixel tile per CTA.       */
+  int32_t mt;
 } atdn_tc_desc;
 
 int atdn_tc_gemm(const atdn_tc_desc* desc, void* stream);

@@ -42,7 +42,7 @@ def check_rows(m=300, n=200, k=256, bn=128, batch=1, pair=False):
     return _cmp(f"rows m={m} n={n} k={k} bn={bn} batch={batch} pair={pair}", out[:, :, :n], ref, 2e-5)
 
 
-def check_conv(cin=64, cout=64, kh=3, kw=3, stride=1, h=20, w=37, batch=2, bn=64, relu=False, resid=False, split=0, pair=False):
+def check_conv(cin=64, cout=64, kh=3, kw=3, stride=1, h=20, w=37, batch=2, bn=64, relu=False, resid=False, split=0, pair=False, mt=0):
     import torch
     import torch.nn.functional as F
     from atdn_vslam_b200 import ops, _lib as L
@@ -74,14 +74,145 @@ def check_conv(cin=64, cout=64, kh=3, kw=3, stride=1, h=20, w=37, batch=2, bn=64
         a1 = ops.View(xn[..., :split].contiguous())
         a2 = ops.View(xn[..., split:].contiguous())
         ops.conv_tc(a1, wp, bp, ops.View(out), cout=cout, taps=(kh, kw), pad=(ph, pw), stride=stride, bn=bn, flags=flags,
-                    a2=a2, resid=rs)
+                    a2=a2, resid=rs, mt=mt)
     else:
         ops.conv_tc(ops.View(xn, 0, cin), wp, bp, ops.View(out), cout=cout, taps=(kh, kw), pad=(ph, pw), stride=stride,
-                    bn=bn, flags=flags, resid=rs)
+                    bn=bn, flags=flags, resid=rs, mt=mt)
     torch.cuda.synchronize()
     got = out[..., :cout].permute(0, 3, 1, 2)
-    return _cmp(f"conv cin={cin} cout={cout} k={kh}x{kw} s={stride} {h}x{w} b={batch} bn={bn} relu={relu} resid={resid} split={split} pair={pair}",
+    return _cmp(f"conv cin={cin} cout={cout} k={kh}x{kw} s={stride} {h}x{w} b={batch} bn={bn} relu={relu} resid={resid} split={split} pair={pair} mt={mt}",
                 got, ref, 2e-3)
+
+
+
+def check_gru(mt=2, kind="zr", h=37, w=45, batch=2, taps=(1, 5), pair=False, bn=128):
+    """SepConvGRU epilogues of the halo kernel against a PyTorch fp32 reference of the same op (update.py:48-63)."""
+    import torch
+    import torch.nn.functional as F
+    from atdn_vslam_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(5)
+    pad = (taps[0] // 2, taps[1] // 2)
+    hx = torch.randn(batch, h, w, 512, generator=g).half()
+    h32 = torch.randn(batch * h * w, 128, generator=g)
+    hx[..., :128] = h32.view(batch, h, w, 128).half()
+    ok = True
+    if kind == "zr":
+        wt = (torch.randn(256, 512, *taps, generator=g) / (512 * 5) ** 0.5).half()
+        bias = torch.randn(256, generator=g) * 0.1
+        ref = F.conv2d(hx.permute(0, 3, 1, 2).float(), wt.float(), bias, padding=pad).permute(0, 2, 3, 1).reshape(-1, 256)
+        z_ref = torch.sigmoid(ref[:, :128])
+        rh_ref = torch.sigmoid(ref[:, 128:]) * h32
+        z32 = torch.full((batch * h * w, 128), float("nan"), device="cuda")
+        rh = torch.full((batch, h, w, 128), float("nan"), dtype=torch.half, device="cuda")
+        ops.conv_tc(ops.View(hx.cuda()), ops.pack_conv_weight(wt.float().cuda()), ops.pad_bias(bias.cuda()), None, cout=256,
+                    taps=taps, pad=pad, bn=bn, epi=L.EPI_GRU_ZR, h32=h32.cuda(), z32=z32, rh16=rh, mt=mt, flags=L.F_PAIR if pair else 0)
+        torch.cuda.synchronize()
+        ok &= _cmp(f"gru_zr z mt={mt} taps={taps} pair={pair} bn={bn}", z32, z_ref, 2e-3)
+        ok &= _cmp(f"gru_zr r*h mt={mt} taps={taps} pair={pair} bn={bn}", rh.reshape(-1, 128), rh_ref, 2e-3)
+    else:
+        wt = (torch.randn(128, 512, *taps, generator=g) / (512 * 5) ** 0.5).half()
+        bias = torch.randn(128, generator=g) * 0.1
+        rhx = torch.randn(batch, h, w, 128, generator=g).half()
+        z = torch.rand(batch * h * w, 128, generator=g)
+        xin = torch.cat([rhx, hx[..., 128:]], -1)
+        ref = F.conv2d(xin.permute(0, 3, 1, 2).float(), wt.float(), bias, padding=pad).permute(0, 2, 3, 1).reshape(-1, 128)
+        h_ref = (1 - z) * h32 + z * torch.tanh(ref)
+        h32d = h32.cuda()
+        hxd = hx.cuda()
+        out = torch.full((batch, h, w, 128), float("nan"), dtype=torch.half, device="cuda")
+        ops.conv_tc(ops.View(rhx.cuda()), ops.pack_conv_weight(wt.float().cuda()), ops.pad_bias(bias.cuda()), ops.View(out), cout=128,
+                    taps=taps, pad=pad, bn=128 if mt <= 2 else 64, epi=L.EPI_GRU_Q, a2=ops.View(hxd, 128, 384), h32=h32d, z32=z.cuda(), mt=mt,
+                    flags=L.F_PAIR if pair else 0)
+        torch.cuda.synchronize()
+        ok &= _cmp(f"gru_q h32 mt={mt} taps={taps} pair={pair}", h32d, h_ref, 2e-3)
+        ok &= _cmp(f"gru_q h16 mt={mt} taps={taps} pair={pair}", out.reshape(-1, 128), h_ref, 2e-3)
+    return ok
+
+
+def bench_conv(name, cin, cout, taps, bn, mt, batch=6, h=47, w=154, reps=20, epi=None, stamps=False, pair=False):
+    """Timing of one conv layer shape: legacy kernel (mt=0) or halo kernel (mt>0)."""
+    import torch
+    from atdn_vslam_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(0)
+    pad = (taps[0] // 2, taps[1] // 2)
+    cp = (cin + 7) // 8 * 8
+    x = torch.randn(batch, h, w, cp, generator=g).half().cuda()
+    wp = ops.pack_conv_weight((torch.randn(cout, cin, *taps, generator=g) / 50).cuda())
+    bias = ops.pad_bias(torch.zeros(cout).cuda())
+    out = torch.empty(batch, h, w, cout, dtype=torch.half, device="cuda")
+    h32 = torch.randn(batch * h * w, 128, generator=g).cuda()
+    z32 = torch.rand(batch * h * w, 128, generator=g).cuda()
+    rh = torch.empty(batch, h, w, 128, dtype=torch.half, device="cuda")
+    st = torch.zeros(64, dtype=torch.int64, device="cuda") if stamps else None
+    fp = L.F_PAIR if pair else 0
+
+    def run():
+        if epi == "zr":
+            ops.conv_tc(ops.View(x), wp, bias, None, cout=256, taps=taps, pad=pad, bn=bn, epi=L.EPI_GRU_ZR, h32=h32, z32=z32,
+                        rh16=rh, mt=mt, stamps=st, flags=fp)
+        elif epi == "q":
+            ops.conv_tc(ops.View(rh), wp, bias, ops.View(out), cout=128, taps=taps, pad=pad, bn=bn, epi=L.EPI_GRU_Q,
+                        a2=ops.View(x, 128, 384), h32=h32, z32=z32, mt=mt, stamps=st, flags=fp)
+        else:
+            ops.conv_tc(ops.View(x, 0, cin), wp, bias, ops.View(out), cout=cout, taps=taps, pad=pad, bn=bn, flags=L.F_RELU | fp, mt=mt,
+                        stamps=st)
+    for _ in range(3):
+        run()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(reps):
+        run()
+    e.record()
+    torch.cuda.synchronize()
+    us = s.elapsed_time(e) / reps * 1e3
+    flops = 2.0 * batch * h * w * cout * taps[0] * taps[1] * cin
+    print(f"PASS timing {name} cin={cin} cout={cout} taps={taps} batch={batch} {h}x{w} mt={mt} bn={bn} pair={pair}: {us:.1f} us  {flops / us / 1e6:.0f} TFLOP/s", flush=True)
+    if stamps:
+        t = st.cpu().tolist()
+        print("    kernel cycles", t[1] - t[0], "mma_done", [v - t[0] for v in t[8:16] if v], "epi_start", [v - t[0] for v in t[16:24] if v],
+              "epi_end", [v - t[0] for v in t[24:32] if v], flush=True)
+    return True
+
+
+def time_halo():
+    for b in (6, 24):
+        bench_conv("gru_zr", 512, 256, (1, 5), 128, 0, batch=b, epi="zr")
+        bench_conv("gru_zr", 512, 256, (1, 5), 256, 1, batch=b, epi="zr", stamps=True)
+        bench_conv("gru_zr", 512, 256, (1, 5), 256, 1, batch=b, epi="zr", stamps=True, pair=True)
+        bench_conv("gru_zr", 512, 256, (5, 1), 256, 1, batch=b, epi="zr", pair=True)
+        bench_conv("gru_zr", 512, 256, (1, 5), 128, 2, batch=b, epi="zr", pair=True)
+        bench_conv("gru_q", 512, 128, (1, 5), 128, 0, batch=b, epi="q")
+        bench_conv("gru_q", 512, 128, (1, 5), 128, 2, batch=b, epi="q")
+        bench_conv("gru_q", 512, 128, (1, 5), 128, 2, batch=b, epi="q", pair=True, stamps=True)
+        bench_conv("gru_q", 512, 128, (1, 5), 128, 1, batch=b, epi="q", pair=True)
+        bench_conv("c3x3 256->192", 256, 192, (3, 3), 192, 0, batch=b)
+        bench_conv("c3x3 256->192", 256, 192, (3, 3), 192, 1, batch=b)
+        bench_conv("c3x3 256->192", 256, 192, (3, 3), 192, 1, batch=b, pair=True)
+        bench_conv("c3x3 128->256", 128, 256, (3, 3), 128, 0, batch=b)
+        bench_conv("c3x3 128->256", 128, 256, (3, 3), 256, 1, batch=b)
+        bench_conv("c3x3 128->256", 128, 256, (3, 3), 256, 1, batch=b, pair=True)
+        bench_conv("c3x3 256->128", 256, 128, (3, 3), 128, 0, batch=b)
+        bench_conv("c3x3 256->128", 256, 128, (3, 3), 128, 2, batch=b)
+        bench_conv("c3x3 256->128", 256, 128, (3, 3), 128, 2, batch=b, pair=True)
+        bench_conv("c3x3 256->128", 256, 128, (3, 3), 128, 1, batch=b, pair=True)
+        bench_conv("c3x3 128->64", 128, 64, (3, 3), 64, 0, batch=b)
+        bench_conv("c3x3 128->64", 128, 64, (3, 3), 64, 4, batch=b)
+        bench_conv("c3x3 128->64", 128, 64, (3, 3), 64, 4, batch=b, pair=True)
+        bench_conv("c3x3 128->64", 128, 64, (3, 3), 64, 2, batch=b, pair=True)
+        bench_conv("c1x1 324->256", 324, 256, (1, 1), 128, 0, batch=b)
+        bench_conv("c1x1 324->256", 324, 256, (1, 1), 256, 1, batch=b)
+        bench_conv("c1x1 324->256", 324, 256, (1, 1), 256, 1, batch=b, pair=True)
+    bench_conv("enc 64->64", 64, 64, (3, 3), 64, 0, batch=7, h=188, w=616)
+    bench_conv("enc 64->64", 64, 64, (3, 3), 64, 4, batch=7, h=188, w=616)
+    bench_conv("enc 64->64", 64, 64, (3, 3), 64, 4, batch=7, h=188, w=616, pair=True)
+    bench_conv("enc 64->64", 64, 64, (3, 3), 64, 2, batch=7, h=188, w=616, pair=True)
+    bench_conv("enc 96->96", 96, 96, (3, 3), 96, 0, batch=7, h=94, w=308)
+    bench_conv("enc 96->96", 96, 96, (3, 3), 96, 2, batch=7, h=94, w=308)
+    bench_conv("enc 96->96", 96, 96, (3, 3), 96, 2, batch=7, h=94, w=308, pair=True)
+    bench_conv("enc 128->128", 128, 128, (3, 3), 128, 0, batch=7, h=47, w=154)
+    bench_conv("enc 128->128", 128, 128, (3, 3), 128, 2, batch=7, h=47, w=154, pair=True)
+    return True
 
 
 def check_corr(h8=16, w8=20, batch=2, pair=False):
@@ -154,6 +285,33 @@ def bench_gru(pair, bn, kind="zr", batch=6, h=47, w=154, reps=20):
 
 
 CHECKS = {
+    "halo_conv3x3_mt1": lambda: check_conv(cin=64, cout=128, bn=128, mt=1),
+    "halo_conv3x3_mt2": lambda: check_conv(cin=128, cout=256, bn=128, mt=2, relu=True),
+    "halo_conv3x3_mt4": lambda: check_conv(cin=64, cout=64, bn=64, mt=4, relu=True, resid=True, h=50, w=70),
+    "halo_conv3x3_c96": lambda: check_conv(cin=96, cout=96, bn=96, mt=2),
+    "halo_conv3x3_bn192": lambda: check_conv(cin=256, cout=192, bn=192, mt=1, relu=True),
+    "halo_conv3x3_bn256": lambda: check_conv(cin=128, cout=256, bn=256, mt=1, relu=True),
+    "halo_conv1x1_c324": lambda: check_conv(cin=324, cout=256, kh=1, kw=1, bn=128, mt=2),
+    "halo_conv1x5_split": lambda: check_conv(cin=512, cout=128, kh=1, kw=5, bn=128, split=128, mt=2),
+    "halo_conv5x1": lambda: check_conv(cin=128, cout=128, kh=5, kw=1, bn=64, relu=True, mt=4),
+    "halo_conv_big": lambda: check_conv(cin=64, cout=64, bn=64, mt=4, h=94, w=154, batch=3),
+    "halo_gru_zr": lambda: check_gru(2, "zr"),
+    "halo_gru_zr_5x1": lambda: check_gru(2, "zr", taps=(5, 1)),
+    "halo_gru_q": lambda: check_gru(2, "q"),
+    "halo_gru_q_mt4": lambda: check_gru(4, "q", taps=(5, 1)),
+    "hpair_conv3x3_mt1": lambda: check_conv(cin=64, cout=128, bn=128, mt=1, pair=True),
+    "hpair_conv3x3_bn256": lambda: check_conv(cin=128, cout=256, bn=256, mt=1, relu=True, pair=True),
+    "hpair_conv3x3_mt4": lambda: check_conv(cin=64, cout=64, bn=64, mt=4, relu=True, resid=True, h=50, w=70, pair=True),
+    "hpair_conv3x3_c96": lambda: check_conv(cin=96, cout=96, bn=96, mt=2, pair=True),
+    "hpair_conv3x3_bn192": lambda: check_conv(cin=256, cout=192, bn=192, mt=1, relu=True, pair=True),
+    "hpair_conv1x1_c324": lambda: check_conv(cin=324, cout=256, kh=1, kw=1, bn=256, mt=1, pair=True),
+    "hpair_conv1x5_split": lambda: check_conv(cin=512, cout=128, kh=1, kw=5, bn=128, split=128, mt=2, pair=True),
+    "hpair_conv_big": lambda: check_conv(cin=64, cout=64, bn=64, mt=4, h=94, w=154, batch=3, pair=True),
+    "hpair_gru_zr": lambda: check_gru(1, "zr", pair=True, bn=256),
+    "hpair_gru_zr_5x1": lambda: check_gru(2, "zr", taps=(5, 1), pair=True),
+    "hpair_gru_q": lambda: check_gru(2, "q", pair=True),
+    "halo_gru_zr_bn256": lambda: check_gru(1, "zr", bn=256),
+    "time_halo": time_halo,
     "pair_rows_basic": lambda: check_rows(pair=True),
     "pair_rows_bn256": lambda: check_rows(m=700, n=512, k=256, bn=256, pair=True),
     "pair_rows_bn64_batch": lambda: check_rows(m=130, n=70, k=128, bn=64, batch=3, pair=True),
@@ -189,6 +347,18 @@ CHECKS = {
 
 def main():
     names = sys.argv[1:]
+    if names and names[0] == "--inproc":       # all checks in ONE process (cheap; a trapped kernel fails the rest)
+        import traceback
+        results = {}
+        for n in names[1:] or list(CHECKS):
+            print(f"=== {n}", flush=True)
+            try:
+                results[n] = 0 if CHECKS[n]() else 1
+            except Exception:
+                traceback.print_exc()
+                results[n] = "exception"
+        print("SUMMARY", results, flush=True)
+        sys.exit(0 if all(v == 0 for v in results.values()) else 1)
     if len(names) == 1 and names[0] in CHECKS and os.environ.get("ATDN_DIAG_CHILD"):
         ok = CHECKS[names[0]]()
         sys.exit(0 if ok else 1)
@@ -210,64 +380,5 @@ def main():
 
 
 
-def experiment_pipeline():
-    """Where does a K step go?  zr-conv shape, single-CTA kernel, with loads and/or MMAs disabled."""
-    import torch
-    from atdn_vslam_b200 import ops, _lib as L
-    g = torch.Generator().manual_seed(0)
-    for batch in (1, 2, 3, 6, 12):
-        h, w = 47, 154
-        hx = torch.randn(batch, h, w, 512, generator=g).half().cuda()
-        hxc = torch.randn(batch, h, w, 64, generator=g).half().cuda()
-        wp = ops.pack_conv_weight((torch.randn(256, 512, 1, 5, generator=g) / 50).cuda())
-        wpc = ops.pack_conv_weight((torch.randn(256, 64, 1, 5, generator=g) / 50).cuda())
-        bias = ops.pad_bias(torch.zeros(256).cuda())
-        out = torch.empty(batch, h, w, 256, dtype=torch.half, device="cuda")
-        for name, fl in (("full", 0), ("no_mma", 128), ("no_tma", 256), ("neither", 384)):
-            def run():
-                ops.conv_tc(ops.View(hx), wp, bias, ops.View(out), cout=256, taps=(1, 5), pad=(0, 2), bn=128, flags=fl)
-            for _ in range(3):
-                run()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            s.record()
-            for _ in range(10):
-                run()
-            e.record()
-            torch.cuda.synchronize()
-            print(f"PASS exp batch={batch} ctas={batch * 120} {name}: {s.elapsed_time(e) / 10 * 1e3:.1f} us", flush=True)
-    return True
-
-
-def experiment_stamps():
-    import torch
-    from atdn_vslam_b200 import ops, _lib as L
-    g = torch.Generator().manual_seed(0)
-    batch, h, w = 6, 47, 154
-    hx = torch.randn(batch, h, w, 512, generator=g).half().cuda()
-    wp = ops.pack_conv_weight((torch.randn(256, 512, 1, 5, generator=g) / 50).cuda())
-    bias = ops.pad_bias(torch.zeros(256).cuda())
-    out = torch.empty(batch, h, w, 256, dtype=torch.half, device="cuda")
-    dbuf = torch.zeros(128, dtype=torch.int64, device="cuda")
-    for name, fl in (("full", 0), ("no_mma", 128), ("no_tma", 256), ("neither", 384)):
-        for rep in range(3):
-            d = L.TcDesc()
-            a = ops.View(hx)
-            d.bn, d.epi, d.flags, d.a_mode, d.b_mode = 128, L.EPI_STORE16, fl | 512, L.MODE_PATCH, L.MODE_ROWS
-            d.out_h, d.out_w, d.taps_h, d.taps_w, d.pad_h, d.pad_w, d.stride = h, w, 1, 5, 0, 2, 1
-            d.a = a.ptr(); L._set(d.a_dims, (512, w, h, batch)); L._set(d.a_strides, (512, w * 512, h * w * 512))
-            ops._fill_weight(d, wp); ops._fill_out(d, ops.View(out), 256, 1.0, bias)
-            d.lvl[2] = dbuf.data_ptr()
-            L.tc_gemm(d)
-            torch.cuda.synchronize()
-        t = dbuf.cpu().tolist()
-        print("    prod:", [t[8 + i] - t[0] for i in range(0, 40, 3)], flush=True)
-        print("    cons:", [t[64 + i] - t[0] for i in range(0, 40, 3)], flush=True)
-        print(f"PASS stamps {name}: setup->prod_end {t[1]-t[0]} mma_end {t[2]-t[0]} epi_start {t[3]-t[0]} epi_end {t[4]-t[0]} exit {t[5]-t[0]} cycles", flush=True)
-    return True
-
-
-CHECKS["exp_stamps"] = experiment_stamps
-CHECKS["exp_pipeline"] = experiment_pipeline
 if __name__ == "__main__":
     main()

@@ -64,6 +64,51 @@ __global__ void pingpong(int iters, int prod_warp, int cons_warp, long long* out
     out[blockIdx.x] = clock64() - t0;
   }
 }
+
+// Ping-pong with the rest of the CTA behaving like the GEMM kernel's idle roles:
+//   BG = 1: warps 0-3 sleep in a named hardware barrier that is released at the end
+//   BG = 2: BG 1 + thread 0 polls a never-completing mbarrier with try_wait + nanosleep(40) (the accumulator wait)
+//   BG = 3: all 128 threads of warps 0-3 poll the never-completing mbarrier with try_wait (no sleep)
+//   BG = 4: thread 0 polls it with try_wait only (no sleep), the others sleep in the named barrier
+//   lanes 1-31 of the producer / consumer warps wait at the final __syncthreads like in the GEMM kernel.
+template <int STAGES, int BG>
+__global__ void pingpong_bg(int iters, int prod_warp, int cons_warp, long long* out) {
+  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], never;
+  __shared__ volatile int stop;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { binit(&full[s], 1); binit(&empty[s], 1); }
+    binit(&never, 1);
+    stop = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long t0 = clock64();
+  if (warp == prod_warp) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int i = 0; i < iters; ++i) { bwait<0>(&empty[st], ph ^ 1); barrive(&full[st]); if (++st == STAGES) { st = 0; ph ^= 1; } }
+    }
+  } else if (warp == cons_warp) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int i = 0; i < iters; ++i) { bwait<0>(&full[st], ph); barrive(&empty[st]); if (++st == STAGES) { st = 0; ph ^= 1; } }
+      out[blockIdx.x] = clock64() - t0;
+      barrive(&never);
+    }
+  } else {
+    if (BG == 2 || BG == 4) {
+      if (threadIdx.x == 0) { while (!btry(&never, 0)) { if (BG == 2) __nanosleep(40); } }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    } else if (BG == 3) {
+      while (!btry(&never, 0)) {}
+    } else if (BG == 1) {
+      if (threadIdx.x == 0) { while (!btest(&never, 0)) { __nanosleep(2000); } }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+  __syncthreads();
+}
 int main() {
   long long* d; cudaMalloc(&d, 1024 * sizeof(long long));
   long long h[4];
@@ -85,5 +130,11 @@ int main() {
   run("try_wait, consumer arrives via tcgen05.commit", pingpong_fence<3, 2>, 4, 5, 192, 1);
   run("try_wait stages=3 296 blocks", pingpong<3, 0>, 4, 5, 192, 296);
   run("test_wait stages=3 296 blocks", pingpong<3, 1>, 4, 5, 192, 296);
+  run("bg1 named-barrier sleepers", pingpong_bg<3, 1>, 4, 5, 192, 1);
+  run("bg2 + thread0 try_wait+nanosleep", pingpong_bg<3, 2>, 4, 5, 192, 1);
+  run("bg3 128 threads try_wait", pingpong_bg<3, 3>, 4, 5, 192, 1);
+  run("bg4 thread0 try_wait no sleep", pingpong_bg<3, 4>, 4, 5, 192, 1);
+  run("bg2 296 blocks", pingpong_bg<3, 2>, 4, 5, 192, 296);
+  run("bg3 296 blocks", pingpong_bg<3, 3>, 4, 5, 192, 296);
   return 0;
 }

@@ -9,11 +9,15 @@
 namespace atdn {
 
 // ------------------------------------------------------------------------------------------------
-// Correlation lookup: one CTA (4 warps) per query pixel, warp l samples pyramid level l.
-// Each of the 81 taps of a level is an independent bilinear sample; the 10x10 texel footprint of a
-// level stays in L1 across the 3 rounds of a warp.  Coordinates follow the reference's round trip
-// through normalised grid coordinates (utils.py:63-64 then ATen's align_corners un-normalisation),
-// with explicit _rn intrinsics so that nvcc cannot contract the sequence into FMAs.
+// Correlation lookup: one WARP per query pixel, 8 queries per CTA.
+//   1. lanes compute the 4 x (9 + 9) tap coordinates of the query (per level: 9 x and 9 y positions shared by
+//      the 81 taps) exactly like the reference's round trip through normalised grid coordinates (utils.py:63-64
+//      then ATen's align_corners un-normalisation; explicit _rn intrinsics so nvcc cannot contract into FMAs);
+//   2. the 12 x 12 texel window of every level that covers all taps (+-1 texel of rounding slack) is staged in
+//      shared memory with row-contiguous loads: all 18 loads of a lane are independent and in flight together,
+//      and out-of-image texels are staged as the zeros of grid_sample's zero padding;
+//   3. each lane blends its taps from shared memory and writes two adjacent channels per store.
+// The previous version (one CTA per query, 4 dependent scattered loads per tap) ran at 16% of the HBM roofline.
 // ------------------------------------------------------------------------------------------------
 struct LookupParams {
   const float* lvl[4];
@@ -27,64 +31,130 @@ __device__ __forceinline__ float grid_round_trip(float x, int size) {
   return __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.0f), 2.0f), sm1);
 }
 
-__global__ void __launch_bounds__(128) corr_lookup_kernel(LookupParams p, const float* __restrict__ coords,
-                                                          __half* __restrict__ out16, long long out_pitch,
-                                                          float* __restrict__ out32) {
-  const long long q = blockIdx.x;
-  const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+constexpr int kLkWarps = 8;
+constexpr int kLkWin = 12;                       // staged window edge (texels)
+
+__global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_kernel(LookupParams p, const float* __restrict__ coords,
+                                                                    __half* __restrict__ out16, long long out_pitch,
+                                                                    float* __restrict__ out32, long long nq) {
+  __shared__ float win[kLkWarps][4][kLkWin * kLkWin];
+  __shared__ float cfr[kLkWarps][72];            // fractional part of the 4 x (9 x + 9 y) tap coordinates
+  __shared__ int cin[kLkWarps][72];              // integer part (floor), clamped to [-2, size]
+  __shared__ int org[kLkWarps][8];               // window origin (x, y) per level
+  const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = static_cast<long long>(blockIdx.x) * kLkWarps + wq;
+  if (q >= nq) return;
   const float cx = coords[q * 2], cy = coords[q * 2 + 1];
-  const float inv = 1.0f / static_cast<float>(1 << l);
-  const int H = p.h[l], W = p.w[l], pitch = p.pitch[l];
-  const float* __restrict__ base = p.lvl[l] + q * static_cast<long long>(H) * pitch;
-  const float xl = cx * inv, yl = cy * inv;   // exact: division by a power of two
-  for (int t = lane; t < 81; t += 32) {
-    const int a = t / 9, b = t - a * 9;       // a offsets x, b offsets y (corr.py:40-46)
-    const float x = grid_round_trip(__fadd_rn(xl, static_cast<float>(a - 4)), W);
-    const float y = grid_round_trip(__fadd_rn(yl, static_cast<float>(b - 4)), H);
-    const float xf = floorf(x), yf = floorf(y);
-    const float fx = x - xf, fy = y - yf;
+
+  // 1. tap coordinates: idx = level * 18 + axis * 9 + k
+  for (int idx = lane; idx < 72; idx += 32) {
+    const int l = idx / 18, rem = idx - l * 18, axis = rem / 9, k = rem - axis * 9;
+    const float inv = 1.0f / static_cast<float>(1 << l);     // exact: division by a power of two
+    const int size = axis ? p.h[l] : p.w[l];
+    const float c = (axis ? cy : cx) * inv;
+    const float v = grid_round_trip(__fadd_rn(c, static_cast<float>(k - 4)), size);
+    const float vf = floorf(v);
+    cfr[wq][idx] = v - vf;
     // clamp before the int conversion so that far-away coordinates cannot overflow
-    const int x0 = static_cast<int>(fminf(fmaxf(xf, -2.0f), static_cast<float>(W)));
-    const int y0 = static_cast<int>(fminf(fmaxf(yf, -2.0f), static_cast<float>(H)));
-    const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
-    const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
-    const float* r0 = base + static_cast<long long>(y0) * pitch + x0;
-    const float* r1 = r0 + pitch;
-    const float v00 = (xin0 && yin0) ? __ldg(r0) : 0.0f;
-    const float v01 = (xin1 && yin0) ? __ldg(r0 + 1) : 0.0f;
-    const float v10 = (xin0 && yin1) ? __ldg(r1) : 0.0f;
-    const float v11 = (xin1 && yin1) ? __ldg(r1 + 1) : 0.0f;
-    const float val = v00 * ((1.0f - fx) * (1.0f - fy)) + v01 * (fx * (1.0f - fy)) + v10 * ((1.0f - fx) * fy) +
-                      v11 * (fx * fy);
-    const int ch = l * 81 + t;
-    if (out16) out16[q * out_pitch + ch] = __float2half_rn(val);
-    if (out32) out32[q * 324 + ch] = val;
+    cin[wq][idx] = static_cast<int>(fminf(fmaxf(vf, -2.0f), static_cast<float>(size)));
+  }
+  if (lane < 8) {
+    const int l = lane >> 1, axis = lane & 1;
+    const float inv = 1.0f / static_cast<float>(1 << l);
+    const int size = axis ? p.h[l] : p.w[l];
+    const float c = floorf((axis ? cy : cx) * inv);
+    org[wq][lane] = static_cast<int>(fminf(fmaxf(c, -16.0f), static_cast<float>(size + 16))) - 5;
+  }
+  __syncwarp();
+
+  // 2. stage the windows (zero outside the image)
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int H = p.h[l], W = p.w[l], pitch = p.pitch[l];
+    const float* __restrict__ base = p.lvl[l] + q * static_cast<long long>(H) * pitch;
+    const int X0 = org[wq][2 * l], Y0 = org[wq][2 * l + 1];
+#pragma unroll
+    for (int i = 0; i < (kLkWin * kLkWin + 31) / 32; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < kLkWin * kLkWin) {
+        const int ry = idx / kLkWin, rx = idx - ry * kLkWin;
+        const int y = Y0 + ry, x = X0 + rx;
+        float v = 0.0f;
+        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(base + static_cast<long long>(y) * pitch + x);
+        win[wq][l][idx] = v;
+      }
+    }
+  }
+  __syncwarp();
+
+  // 3. blend: channel ch = l * 81 + a * 9 + b  (a offsets x, b offsets y -- corr.py:40-46)
+  for (int c2 = lane; c2 < 162; c2 += 32) {
+    float val[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ch = c2 * 2 + j;
+      const int l = ch / 81, t = ch - l * 81, a = t / 9, b = t - a * 9;
+      const int x0 = cin[wq][l * 18 + a], y0 = cin[wq][l * 18 + 9 + b];
+      const float fx = cfr[wq][l * 18 + a], fy = cfr[wq][l * 18 + 9 + b];
+      const int wx = x0 - org[wq][2 * l], wy = y0 - org[wq][2 * l + 1];
+      float v00, v01, v10, v11;
+      if (wx >= 0 && wx + 1 < kLkWin && wy >= 0 && wy + 1 < kLkWin) {
+        const float* wp = &win[wq][l][wy * kLkWin + wx];
+        v00 = wp[0]; v01 = wp[1]; v10 = wp[kLkWin]; v11 = wp[kLkWin + 1];
+      } else {   // not reachable for finite coordinates near the image; kept exact for robustness
+        const int H = p.h[l], W = p.w[l], pitch = p.pitch[l];
+        const float* base = p.lvl[l] + q * static_cast<long long>(H) * pitch;
+        const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
+        const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
+        const float* r0 = base + static_cast<long long>(y0) * pitch + x0;
+        v00 = (xin0 && yin0) ? __ldg(r0) : 0.0f;
+        v01 = (xin1 && yin0) ? __ldg(r0 + 1) : 0.0f;
+        v10 = (xin0 && yin1) ? __ldg(r0 + pitch) : 0.0f;
+        v11 = (xin1 && yin1) ? __ldg(r0 + pitch + 1) : 0.0f;
+      }
+      val[j] = v00 * ((1.0f - fx) * (1.0f - fy)) + v01 * (fx * (1.0f - fy)) + v10 * ((1.0f - fx) * fy) + v11 * (fx * fy);
+    }
+    if (out16) *reinterpret_cast<__half2*>(out16 + q * out_pitch + c2 * 2) = __floats2half2_rn(val[0], val[1]);
+    if (out32) *reinterpret_cast<float2*>(out32 + q * 324 + c2 * 2) = make_float2(val[0], val[1]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // im2col for the two 7x7 layers whose input has 3 / 2 channels (too thin for a 64-channel K chunk)
 // ------------------------------------------------------------------------------------------------
-__global__ void stem_im2col_kernel(const float* __restrict__ img, __half* __restrict__ rows, long long pitch, int B,
-                                   int H, int W, int OH, int OW) {
-  const long long total = static_cast<long long>(B) * OH * OW * pitch;
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, __half* __restrict__ rows,
+                                                          long long pitch, int B, int H, int W, int OH, int OW) {
+  const int groups = static_cast<int>(pitch >> 3);               // 16-byte groups per row (pitch is a multiple of 8)
+  const long long total = static_cast<long long>(B) * OH * OW * groups;
+  const long long plane = static_cast<long long>(H) * W;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(idx % pitch);
-    const long long pix = idx / pitch;
-    float v = 0.0f;
-    if (k < 147) {
-      const int c = k % 3, tap = k / 3, dy = tap / 7, dx = tap - dy * 7;
-      const int ox = static_cast<int>(pix % OW);
-      const long long t = pix / OW;
-      const int oy = static_cast<int>(t % OH), b = static_cast<int>(t / OH);
-      const int iy = oy * 2 + dy - 3, ix = ox * 2 + dx - 3;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        const float x = __ldg(img + ((static_cast<long long>(b) * 3 + c) * H + iy) * W + ix);
-        v = 2.0f * (x / 255.0f) - 1.0f;        // network.py:75-76
+    const int g = static_cast<int>(idx % groups);
+    const long long pix = idx / groups;
+    const int ox = static_cast<int>(pix % OW);
+    const long long t = pix / OW;
+    const int oy = static_cast<int>(t % OH), b = static_cast<int>(t / OH);
+    const float* im = img + static_cast<long long>(b) * 3 * plane;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float x = 0.0f;
+      if (k < 147) {
+        const int tap = k / 3, c = k - tap * 3, dy = tap / 7, dx = tap - dy * 7;
+        const int iy = oy * 2 + dy - 3, ix = ox * 2 + dx - 3;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) x = 2.0f * (__ldg(im + c * plane + static_cast<long long>(iy) * W + ix) / 255.0f) - 1.0f;   // network.py:75-76
       }
+      v[j] = x;
     }
-    rows[idx] = __float2half_rn(v);
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2);
+    u.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(rows + pix * pitch + g * 8) = u;
   }
 }
 
@@ -150,20 +220,28 @@ __global__ void __launch_bounds__(256) inorm_partial_kernel(const __half* __rest
   }
 }
 
-__global__ void inorm_finalize_kernel(const float* __restrict__ scratch, int parts, int C, int HW,
-                                      float* __restrict__ stats) {
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s = 0.0, ss = 0.0;
-    for (int p = 0; p < parts; ++p) {
-      s += scratch[((static_cast<long long>(b) * parts + p) * C + c) * 2];
-      ss += scratch[((static_cast<long long>(b) * parts + p) * C + c) * 2 + 1];
-    }
+// one warp per (image, channel): lanes stride over the partial sums in a fixed order, fixed shuffle tree
+__global__ void __launch_bounds__(256) inorm_finalize_kernel(const float* __restrict__ scratch, int parts, int C, int HW,
+                                                             int BC, float* __restrict__ stats) {
+  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= BC) return;
+  const int b = wid / C, c = wid - b * C;
+  double s = 0.0, ss = 0.0;
+  for (int p = lane; p < parts; p += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(scratch + ((static_cast<long long>(b) * parts + p) * C + c) * 2);
+    s += v.x;
+    ss += v.y;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (lane == 0) {
     const double mean = s / HW;
     double var = ss / HW - mean * mean;   // biased variance, as nn.InstanceNorm2d
     if (var < 0.0) var = 0.0;
-    stats[(static_cast<long long>(b) * C + c) * 2] = static_cast<float>(mean);
-    stats[(static_cast<long long>(b) * C + c) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+    stats[static_cast<long long>(wid) * 2] = static_cast<float>(mean);
+    stats[static_cast<long long>(wid) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + 1e-5));
   }
 }
 
@@ -410,8 +488,9 @@ extern "C" int atdn_corr_lookup(const float* const lvl[4], const int32_t lvl_pit
     w /= 2;
   }
   const long long nq = static_cast<long long>(batch) * h8 * w8;
-  corr_lookup_kernel<<<static_cast<unsigned>(nq), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, coords, static_cast<__half*>(out16), out_pitch, out32);
+  ATDN_REQUIRE(!out16 || (out_pitch % 2 == 0 && (reinterpret_cast<uintptr_t>(out16) & 3u) == 0), ATDN_ERR_ALIGN, "atdn_corr_lookup: out16 must be 4-byte aligned with an even pitch");
+  corr_lookup_kernel<<<static_cast<unsigned>((nq + kLkWarps - 1) / kLkWarps), kLkWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, coords, static_cast<__half*>(out16), out_pitch, out32, nq);
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -419,9 +498,9 @@ extern "C" int atdn_corr_lookup(const float* const lvl[4], const int32_t lvl_pit
 extern "C" int atdn_stem_im2col(const float* image, void* rows16, int64_t pitch, int32_t batch, int32_t h, int32_t w,
                                 void* stream) {
   if (int e = require_sm100()) return e;
-  ATDN_REQUIRE(image && rows16 && pitch >= 147 && h % 2 == 0 && w % 2 == 0, ATDN_ERR_ARG, "atdn_stem_im2col: bad arguments");
+  ATDN_REQUIRE(image && rows16 && pitch >= 147 && pitch % 8 == 0 && aligned16(rows16) && h % 2 == 0 && w % 2 == 0, ATDN_ERR_ARG, "atdn_stem_im2col: bad arguments");
   const int oh = h / 2, ow = w / 2;
-  const long long total = static_cast<long long>(batch) * oh * ow * pitch;
+  const long long total = static_cast<long long>(batch) * oh * ow * (pitch / 8);
   stem_im2col_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       image, static_cast<__half*>(rows16), pitch, batch, h, w, oh, ow);
   ATDN_CUDA(cudaGetLastError());
@@ -447,7 +526,7 @@ extern "C" int atdn_inorm_stats(const void* x16, int64_t pitch, int32_t batch, i
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   inorm_partial_kernel<<<dim3(parts, batch), 256, 0, s>>>(static_cast<const __half*>(x16), pitch, hw, c, parts, scratch);
   ATDN_CUDA(cudaGetLastError());
-  inorm_finalize_kernel<<<batch, 128, 0, s>>>(scratch, parts, c, hw, stats);
+  inorm_finalize_kernel<<<(batch * c + 7) / 8, 256, 0, s>>>(scratch, parts, c, hw, batch * c, stats);
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }

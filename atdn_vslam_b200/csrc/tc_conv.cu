@@ -338,6 +338,7 @@ static int dispatch_conv(int mt, int bn, const ConvParams& p, int smem, cudaStre
   if (mt == 2 && bn == 96) return launch_conv<2, 96, EPI, PAIR>(p, smem, s);
   if (mt == 2 && bn == 64) return launch_conv<2, 64, EPI, PAIR>(p, smem, s);
   if (mt == 4 && bn == 64) return launch_conv<4, 64, EPI, PAIR>(p, smem, s);
+  if (mt == 4 && bn == 32) return launch_conv<4, 32, EPI, PAIR>(p, smem, s);
   return set_error(ATDN_ERR_UNSUP, "atdn_tc_gemm: halo conv kernel has no (mt=%d, bn=%d) instance", mt, bn);
 }
 template <int EPI>
@@ -370,6 +371,8 @@ int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream) {
   p.e.rh16 = static_cast<__half*>(d->rh16);
   p.e.aux32 = d->aux32;
   p.e.gamma = d->gamma;
+  p.e.img_w = d->out_w;
+  p.e.img_h = d->out_h;
   p.stamps = reinterpret_cast<long long*>(d->lvl[2]);   // timing experiments only (normally null)
 
   const int box_w = kSubW * mt + d->taps_w - 1, box_h = kSubH + d->taps_h - 1;
@@ -432,6 +435,9 @@ int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream) {
     case ATDN_EPI_GRU_Q:
       ATDN_REQUIRE(d->n_valid == 128 && d->h32 && d->z32 && d->out, ATDN_ERR_ARG, "atdn_tc_gemm: GRU_Q arguments");
       return dispatch_conv<ATDN_EPI_GRU_Q>(pair, mt, bn, p, smem, stream);
+    case ATDN_EPI_FLOW:
+      ATDN_REQUIRE(d->n_valid == 2 && bn == 32 && mt == 4 && !pair && d->h32 && d->z32, ATDN_ERR_ARG, "atdn_tc_gemm: FLOW arguments (n_valid 2, mt 4, bn 32, no pair)");
+      return launch_conv<4, 32, ATDN_EPI_FLOW, false>(p, smem, stream);
     default:
       return set_error(ATDN_ERR_UNSUP, "atdn_tc_gemm: epilogue %d is not available in the halo conv kernel", d->epi);
   }

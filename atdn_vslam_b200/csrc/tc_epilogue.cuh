@@ -24,6 +24,7 @@ struct EpiParams {
   __half* rh16;
   const float* aux32;
   const float* gamma;
+  int img_w, img_h;   // FLOW: output image size (pixel coordinates of `pix`)
 };
 
 // 1/(1+e^-x) and tanh through MUFU.EX2 + MUFU.RCP: ~1e-6 relative, far below the fp16 operand rounding (5e-4)
@@ -185,6 +186,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n);
 #pragma unroll
     for (int g = 0; g < 4; ++g) dst[g] = pack8_f16(&y[g * 8]);
+  } else if constexpr (EPI == ATDN_EPI_FLOW) {
+    if (n == 0) {
+      float2* c1 = reinterpret_cast<float2*>(p.h32) + pix;
+      const float2 c = *c1;
+      const int xw = static_cast<int>(pix % p.img_w);
+      const int yh = static_cast<int>((pix / p.img_w) % p.img_h);
+      const float cxn = c.x + y[0], cyn = c.y + y[1];
+      *c1 = make_float2(cxn, cyn);
+      reinterpret_cast<float2*>(p.z32)[pix] = make_float2(cxn - static_cast<float>(xw), cyn - static_cast<float>(yh));
+    }
   } else if constexpr (EPI == ATDN_EPI_PV) {
     const float scale = p.aux32[pix] * __ldg(p.gamma);
     const uint4* rp = reinterpret_cast<const uint4*>(p.resid + pix * p.resid_pitch + p.resid_ch_off + n);

@@ -158,8 +158,8 @@ class _Packed:
             wq, bq = g("gru.convq" + n)
             self.gru.append((_Conv(torch.cat([wz, wr], 0), torch.cat([bz, br], 0)), _Conv(wq, bq)))
         self.fh1 = _Conv(*g("flow_head.conv1"))
-        self.fh2_w = sd[u + "flow_head.conv2.weight"].float().contiguous()
-        self.fh2_b = sd[u + "flow_head.conv2.bias"].float().contiguous()
+        w2, b2 = g("flow_head.conv2")                  # 3x3, 256 -> 2: zero-padded to one 32-column MMA tile
+        self.fh2 = _Conv(torch.cat([w2.float(), torch.zeros(30, *w2.shape[1:], device=w2.device)], 0), b2)
         self.mask0 = _Conv(*g("mask.0"))
         self.mask2 = _Conv(*g("mask.2"))
         self.gamma = sd[u + "aggregator.gamma"].float().contiguous()
@@ -428,7 +428,7 @@ class RAFTGMA(nn.Module):
         d.out, d.out_pitch = L.ptr(plan.vt), np_
         L.tc_gemm(d)
         ops.gemm_rows(L.ptr(plan.p16), n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
-                      b_bstride=128 * np_, bn=64, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
+                      b_bstride=128 * np_, bn=128, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
                       aux32=plan.inv_sum, gamma=wts.gamma)
         for (zr, q), taps, pad in ((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0))):
             _conv_s1(View(hx), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, h32=plan.h32, z32=plan.z32, rh16=plan.rh)
@@ -436,7 +436,9 @@ class RAFTGMA(nn.Module):
                      h32=plan.h32, z32=plan.z32)
         c = wts.fh1
         _conv_s1(View(hx, 0, 128), c, View(plan.fh), cout=256, taps=(3, 3), flags=R)
-        ops.flow_head_update(View(plan.fh), wts.fh2_w, wts.fh2_b, plan.coords1, plan.flow)
+        c = wts.fh2   # flow_head.conv2 + coords update (network.py:111,116) in the conv epilogue
+        ops.conv_tc(View(plan.fh), c.wp, c.bias, None, cout=2, taps=(3, 3), pad=(1, 1), bn=32, mt=4, epi=L.EPI_FLOW,
+                    h32=plan.coords1, z32=plan.flow)
 
 
 class CorrBlock:

@@ -14,6 +14,19 @@ import torch
 from . import _lib as L
 
 
+def _profiled(fn):
+    """When bench.py installs L.PROFILER, time this op's launches with CUDA events under the op's name."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **kw):
+        if L.PROFILER is None:
+            return fn(*a, **kw)
+        with L.PROFILER(fn.__name__, 0.0, 0.0):
+            return fn(*a, **kw)
+    return wrapper
+
+
 class View:
     """Channels [c0, c0+c) of an NHWC buffer ``t`` of shape [B, H, W, pitch]."""
 
@@ -195,23 +208,27 @@ def corr_lookup(levels, coords, out16=None, out32=None):
 # ----------------------------------------------------------------------------------------------
 # element-wise
 # ----------------------------------------------------------------------------------------------
+@_profiled
 def stem_im2col(image, rows):
     b, _, h, w = image.shape
     L.check(L.load().atdn_stem_im2col(L.ptr(image), L.ptr(rows), C.c_int64(rows.shape[-1]), b, h, w, L.stream_ptr()),
             "atdn_stem_im2col")
 
 
+@_profiled
 def flow_im2col(flow, rows):
     b, h8, w8, _ = flow.shape
     L.check(L.load().atdn_flow_im2col(L.ptr(flow), L.ptr(rows), C.c_int64(rows.shape[-1]), b, h8, w8, L.stream_ptr()),
             "atdn_flow_im2col")
 
 
+@_profiled
 def inorm_stats(x, scratch, parts, stats):
     L.check(L.load().atdn_inorm_stats(x.ptr(), C.c_int64(x.pitch), x.B, x.H * x.W, x.c, L.ptr(scratch), parts,
                                       L.ptr(stats), L.stream_ptr()), "atdn_inorm_stats", 2)
 
 
+@_profiled
 def inorm_apply(x, stats, y, resid=None, relu=True):
     L.check(L.load().atdn_inorm_apply(x.ptr(), C.c_int64(x.pitch), L.ptr(stats),
                                       resid.ptr() if resid is not None else None,
@@ -219,22 +236,26 @@ def inorm_apply(x, stats, y, resid=None, relu=True):
                                       x.B, x.H * x.W, x.c, int(relu), L.stream_ptr()), "atdn_inorm_apply")
 
 
+@_profiled
 def softmax_rows(s32, p16, inv_sum, rows, cols):
     L.check(L.load().atdn_softmax_rows(L.ptr(s32), C.c_int64(s32.shape[-1]), L.ptr(p16), C.c_int64(p16.shape[-1]),
                                        L.ptr(inv_sum), C.c_int64(rows), cols, L.stream_ptr()), "atdn_softmax_rows")
 
 
+@_profiled
 def flow_head_update(x, w, bias, coords1, flow):
     L.check(L.load().atdn_flow_head_update(x.ptr(), C.c_int64(x.pitch), L.ptr(w), L.ptr(bias), L.ptr(coords1),
                                            L.ptr(flow), x.B, x.H, x.W, L.stream_ptr()), "atdn_flow_head_update")
 
 
+@_profiled
 def convex_upsample(mask32, flow, flow_up, flow_lo=None):
     b, h8, w8, _ = flow.shape
     L.check(L.load().atdn_convex_upsample(L.ptr(mask32), C.c_int64(mask32.shape[-1]), L.ptr(flow), L.ptr(flow_up),
                                           L.ptr(flow_lo), b, h8, w8, L.stream_ptr()), "atdn_convex_upsample")
 
 
+@_profiled
 def coords_init(coords1, flow, flow_init=None):
     b, h8, w8, _ = coords1.shape
     L.check(L.load().atdn_coords_init(L.ptr(coords1), L.ptr(flow), L.ptr(flow_init), b, h8, w8, L.stream_ptr()),
@@ -244,6 +265,7 @@ def coords_init(coords1, flow, flow_init=None):
 # ----------------------------------------------------------------------------------------------
 # fp32 small nets
 # ----------------------------------------------------------------------------------------------
+@_profiled
 def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shift=None, skip=None, bn_scale=None,
            bn_shift=None, bn2_scale=None, bn2_shift=None):
     d = L.Conv32Desc()
@@ -257,16 +279,19 @@ def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shif
     L.check(L.load().atdn_conv32(C.byref(d), L.stream_ptr()), "atdn_conv32")
 
 
+@_profiled
 def linear32(x, w, bias, y, act=0):
     L.check(L.load().atdn_linear32(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(y), x.shape[0], w.shape[1], w.shape[0], act,
                                    L.stream_ptr()), "atdn_linear32")
 
 
+@_profiled
 def lstm_cell(x, w_ih, w_hh, b_ih, b_hh, h, c, gates):
     L.check(L.load().atdn_lstm_cell(L.ptr(x), L.ptr(w_ih), L.ptr(w_hh), L.ptr(b_ih), L.ptr(b_hh), L.ptr(h), L.ptr(c),
                                     L.ptr(gates), x.shape[0], w_ih.shape[1], h.shape[1], L.stream_ptr()), "atdn_lstm_cell", 2)
 
 
+@_profiled
 def keyframe_search(emb, code, dist, index):
     L.check(L.load().atdn_keyframe_search(L.ptr(emb), L.ptr(code), L.ptr(dist), L.ptr(index), C.c_int64(emb.shape[0]),
                                           emb.shape[1], L.stream_ptr()), "atdn_keyframe_search", 2)

@@ -65,7 +65,10 @@ enum {
   ATDN_EPI_CORR    = 2, /* corr pyramid: level0 = alpha*acc, levels 1..3 = 2x2 means, fp32 (corr.py:16-30)              */
   ATDN_EPI_GRU_ZR  = 3, /* n<128: z32 = sigmoid(acc+b); n>=128: rh16 = sigmoid(acc+b) * h32   (update.py:51-53,58-60)   */
   ATDN_EPI_GRU_Q   = 4, /* q = tanh(acc+b); h32 = (1-z)*h32 + z*q; out16 = h32               (update.py:53-54,60-61)   */
-  ATDN_EPI_PV      = 5  /* out16 = resid16 + gamma * acc * row_scale[pix]                    (gma.py:107-113)           */
+  ATDN_EPI_PV      = 5, /* out16 = resid16 + gamma * acc * row_scale[pix]                    (gma.py:107-113)           */
+  ATDN_EPI_FLOW    = 6  /* halo kernel only, n_valid = 2 (weights zero-padded to 32 rows): delta = acc + bias;
+                           coords1[pix] += delta; flow[pix] = coords1[pix] - (x, y); coords1 = h32, flow = z32
+                           (update.py:14 flow_head.conv2 + network.py:111,116)                                           */
 };
 
 enum {
@@ -113,8 +116,8 @@ typedef struct atdn_tc_desc {
   /* mt > 0 selects the persistent halo-reuse convolution kernel (PATCH A, stride 1): one CTA owns
    * `mt` side-by-side sub-tiles of 16 x 8 output pixels, stages one (16+kh-1) x (8*mt+kw-1) input box per
    * 64-channel chunk and reads every filter tap as a shifted view of it; mt * bn <= 256 (two TMEM
-   * accumulator buffers).  Instances: (mt, bn) = (1,256) (1,192) (1,128) (2,128) (2,96) (2,64) (4,64);
-   * epilogues STORE16, STORE32, GRU_ZR (bn 128), GRU_Q.  mt = 0: one 8 x 16 pixel tile per CTA.       */
+   * accumulator buffers).  Instances: (mt, bn) = (1,256) (1,192) (1,128) (2,128) (2,96) (2,64) (4,64) (4,32);
+   * epilogues STORE16, STORE32, GRU_ZR, GRU_Q, FLOW (bn 32).  mt = 0: one 8 x 16 pixel tile per CTA.       */
   int32_t mt;
 } atdn_tc_desc;
 

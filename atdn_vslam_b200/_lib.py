@@ -18,7 +18,7 @@ EXPORTS = (
     "atdn_last_error", "atdn_version", "atdn_check_device", "atdn_tc_gemm", "atdn_corr_lookup",
     "atdn_stem_im2col", "atdn_flow_im2col", "atdn_inorm_stats", "atdn_inorm_apply", "atdn_softmax_rows",
     "atdn_flow_head_update", "atdn_convex_upsample", "atdn_coords_init", "atdn_conv32", "atdn_linear32",
-    "atdn_lstm_cell", "atdn_keyframe_search",
+    "atdn_lstm_cell", "atdn_keyframe_search", "atdn_attn_probs",
 )
 
 

@@ -12,7 +12,8 @@ Data layout in HBM (per batch of B pairs, 1/8-resolution grid H8 x W8, N = H8*W8
                           torch.cat([net, inp, mf, mfg]) materialised once, never copied)
   h32 [B*N,128]    fp32 master copy of the hidden state (recurrent precision)
   corr pyramid     fp32 [B*N, H_l, pitch_l] for l = 0..3 (pitch = W_l rounded up to 4)
-  P   [B,N,Np]     fp16 un-normalised attention probabilities exp(s - max), Np = N rounded up to 64;
+  P   [B,N,Np]     fp16 un-normalised attention probabilities exp(s - max), Np = N rounded up to 64
+                   (written by the fused q.k^T/softmax kernel: the fp32 logits never reach HBM);
   inv_sum [B*N]    fp32 1/sum(P) applied in the P.V epilogue
   coords1, flow    fp32 [B,H8,W8,2]
 """
@@ -188,7 +189,6 @@ class _Plan:
         self.rh = f16(b, h8, w8, 128)
         self.pyr = ops.alloc_pyramid(b, h8, w8, dev)
         self.qk = f16(b, h8, w8, 256)
-        self.s32 = f32(b, n, self.np_)
         self.p16 = f16(b, n, self.np_)
         self.inv_sum = f32(b * n)
         self.vt = f16(b, 128, self.np_)
@@ -369,9 +369,7 @@ class RAFTGMA(nn.Module):
 
         # attention (gma.py:54-76): q.k^T * scale -> softmax
         _conv_s1(View(hx, 128, 128), wts.to_qk, View(plan.qk), cout=256, taps=(1, 1))
-        ops.gemm_rows(L.ptr(plan.qk), 128, n, 256, b, L.ptr(plan.qk, 128), n, 256, L.ptr(plan.s32), np_, n_valid=n,
-                      b_bstride=n * 256, bn=128, epi=L.EPI_STORE32, alpha=128 ** -0.5)
-        ops.softmax_rows(plan.s32, plan.p16, plan.inv_sum, b * n, n)
+        ops.attn_probs(plan.qk, plan.p16, plan.inv_sum, 128 ** -0.5)
 
         if flow_init is not None:
             flow_init = flow_init.float().contiguous()

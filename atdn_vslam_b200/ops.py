@@ -242,6 +242,22 @@ def softmax_rows(s32, p16, inv_sum, rows, cols):
                                        L.ptr(inv_sum), C.c_int64(rows), cols, L.stream_ptr()), "atdn_softmax_rows")
 
 
+def attn_probs(qk, p16, inv_sum, scale):
+    """qk fp16 [B,H8,W8,256] (q | k) -> p16 [B,N,Np] un-normalised probabilities, inv_sum [B*N] (gma.py:66-73)."""
+    b, h8, w8, pitch = qk.shape
+    n = h8 * w8
+
+    def go():
+        L.check(L.load().atdn_attn_probs(L.ptr(qk), C.c_int64(pitch), L.ptr(p16), C.c_int64(p16.shape[-1]), L.ptr(inv_sum),
+                                         b, n, C.c_float(scale), L.stream_ptr()), "atdn_attn_probs")
+    if L.PROFILER is not None:
+        # algorithmic: one q.k^T (2*N*N*128 flop) and N*N fp16 probabilities written per image
+        with L.PROFILER("attn_probs", 2.0 * b * n * n * 128, 2.0 * b * n * n):
+            go()
+        return
+    go()
+
+
 @_profiled
 def flow_head_update(x, w, bias, coords1, flow):
     L.check(L.load().atdn_flow_head_update(x.ptr(), C.c_int64(x.pitch), L.ptr(w), L.ptr(bias), L.ptr(coords1),

@@ -124,6 +124,18 @@ typedef struct atdn_tc_desc {
 int atdn_tc_gemm(const atdn_tc_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused attention probabilities -- GMA.whl!/GMA/core/gma.py:66-73 (q k^T * scale, softmax over keys);
+ * replaces cuBLAS batched GEMM + softmax.  qk16: fp16 [batch, n, qk_pitch] with q in channels 0..127 and k
+ * in channels 128..255 (the to_qk 1x1 conv output).  The logits never reach HBM: every key tile goes
+ * through tcgen05 twice (row maxima, then probabilities).
+ *   p16[b, i, j]  = exp((q_i . k_j - max_j q_i . k_j) * scale)   fp16, un-normalised, j < n; columns [n, ceil8(n)) are
+ *                   written as zeros (16-byte store granularity), the rest of the row pad is untouched
+ *   inv_sum[b, i] = 1 / sum_j p16[b, i, j]                       fp32
+ * ---------------------------------------------------------------------------------------------- */
+int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, int64_t p_pitch, float* inv_sum,
+                    int32_t batch, int32_t n, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Correlation lookup -- GMA.whl!/GMA/core/corr.py:32-53 + utils/utils.py:59-73 (grid_sample).
  * coords: fp32 [B, H8, W8, 2] (x, y); levels as written by ATDN_EPI_CORR;
  * out: fp16 [B*H8*W8, out_pitch], channel = level*81 + a*9 + b  (a offsets x, b offsets y).

@@ -284,7 +284,47 @@ def bench_gru(pair, bn, kind="zr", batch=6, h=47, w=154, reps=20):
     return True
 
 
+def check_attn(n=1000, batch=2, reps=0):
+    """atdn_attn_probs vs fp32 torch on the same fp16 q/k: P within one fp16 rounding, 1/rowsum 1e-4."""
+    import torch
+    from atdn_vslam_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    h8 = 1
+    qk = (torch.randn(batch, h8, n, 256, generator=g) * 1.5).half().cuda()
+    np_ = (n + 63) // 64 * 64
+    p16 = torch.full((batch, n, np_), float("nan"), dtype=torch.half, device="cuda")
+    inv = torch.full((batch * n,), float("nan"), dtype=torch.float32, device="cuda")
+    scale = 128 ** -0.5
+    ops.attn_probs(qk, p16, inv, scale)
+    torch.cuda.synchronize()
+    q, k = qk[:, 0, :, :128].float(), qk[:, 0, :, 128:].float()
+    s = torch.matmul(q, k.transpose(1, 2)) * scale
+    pref = torch.exp(s - s.max(dim=2, keepdim=True).values)
+    ok = _cmp(f"attn P n={n} batch={batch}", p16[:, :, :n], pref, 1.5e-3)
+    n8 = (n + 7) // 8 * 8          # TMA store clipping is 16-byte granular: columns [n, n8) are written as zeros
+    ok &= bool((p16[:, :, n:n8] == 0).all()) and bool(torch.isnan(p16[:, :, n8:]).all())
+    isum = 1.0 / p16[:, :, :n].float().sum(2).reshape(-1)
+    ok &= _cmp("attn inv_sum", inv, isum, 1e-4)
+    ok &= _cmp("attn softmax", p16[:, :, :n].float() * inv.view(batch, n, 1), torch.softmax(s, 2), 2e-3)
+    if reps:
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            ops.attn_probs(qk, p16, inv, scale)
+        s1.record()
+        torch.cuda.synchronize()
+        ms = s0.elapsed_time(s1) / reps
+        print(f"TIME attn_probs n={n} batch={batch}: {ms:.3f} ms  ({2.0 * batch * n * n / ms / 1e6:.0f} GB/s of P written, "
+              f"{2 * 2.0 * batch * n * n * 128 / ms / 1e9:.0f} TFLOP/s issued)", flush=True)
+    return ok
+
+
 CHECKS = {
+    "attn_small": lambda: check_attn(),
+    "attn_tiny": lambda: check_attn(n=256, batch=1),
+    "attn_one_tile_plus": lambda: check_attn(n=300, batch=3),
+    "attn_full": lambda: check_attn(n=7238, batch=2),
+    "time_attn": lambda: check_attn(n=7238, batch=27, reps=5),
     "halo_conv3x3_mt1": lambda: check_conv(cin=64, cout=128, bn=128, mt=1),
     "halo_conv3x3_mt2": lambda: check_conv(cin=128, cout=256, bn=128, mt=2, relu=True),
     "halo_conv3x3_mt4": lambda: check_conv(cin=64, cout=64, bn=64, mt=4, relu=True, resid=True, h=50, w=70),

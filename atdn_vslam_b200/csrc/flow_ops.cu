@@ -120,32 +120,46 @@ __global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_kernel(LookupParams
 }
 
 // ------------------------------------------------------------------------------------------------
-// im2col for the two 7x7 layers whose input has 3 / 2 channels (too thin for a 64-channel K chunk)
+// The two 7x7 layers whose input has 3 / 2 channels (too thin for a 64-channel K chunk) run on the halo
+// implicit-GEMM kernel after folding the horizontal taps into channels ("row packing"): the packed tensor is
+// 3.2x (stem) / 6.5x (flow) smaller than a full im2col matrix and the vertical taps stay implicit.
+//
+// Stem (extractor.py:173, 7x7 stride 2 pad 3 on the normalised image, network.py:75-76):
+//   X[b, y2, ox, (ry*3 + c)*8 + xx] = 2*(img[b, c, 2*y2 + ry, 2*(ox-2) + xx]/255) - 1   (0 outside the image)
+//   out[oy, ox] = sum_{ai<4} sum_ch W4[ai, ch] X[oy + ai - 2, ox, ch],  W4[ai, (ry,c,xx)] = w[c, 2*ai+ry-1, xx-1]
+// i.e. a 4x1 convolution with 48 input channels, top padding 2 (rows past the image are TMA zero fill).
+// One thread = one 16-byte group of 8 consecutive xx = 8 consecutive image pixels of one (row, plane).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ img, __half* __restrict__ rows,
-                                                          long long pitch, int B, int H, int W, int OH, int OW) {
-  const int groups = static_cast<int>(pitch >> 3);               // 16-byte groups per row (pitch is a multiple of 8)
-  const long long total = static_cast<long long>(B) * OH * OW * groups;
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ img, __half* __restrict__ x, int B, int H,
+                                                        int W, int OH, int OW) {
+  const long long total = static_cast<long long>(B) * OH * OW * 6;
   const long long plane = static_cast<long long>(H) * W;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx % groups);
-    const long long pix = idx / groups;
+    const int g = static_cast<int>(idx % 6);
+    const long long pix = idx / 6;
     const int ox = static_cast<int>(pix % OW);
     const long long t = pix / OW;
-    const int oy = static_cast<int>(t % OH), b = static_cast<int>(t / OH);
-    const float* im = img + static_cast<long long>(b) * 3 * plane;
+    const int y2 = static_cast<int>(t % OH), b = static_cast<int>(t / OH);
+    const int ry = g / 3, c = g - ry * 3;
+    const float* row = img + (static_cast<long long>(b) * 3 + c) * plane + static_cast<long long>(2 * y2 + ry) * W;
+    const int x0 = 2 * ox - 4;
     float v[8];
+    if (x0 >= 0 && x0 + 8 <= W) {   // x0 is even: 8-byte aligned pairs (W is even)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      float x = 0.0f;
-      if (k < 147) {
-        const int tap = k / 3, c = k - tap * 3, dy = tap / 7, dx = tap - dy * 7;
-        const int iy = oy * 2 + dy - 3, ix = ox * 2 + dx - 3;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) x = 2.0f * (__ldg(im + c * plane + static_cast<long long>(iy) * W + ix) / 255.0f) - 1.0f;   // network.py:75-76
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __ldg(reinterpret_cast<const float2*>(row + x0) + j);
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
       }
-      v[j] = x;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 2.0f * (v[j] / 255.0f) - 1.0f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ix = x0 + j;
+        v[j] = (ix >= 0 && ix < W) ? 2.0f * (__ldg(row + ix) / 255.0f) - 1.0f : 0.0f;
+      }
     }
     __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
     __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
@@ -154,28 +168,35 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     u.y = *reinterpret_cast<uint32_t*>(&h1);
     u.z = *reinterpret_cast<uint32_t*>(&h2);
     u.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(rows + pix * pitch + g * 8) = u;
+    *reinterpret_cast<uint4*>(x + pix * 48 + g * 8) = u;
   }
 }
 
-__global__ void flow_im2col_kernel(const float* __restrict__ flow, __half* __restrict__ rows, long long pitch, int B,
-                                   int H, int W) {
-  const long long total = static_cast<long long>(B) * H * W * pitch;
+// Flow (update.py:79 convf1, 7x7 pad 3 on the 2-channel flow): X[b, y, x, dx*2 + c] = flow[b, y, x + dx - 3, c]
+// (14 channels + 2 zeros, 32 bytes per pixel); the 7 vertical taps stay implicit (7x1 convolution, pad 3).
+__global__ void __launch_bounds__(256) flow_pack_kernel(const float* __restrict__ flow, __half* __restrict__ x, int B, int H,
+                                                        int W) {
+  const long long total = static_cast<long long>(B) * H * W * 2;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(idx % pitch);
-    const long long pix = idx / pitch;
-    float v = 0.0f;
-    if (k < 98) {
-      const int c = k & 1, tap = k >> 1, dy = tap / 7, dx = tap - dy * 7;
-      const int x = static_cast<int>(pix % W);
-      const long long t = pix / W;
-      const int y = static_cast<int>(t % H), b = static_cast<int>(t / H);
-      const int iy = y + dy - 3, ix = x + dx - 3;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-        v = __ldg(flow + ((static_cast<long long>(b) * H + iy) * W + ix) * 2 + c);
+    const int g = static_cast<int>(idx & 1);   // dx 0..3 | dx 4..6 + pad
+    const long long pix = idx >> 1;
+    const int xw = static_cast<int>(pix % W);
+    const float2* row = reinterpret_cast<const float2*>(flow) + (pix - xw);
+    float2 f[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int dx = g * 4 + j, ix = xw + dx - 3;
+      f[j] = (dx < 7 && ix >= 0 && ix < W) ? __ldg(row + ix) : make_float2(0.0f, 0.0f);
     }
-    rows[idx] = __float2half_rn(v);
+    __half2 h0 = __floats2half2_rn(f[0].x, f[0].y), h1 = __floats2half2_rn(f[1].x, f[1].y);
+    __half2 h2 = __floats2half2_rn(f[2].x, f[2].y), h3 = __floats2half2_rn(f[3].x, f[3].y);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2);
+    u.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(x + pix * 16 + g * 8) = u;
   }
 }
 
@@ -495,25 +516,22 @@ extern "C" int atdn_corr_lookup(const float* const lvl[4], const int32_t lvl_pit
   return 0;
 }
 
-extern "C" int atdn_stem_im2col(const float* image, void* rows16, int64_t pitch, int32_t batch, int32_t h, int32_t w,
-                                void* stream) {
+extern "C" int atdn_stem_pack(const float* image, void* x16, int32_t batch, int32_t h, int32_t w, void* stream) {
   if (int e = require_sm100()) return e;
-  ATDN_REQUIRE(image && rows16 && pitch >= 147 && pitch % 8 == 0 && aligned16(rows16) && h % 2 == 0 && w % 2 == 0, ATDN_ERR_ARG, "atdn_stem_im2col: bad arguments");
+  ATDN_REQUIRE(image && x16 && aligned16(x16) && (reinterpret_cast<uintptr_t>(image) & 7u) == 0 && h % 2 == 0 && w % 2 == 0 && w >= 8,
+               ATDN_ERR_ARG, "atdn_stem_pack: bad arguments (even h, w >= 8; 8-byte aligned image, 16-byte aligned output)");
   const int oh = h / 2, ow = w / 2;
-  const long long total = static_cast<long long>(batch) * oh * ow * (pitch / 8);
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      image, static_cast<__half*>(rows16), pitch, batch, h, w, oh, ow);
+  const long long total = static_cast<long long>(batch) * oh * ow * 6;
+  stem_pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, static_cast<__half*>(x16), batch, h, w, oh, ow);
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int atdn_flow_im2col(const float* flow, void* rows16, int64_t pitch, int32_t batch, int32_t h8, int32_t w8,
-                                void* stream) {
+extern "C" int atdn_flow_pack(const float* flow, void* x16, int32_t batch, int32_t h8, int32_t w8, void* stream) {
   if (int e = require_sm100()) return e;
-  ATDN_REQUIRE(flow && rows16 && pitch >= 98, ATDN_ERR_ARG, "atdn_flow_im2col: bad arguments");
-  const long long total = static_cast<long long>(batch) * h8 * w8 * pitch;
-  flow_im2col_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      flow, static_cast<__half*>(rows16), pitch, batch, h8, w8);
+  ATDN_REQUIRE(flow && x16 && aligned16(x16) && (reinterpret_cast<uintptr_t>(flow) & 7u) == 0, ATDN_ERR_ARG, "atdn_flow_pack: bad arguments");
+  const long long total = static_cast<long long>(batch) * h8 * w8 * 2;
+  flow_pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(flow, static_cast<__half*>(x16), batch, h8, w8);
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,328 @@
+// All-pairs correlation volume + 4-level average-pooled pyramid for sm_100a in one kernel
+// (GMA.whl!/GMA/core/corr.py:16-30 CorrBlock.__init__ and :55-63 CorrBlock.corr).
+//
+// The kernel is bound by the fp32 pyramid WRITE (4 N^2 * 1.33 bytes per pair; the MMA work is 13% of that in
+// time), so it is organised around the store path:
+//   * one CTA owns 128 query pixels (fmap1 rows, resident in shared memory) and streams the 8 x 32 target-pixel
+//     tiles of fmap2 through a TMA ring; the 512 TMEM columns hold two 128 x 256 accumulators so the MMA warp
+//     fills one while the epilogue drains the other;
+//   * epilogue warps (two groups of four, one group per accumulator) own one query per thread, scale the
+//     accumulator row, stage [32 queries x 32 targets] fp32 boxes in swizzled shared memory and hand them to
+//     TMA stores: every box row is a contiguous 128-byte run of one query's level-0 map, written by the TMA
+//     engine as full sectors (the previous per-thread float4 stores used 16 of every 32-byte sector and ran
+//     at 24% of the HBM roofline);
+//   * levels 1..3 are the hierarchical 2x2 means of corr.py:28-30 (floor semantics), accumulated in registers
+//     from the same accumulator rows and stored the same way (boxes of 16 / 8 / 4 floats per query);
+//   * TMA clipping against the true extents (W_l, H_l, N, batch) replaces every edge predicate.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.h"
+#include "tc_host.cuh"
+#include "tc_ptx.cuh"
+
+namespace atdn {
+
+constexpr int kCorrThreads = 384;
+constexpr int kCorrBStages = 3;                    // ring of 256 x 64 fp16 chunks of the target tile (32 KiB each)
+constexpr int kCorrABytes = 4 * 128 * 128;         // 128 queries x 256 channels
+constexpr int kCorrBStageBytes = 256 * 128;
+constexpr int kCorrSlotBytes = 32 * 128;           // one staging slot: 32 queries x 32 fp32
+constexpr int kCorrSmem = kCorrABytes + kCorrBStages * kCorrBStageBytes + 8 * 2 * kCorrSlotBytes + 1024;
+
+struct alignas(64) CorrParams {
+  CUtensorMap tmA, tmB, tmL[4];
+  int h, w, tiles_w, tiles;
+  float alpha;
+  int dbg;                // experiment switches (ATDN_CORR_DBG): 1 = no level 1..3 stores, 2 = no stores, 4 = LSU level-0 stores
+  float* l0;
+  int n, pitch0;
+};
+
+__global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __grid_constant__ CorrParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full, b_full[kCorrBStages], b_empty[kCorrBStages], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kCorrABytes;
+  uint8_t* smem_st = smem_b + kCorrBStages * kCorrBStageBytes;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int batch = blockIdx.y;
+  const int T = p.tiles;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&a_full, 1);
+    for (int s = 0; s < kCorrBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int l = 0; l < 4; ++l) tma_prefetch_desc(&p.tmL[l]);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(&a_full, kCorrABytes);
+      for (int c = 0; c < 4; ++c) tma_load_4d(smem_a + c * 128 * 128, &p.tmA, &a_full, c * 64, m0, 0, batch);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < T; ++t) {
+      const int bh0 = (t / p.tiles_w) * 8, bw0 = (t % p.tiles_w) * 32;
+      for (int c = 0; c < 4; ++c) {
+        mbar_wait(&b_empty[stage], phase ^ 1u);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&b_full[stage], kCorrBStageBytes);
+          tma_load_4d(smem_b + stage * kCorrBStageBytes, &p.tmB, &b_full[stage], c * 64, bw0, bh0, batch);
+        }
+        __syncwarp();
+        if (++stage == kCorrBStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t kIdesc = make_idesc_f16(128, 256);
+    const uint32_t a_u32 = smem_u32(smem_a), b_u32 = smem_u32(smem_b);
+    int stage = 0;
+    uint32_t phase = 0, pe0 = 0, pe1 = 0;
+    mbar_wait(&a_full, 0);
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      const uint32_t pe = buf ? pe1 : pe0;
+      mbar_wait(&acc_empty[buf], pe ^ 1u);
+      if (buf) pe1 ^= 1u; else pe0 ^= 1u;
+      tcgen05_fence_after();
+      const uint32_t d = tmem_base + static_cast<uint32_t>(buf * 256);
+      for (int c = 0; c < 4; ++c) {
+        mbar_wait(&b_full[stage], phase);
+        tcgen05_fence_after();
+        const uint64_t a_desc = make_smem_desc_sw128(a_u32 + c * 128 * 128);
+        const uint64_t b_desc = make_smem_desc_sw128(b_u32 + stage * kCorrBStageBytes);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(d, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (c | k) ? 1u : 0u);
+          umma_commit(&b_empty[stage]);
+          if (c == 3) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == kCorrBStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp & 3, g = (warp - 4) >> 2;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 256);
+    uint8_t* st_ptr = smem_st + (warp - 4) * 2 * kCorrSlotBytes;
+    const uint32_t st_u32 = smem_u32(st_ptr);
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const int H1 = p.h / 2, H2 = H1 / 2, H3 = H2 / 2;
+    const int qrow = m0 + q * 32;
+    uint32_t pf = 0;
+    int nstore = 0;
+
+    // staging slot ring: a slot is reused once the bulk store issued two stores ago has read it
+    auto acquire = [&]() -> int {
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      return (nstore & 1) * kCorrSlotBytes;
+    };
+    auto commit = [&](const CUtensorMap* m, int off, int c0, int c1) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(m, st_ptr + off, c0, c1, qrow, batch);
+        bulk_commit();
+      }
+      ++nstore;
+    };
+
+    for (int t = g; t < T; t += 2) {
+      const int bh0 = (t / p.tiles_w) * 8, bw0 = (t % p.tiles_w) * 32;
+      mbar_wait(&acc_full[g], pf);
+      pf ^= 1u;
+      tcgen05_fence_after();
+      float hs1[16];   // horizontal pair sums of the previous (even) level-0 row
+      float hs2[8];    // ... of the previous (even) level-1 row
+      float hs3[4];    // ... of the previous (even) level-2 row
+#pragma unroll
+      for (int hl = 0; hl < 8; ++hl) {
+        const int h = bh0 + hl;
+        if (h >= p.h) break;                       // warp-uniform; rows past the grid only feed non-existent pooled rows
+        uint32_t v[32];
+        tmem_ld_32x32(trow + hl * 32, v);
+        tmem_ld_wait();
+        float c[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) c[j] = p.alpha * __uint_as_float(v[j]);
+        if (p.dbg & 4) {
+          // LSU path: transpose through the swizzled slot, then 8 lanes write one 128-byte row segment
+          const int off = (nstore & 1) * kCorrSlotBytes;
+          ++nstore;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4),
+                         make_uint4(__float_as_uint(c[4 * ch]), __float_as_uint(c[4 * ch + 1]), __float_as_uint(c[4 * ch + 2]),
+                                    __float_as_uint(c[4 * ch + 3])));
+          __syncwarp();
+          const int chn = lane & 7, r0 = lane >> 3;
+          const bool colok = bw0 + chn * 4 < p.pitch0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 4 * i;
+            uint4 val;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(st_u32 + off + r * 128 + ((static_cast<uint32_t>(chn) ^ static_cast<uint32_t>(r & 7)) << 4)));
+            if (colok && qrow + r < p.n)
+              *reinterpret_cast<uint4*>(p.l0 + ((static_cast<long long>(batch) * p.n + qrow + r) * p.h + h) * p.pitch0 + bw0 + chn * 4) = val;
+          }
+        } else if (!(p.dbg & 2)) {
+          const int off = acquire();
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4),
+                         make_uint4(__float_as_uint(c[4 * ch]), __float_as_uint(c[4 * ch + 1]), __float_as_uint(c[4 * ch + 2]),
+                                    __float_as_uint(c[4 * ch + 3])));
+          commit(&p.tmL[0], off, bw0, h);
+        }
+        if ((hl & 1) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hs1[j] = c[2 * j] + c[2 * j + 1];
+        } else {
+          float l1[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) l1[j] = (hs1[j] + (c[2 * j] + c[2 * j + 1])) * 0.25f;
+          const int r1 = h >> 1;
+          if (r1 < H1 && !(p.dbg & 3)) {
+            const int off = acquire();
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              st_shared_v4(st_u32 + off + lane * 64 + ch * 16,
+                           make_uint4(__float_as_uint(l1[4 * ch]), __float_as_uint(l1[4 * ch + 1]), __float_as_uint(l1[4 * ch + 2]),
+                                      __float_as_uint(l1[4 * ch + 3])));
+            commit(&p.tmL[1], off, bw0 >> 1, r1);
+          }
+          if ((hl & 3) == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hs2[j] = l1[2 * j] + l1[2 * j + 1];
+          } else {
+            float l2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) l2[j] = (hs2[j] + (l1[2 * j] + l1[2 * j + 1])) * 0.25f;
+            const int r2 = h >> 2;
+            if (r2 < H2 && !(p.dbg & 3)) {
+              const int off = acquire();
+#pragma unroll
+              for (int ch = 0; ch < 2; ++ch)
+                st_shared_v4(st_u32 + off + lane * 32 + ch * 16,
+                             make_uint4(__float_as_uint(l2[4 * ch]), __float_as_uint(l2[4 * ch + 1]), __float_as_uint(l2[4 * ch + 2]),
+                                        __float_as_uint(l2[4 * ch + 3])));
+              commit(&p.tmL[2], off, bw0 >> 2, r2);
+            }
+            if (hl == 3) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) hs3[j] = l2[2 * j] + l2[2 * j + 1];
+            } else {
+              const int r3 = h >> 3;
+              if (r3 < H3 && !(p.dbg & 3)) {
+                const int off = acquire();
+                st_shared_v4(st_u32 + off + lane * 16,
+                             make_uint4(__float_as_uint((hs3[0] + (l2[0] + l2[1])) * 0.25f), __float_as_uint((hs3[1] + (l2[2] + l2[3])) * 0.25f),
+                                        __float_as_uint((hs3[2] + (l2[4] + l2[5])) * 0.25f), __float_as_uint((hs3[3] + (l2[6] + l2[7])) * 0.25f)));
+                commit(&p.tmL[3], off, bw0 >> 3, r3);
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[g]);
+    }
+    if (lane == 0) bulk_wait_read<0>();             // shared memory stays valid until the last store has read it
+    __syncwarp();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace atdn
+
+using namespace atdn;
+
+extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t fmap_pitch, int32_t channels,
+                                 float* const lvl[4], const int32_t lvl_pitch[4], int32_t batch, int32_t h8, int32_t w8,
+                                 float alpha, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = require_sm100()) return e;
+  ATDN_REQUIRE(fmap1 && fmap2 && lvl && lvl_pitch && batch > 0, ATDN_ERR_ARG, "atdn_corr_pyramid: null / empty argument");
+  ATDN_REQUIRE(channels == 256, ATDN_ERR_UNSUP, "atdn_corr_pyramid: %d feature channels (the GMA feature net has 256)", channels);
+  ATDN_REQUIRE(h8 >= 16 && w8 >= 16, ATDN_ERR_ARG, "atdn_corr_pyramid: grid %dx%d is smaller than 16x16 (level 3 would be < 2x2)", h8, w8);
+  ATDN_REQUIRE(fmap_pitch >= channels && fmap_pitch % 8 == 0, ATDN_ERR_ALIGN, "atdn_corr_pyramid: fmap_pitch %lld", (long long)fmap_pitch);
+  CorrParams p;
+  memset(&p, 0, sizeof(p));
+  const int n = h8 * w8;
+  p.h = h8;
+  p.w = w8;
+  p.tiles_w = ceil_div(w8, 32);
+  p.tiles = p.tiles_w * ceil_div(h8, 8);
+  p.alpha = alpha;
+  {
+    const char* dbg = getenv("ATDN_CORR_DBG");
+    p.dbg = dbg ? atoi(dbg) : 0;
+  }
+  p.l0 = lvl[0];
+  p.n = n;
+  p.pitch0 = lvl_pitch[0];
+  const uint32_t ones[4] = {1, 1, 1, 1};
+  {
+    const int64_t dims[4] = {channels, n, 1, batch};
+    const int64_t str[3] = {fmap_pitch, (int64_t)n * fmap_pitch, (int64_t)n * fmap_pitch};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int e = make_map_f16(&p.tmA, fmap1, dims, str, box, ones, "fmap1")) return e;
+  }
+  {
+    const int64_t dims[4] = {channels, w8, h8, batch};
+    const int64_t str[3] = {fmap_pitch, (int64_t)w8 * fmap_pitch, (int64_t)n * fmap_pitch};
+    const uint32_t box[4] = {64, 32, 8, 1};
+    if (int e = make_map_f16(&p.tmB, fmap2, dims, str, box, ones, "fmap2")) return e;
+  }
+  int hl = h8, wl = w8;
+  for (int l = 0; l < 4; ++l) {
+    ATDN_REQUIRE(lvl[l] != nullptr && lvl_pitch[l] % 4 == 0 && lvl_pitch[l] >= wl, ATDN_ERR_ALIGN, "atdn_corr_pyramid: level %d pitch %d", l, lvl_pitch[l]);
+    const int64_t dims[4] = {wl, hl, n, batch};
+    const int64_t str[3] = {lvl_pitch[l], (int64_t)hl * lvl_pitch[l], (int64_t)n * hl * lvl_pitch[l]};
+    const uint32_t box[4] = {32u >> l, 1, 32, 1};
+    if (int e = make_map(&p.tmL[l], 4, l == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, lvl[l], dims, str, box, ones, "pyramid level")) return e;
+    hl /= 2;
+    wl /= 2;
+  }
+  static bool configured = false;
+  if (!configured) {
+    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
+    configured = true;
+  }
+  corr_pyramid_kernel<<<dim3(ceil_div(n, 128), batch), kCorrThreads, kCorrSmem, stream>>>(p);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -11,7 +11,7 @@ Data layout in HBM (per batch of B pairs, 1/8-resolution grid H8 x W8, N = H8*W8
                           features | [384:512] globally aggregated motion features  (the reference's
                           torch.cat([net, inp, mf, mfg]) materialised once, never copied)
   h32 [B*N,128]    fp32 master copy of the hidden state (recurrent precision)
-  corr pyramid     fp32 [B*N, H_l, pitch_l] for l = 0..3 (pitch = W_l rounded up to 4)
+  corr pyramid     fp32 [B*N, H_l, pitch_l] for l = 0..3 (pitch = W_l rounded up to 32/16/8/8 floats: sector-aligned store boxes)
   P   [B,N,Np]     fp16 un-normalised attention probabilities exp(s - max), Np = N rounded up to 64
                    (written by the fused q.k^T/softmax kernel: the fp32 logits never reach HBM);
   inv_sum [B*N]    fp32 1/sum(P) applied in the P.V epilogue
@@ -123,7 +123,7 @@ class _EncoderWeights:
             return w, b
 
         w, b = conv(p + "conv1", p + "norm1")
-        self.stem = _Conv(w, b, rows=True)
+        self.stem = _Conv(ops.stem_weight(w), b)      # 7x7/2 as a 4x1 conv over the row-packed image (ops.stem_pack)
         self.blocks = []
         for li, (planes, stride) in enumerate(schema.ENCODER_STAGES, start=1):
             for bi in range(2):
@@ -148,7 +148,8 @@ class _Packed:
         g = lambda n: (sd[u + n + ".weight"], sd[u + n + ".bias"])
         self.convc1 = _Conv(*g("encoder.convc1"))
         self.convc2 = _Conv(*g("encoder.convc2"))
-        self.convf1 = _Conv(*g("encoder.convf1"), rows=True)
+        wf, bf = g("encoder.convf1")
+        self.convf1 = _Conv(ops.flow_weight(wf), bf)           # 7x7 as a 7x1 conv over the row-packed flow (ops.flow_pack)
         self.convf2 = _Conv(*g("encoder.convf2"))
         w, b = g("encoder.conv")                       # 126 outputs + 2 raw flow channels (update.py:84)
         self.conv = _Conv(w, torch.cat([b.float(), torch.zeros(2, device=b.device)]))
@@ -197,7 +198,7 @@ class _Plan:
         self.corrfeat = f16(b, h8, w8, 328)
         self.c1 = f16(b, h8, w8, 256)
         self.corflo = f16(b, h8, w8, 256)
-        self.frows = f16(b * n, 104)
+        self.fpack = f16(b, h8, w8, 16)
         self.f1 = f16(b, h8, w8, 128)
         self.fh = f16(b, h8, w8, 256)
         self.mh = f16(b, h8, w8, 256)
@@ -215,7 +216,7 @@ class _Plan:
             f16 = lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)
             h2, w2, h4, w4, h8, w8 = self.h // 2, self.w // 2, self.h // 4, self.w // 4, self.h8, self.w8
             self.enc[nimg] = {
-                "rows": f16(nimg * h2 * w2, 152),
+                "xpack": f16(nimg, h2, w2, 48),
                 "r2": [f16(nimg, h2, w2, 64) for _ in range(4)],
                 "r4": [f16(nimg, h4, w4, 96) for _ in range(4)],
                 "r8": [f16(nimg, h8, w8, 128) for _ in range(4)],
@@ -284,10 +285,10 @@ class RAFTGMA(nn.Module):
             ops.inorm_stats(x, sc["scratch"], 296, sc["stats"])
             ops.inorm_apply(x, sc["stats"], y, resid=resid, relu=act)
 
-        ops.stem_im2col(images, sc["rows"])
+        ops.stem_pack(images, sc["xpack"])
         r2 = sc["r2"]
-        ops.gemm_rows(L.ptr(sc["rows"]), 147, n * h2 * w2, 152, 1, L.ptr(ew.stem.wp), 64, ew.stem.wp.shape[1],
-                      L.ptr(r2[0]), 64, n_valid=64, bn=64, flags=relu, bias=ew.stem.bias)
+        ops.conv_tc(View(sc["xpack"]), ew.stem.wp, ew.stem.bias, View(r2[0]), cout=64, taps=(4, 1), pad=(2, 0), bn=64, mt=4,
+                    flags=relu, out_hw=(h2, w2))
         x = View(r2[0])
         if inst:
             norm_apply(x, x)
@@ -404,10 +405,10 @@ class RAFTGMA(nn.Module):
         _conv_s1(View(plan.corrfeat, 0, 324), c, View(plan.c1), cout=256, taps=(1, 1), flags=R)
         c = wts.convc2
         _conv_s1(View(plan.c1), c, View(plan.corflo, 0, 192), cout=192, taps=(3, 3), flags=R)
-        ops.flow_im2col(plan.flow, plan.frows)
+        ops.flow_pack(plan.flow, plan.fpack)
         c = wts.convf1
-        ops.gemm_rows(L.ptr(plan.frows), 98, b * n, 104, 1, L.ptr(c.wp), 128, c.wp.shape[1], L.ptr(plan.f1), 128,
-                      n_valid=128, bn=_pick_bn(128, m_tiles), flags=R, bias=c.bias)
+        ops.conv_tc(View(plan.fpack, 0, 14), c.wp, c.bias, View(plan.f1), cout=128, taps=(7, 1), pad=(3, 0), bn=128, mt=2,
+                    flags=R | L.F_PAIR)
         c = wts.convf2
         ops.conv_tc(View(plan.f1), c.wp, c.bias, View(plan.corflo, 192, 64), cout=64, taps=(3, 3), pad=(1, 1), bn=64, mt=2,
                     flags=R | L.F_PAIR)

@@ -89,7 +89,8 @@ def _fill_out(d, out, n_valid, alpha, bias):
 
 
 def conv_tc(a, wp, bias, out, *, cout, taps=(1, 1), pad=(0, 0), stride=1, bn=128, epi=L.EPI_STORE16, flags=0,
-            alpha=1.0, a2=None, resid=None, h32=None, z32=None, rh16=None, aux32=None, gamma=None, mt=0, stamps=None):
+            alpha=1.0, a2=None, resid=None, h32=None, z32=None, rh16=None, aux32=None, gamma=None, mt=0, stamps=None,
+            out_hw=None):
     """Convolution as implicit GEMM on tcgen05.  ``a`` (and optional ``a2``, concatenated after it)
     are NHWC fp16 Views of the INPUT image; ``out`` is a View of the output buffer."""
     d = L.TcDesc()
@@ -100,6 +101,8 @@ def conv_tc(a, wp, bias, out, *, cout, taps=(1, 1), pad=(0, 0), stride=1, bn=128
     kh, kw = taps
     oh = (a.H + 2 * pad[0] - kh) // stride + 1
     ow = (a.W + 2 * pad[1] - kw) // stride + 1
+    if out_hw is not None:   # asymmetric padding: `pad` is the leading pad, the trailing one follows from the output size
+        oh, ow = out_hw
     d.out_h, d.out_w = oh, ow
     d.taps_h, d.taps_w, d.pad_h, d.pad_w, d.stride = kh, kw, pad[0], pad[1], stride
     d.a = a.ptr()
@@ -149,10 +152,13 @@ def gemm_rows(a, a_k, a_rows, a_pitch, batch, b, b_rows, b_pitch, out_ptr, out_p
 # correlation pyramid
 # ----------------------------------------------------------------------------------------------
 def pyramid_shapes(h8, w8):
-    """[(H_l, W_l, pitch_l)] for the 4 levels; pitch = W_l rounded up to 4 floats (16 bytes)."""
+    """[(H_l, W_l, pitch_l)] for the 4 levels.  The row pitch rounds W_l up so that every box the pyramid kernel
+    stores (32 / 16 / 8 / 4 floats per row at levels 0..3) starts on a 128 / 64 / 32 / 32-byte boundary: level-0
+    rows are whole cache lines and no store leaves a partially written 32-byte sector behind."""
     out, h, w = [], h8, w8
-    for _ in range(4):
-        out.append((h, w, (w + 3) // 4 * 4))
+    for l in range(4):
+        q = (32, 16, 8, 8)[l]
+        out.append((h, w, (w + q - 1) // q * q))
         h, w = h // 2, w // 2
     return out
 
@@ -162,11 +168,27 @@ def alloc_pyramid(batch, h8, w8, device):
     return [torch.empty(batch * n, h, p, dtype=torch.float32, device=device) for (h, w, p) in pyramid_shapes(h8, w8)]
 
 
-def corr_pyramid_build(fmap1, fmap2, levels, pair=False):
+def corr_pyramid_build(fmap1, fmap2, levels, legacy=False, pair=False):
     """fmap1/fmap2: Views [B,H8,W8,256] fp16 -> the 4 fp32 pyramid levels (corr.py:16-30, 55-63)."""
-    d = L.TcDesc()
     b, h8, w8 = fmap1.B, fmap1.H, fmap1.W
     n = h8 * w8
+    if not legacy:
+        assert fmap1.pitch == fmap2.pitch and fmap1.c == fmap2.c
+        lv = (C.c_void_p * 4)(*[t.data_ptr() for t in levels])
+        lp = (C.c_int32 * 4)(*[t.shape[2] for t in levels])
+
+        def go():
+            L.check(L.load().atdn_corr_pyramid(fmap1.ptr(), fmap2.ptr(), C.c_int64(fmap1.pitch), fmap1.c, lv, lp, b, h8, w8,
+                                               C.c_float(1.0 / math.sqrt(fmap1.c)), L.stream_ptr()), "atdn_corr_pyramid")
+        if L.PROFILER is not None:
+            # algorithmic: 2*N*N*C flop; bytes = the four fp32 levels written + both feature maps read once
+            nbytes = sum(4.0 * b * n * (h8 >> l) * (w8 >> l) for l in range(4)) + 2.0 * b * n * fmap1.c * 2
+            with L.PROFILER("corr_pyramid", 2.0 * b * n * n * fmap1.c, nbytes):
+                go()
+            return
+        go()
+        return
+    d = L.TcDesc()
     d.bn, d.epi, d.a_mode, d.b_mode = 256, L.EPI_CORR, L.MODE_ROWS, L.MODE_PATCH
     d.flags = L.F_B_BATCHED | (L.F_PAIR if pair else 0)
     d.a = fmap1.ptr()
@@ -209,17 +231,37 @@ def corr_lookup(levels, coords, out16=None, out32=None):
 # element-wise
 # ----------------------------------------------------------------------------------------------
 @_profiled
-def stem_im2col(image, rows):
+def stem_pack(image, x16):
+    """image fp32 [B,3,H,W] -> x16 [B,H/2,W/2,48]: normalised, horizontal taps of the 7x7/2 stem folded into channels."""
     b, _, h, w = image.shape
-    L.check(L.load().atdn_stem_im2col(L.ptr(image), L.ptr(rows), C.c_int64(rows.shape[-1]), b, h, w, L.stream_ptr()),
-            "atdn_stem_im2col")
+    L.check(L.load().atdn_stem_pack(L.ptr(image), L.ptr(x16), b, h, w, L.stream_ptr()), "atdn_stem_pack")
+
+
+def stem_weight(w):
+    """[Cout,3,7,7] -> [Cout,48,4,1] for the 4x1 convolution over the packed stem input (see atdn_stem_pack)."""
+    cout = w.shape[0]
+    w4 = torch.zeros(cout, 48, 4, 1, dtype=torch.float32, device=w.device)
+    for ai in range(4):
+        for ry in range(2):
+            dy = 2 * ai + ry - 1
+            if not 0 <= dy <= 6:
+                continue
+            for c in range(3):
+                ch = (ry * 3 + c) * 8
+                w4[:, ch + 1:ch + 8, ai, 0] = w[:, c, dy, :].float()
+    return w4
 
 
 @_profiled
-def flow_im2col(flow, rows):
+def flow_pack(flow, x16):
+    """flow fp32 [B,H8,W8,2] -> x16 [B,H8,W8,16]: horizontal taps of convf1 (7x7) folded into channels."""
     b, h8, w8, _ = flow.shape
-    L.check(L.load().atdn_flow_im2col(L.ptr(flow), L.ptr(rows), C.c_int64(rows.shape[-1]), b, h8, w8, L.stream_ptr()),
-            "atdn_flow_im2col")
+    L.check(L.load().atdn_flow_pack(L.ptr(flow), L.ptr(x16), b, h8, w8, L.stream_ptr()), "atdn_flow_pack")
+
+
+def flow_weight(w):
+    """[Cout,2,7,7] -> [Cout,14,7,1] for the 7x1 convolution over the packed flow (see atdn_flow_pack)."""
+    return w.float().permute(0, 3, 1, 2).reshape(w.shape[0], 14, 7).unsqueeze(-1).contiguous()   # [o, dx*2+c, dy, 1]
 
 
 @_profiled

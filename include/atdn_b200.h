@@ -124,6 +124,21 @@ typedef struct atdn_tc_desc {
 int atdn_tc_gemm(const atdn_tc_desc* desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Correlation volume + pyramid -- GMA.whl!/GMA/core/corr.py:16-30 (CorrBlock.__init__) and :55-63
+ * (CorrBlock.corr); replaces cuBLAS SGEMM + 3 x avg_pool2d.  fmap1 / fmap2: NHWC fp16 [batch, h8, w8, fmap_pitch]
+ * (channels = 256).  lvl[l]: fp32 [batch * h8 * w8, H_l, lvl_pitch[l]] with H_l = h8 >> l, W_l = w8 >> l
+ * (floor), lvl_pitch[l] >= W_l and a multiple of 4:
+ *   lvl[0][q, y, x]   = alpha * <fmap1[q], fmap2[y, x]>          (alpha = 1 / sqrt(channels))
+ *   lvl[l+1][q, y, x] = mean of the 2x2 block of lvl[l]           (hierarchical, fp32)
+ * One persistent-style kernel: tcgen05 MMAs into two TMEM accumulators, fp32 boxes staged in shared memory
+ * and written with TMA stores (full 128-byte runs per query row); columns [W_l, ceil4(W_l)) of a row may be
+ * overwritten with pad values (16-byte store granularity).
+ * ---------------------------------------------------------------------------------------------- */
+int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t fmap_pitch, int32_t channels,
+                      float* const lvl[4], const int32_t lvl_pitch[4], int32_t batch, int32_t h8, int32_t w8,
+                      float alpha, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused attention probabilities -- GMA.whl!/GMA/core/gma.py:66-73 (q k^T * scale, softmax over keys);
  * replaces cuBLAS batched GEMM + softmax.  qk16: fp16 [batch, n, qk_pitch] with q in channels 0..127 and k
  * in channels 128..255 (the to_qk 1x1 conv output).  The logits never reach HBM: every key tile goes
@@ -147,14 +162,18 @@ int atdn_corr_lookup(const float* const lvl[4], const int32_t lvl_pitch[4], cons
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / data-movement kernels of the flow net
  * ---------------------------------------------------------------------------------------------- */
-/* network.py:75-79 + im2col for the 7x7 stride-2 stem (extractor.py:173): image fp32 NCHW [B,3,H,W]
- * in 0..255 -> rows fp16 [B*(H/2)*(W/2), pitch] with k = (dy*7+dx)*3 + c of 2*(x/255)-1.            */
-int atdn_stem_im2col(const float* image, void* rows16, int64_t pitch, int32_t batch, int32_t h, int32_t w,
-                     void* stream);
-/* update.py:79 (convf1 7x7 on the 2-channel flow): flow fp32 [B,H8,W8,2] -> rows fp16 [pix, pitch],
- * k = (dy*7+dx)*2 + c, zero padded.                                                                 */
-int atdn_flow_im2col(const float* flow, void* rows16, int64_t pitch, int32_t batch, int32_t h8, int32_t w8,
-                     void* stream);
+/* The two 7x7 convolutions on thin inputs (3-channel image, 2-channel flow) run on atdn_tc_gemm after their
+ * HORIZONTAL taps have been folded into channels; the vertical taps stay implicit in the convolution.
+ *
+ * network.py:75-76 (2*(image/255)-1) + extractor.py:173 (conv1 7x7 stride 2 pad 3): image fp32 NCHW [B,3,H,W]
+ * in 0..255 -> x16 NHWC fp16 [B, H/2, W/2, 48],
+ *   x16[b, y2, ox, (ry*3 + c)*8 + xx] = 2*(image[b, c, 2*y2+ry, 2*(ox-2)+xx]/255) - 1   (0 outside the image),
+ * to be convolved 4x1 (top padding 2) with W4[o, (ry*3+c)*8+xx, ai] = w[o, c, 2*ai+ry-1, xx-1] (0 outside 7x7). */
+int atdn_stem_pack(const float* image, void* x16, int32_t batch, int32_t h, int32_t w, void* stream);
+/* update.py:79 (convf1 7x7 pad 3 on the 2-channel flow): flow fp32 [B,H8,W8,2] -> x16 NHWC fp16 [B,H8,W8,16],
+ *   x16[b, y, x, dx*2 + c] = flow[b, y, x+dx-3, c] (0 outside; channels 14, 15 = 0),
+ * to be convolved 7x1 (padding 3) with W7[o, dx*2+c, dy] = w[o, c, dy, dx].                                  */
+int atdn_flow_pack(const float* flow, void* x16, int32_t batch, int32_t h8, int32_t w8, void* stream);
 /* nn.InstanceNorm2d (extractor.py:28-32,127) on NHWC fp16: per (image, channel) mean / rstd over H*W
  * into stats fp32 [B, C, 2]; two-stage, deterministic.  scratch: fp32 [B * parts * C * 2].          */
 int atdn_inorm_stats(const void* x16, int64_t pitch, int32_t batch, int32_t hw, int32_t c,

@@ -215,7 +215,42 @@ def time_halo():
     return True
 
 
-def check_corr(h8=16, w8=20, batch=2, pair=False):
+def check_corr_full(h8=47, w8=154, batch=2, reps=0):
+    """streaming corr-pyramid kernel at full size: bit-identical to the one-tile-per-CTA kernel (same MMA shape,
+    same K order, same pooling arithmetic), and timing."""
+    import torch
+    from atdn_vslam_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    v1 = ops.View(torch.randn(batch, h8, w8, 256, generator=g).half().cuda())
+    v2 = ops.View(torch.randn(batch, h8, w8, 256, generator=g).half().cuda())
+    lv = ops.alloc_pyramid(batch, h8, w8, "cuda")
+    ok = True
+    if batch <= 4:
+        ref = ops.alloc_pyramid(batch, h8, w8, "cuda")
+        ops.corr_pyramid_build(v1, v2, ref, legacy=True)
+        ops.corr_pyramid_build(v1, v2, lv)
+        torch.cuda.synchronize()
+        for l, (t, r) in enumerate(zip(lv, ref)):
+            wl = w8 >> l
+            same = bool(torch.equal(t[:, :, :wl], r[:, :, :wl]))
+            print(f"{'PASS' if same else 'FAIL'} corr level {l} bit-identical to the legacy kernel: {same}", flush=True)
+            ok &= same
+    if reps:
+        for legacy in (True, False):
+            ops.corr_pyramid_build(v1, v2, lv, legacy=legacy)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(reps):
+                ops.corr_pyramid_build(v1, v2, lv, legacy=legacy)
+            s1.record()
+            torch.cuda.synchronize()
+            ms = s0.elapsed_time(s1) / reps
+            nbytes = sum(t.shape[0] * t.shape[1] * (w8 >> l) * 4.0 for l, t in enumerate(lv))
+            print(f"TIME corr_pyramid legacy={legacy} batch={batch}: {ms:.3f} ms, {nbytes / ms / 1e6:.0f} GB/s written", flush=True)
+    return ok
+
+
+def check_corr(h8=16, w8=20, batch=2, pair=False, legacy=False):
     import torch
     from atdn_vslam_b200 import ops
     from oracle import gma_oracle
@@ -228,7 +263,7 @@ def check_corr(h8=16, w8=20, batch=2, pair=False):
     lv = ops.alloc_pyramid(batch, h8, w8, "cuda")
     for t in lv:
         t.fill_(float("nan"))
-    ops.corr_pyramid_build(v1, v2, lv, pair=pair)
+    ops.corr_pyramid_build(v1, v2, lv, pair=pair, legacy=legacy or pair)
     torch.cuda.synchronize()
     ok = True
     for l, (t, r) in enumerate(zip(lv, pyr)):
@@ -320,6 +355,11 @@ def check_attn(n=1000, batch=2, reps=0):
 
 
 CHECKS = {
+    "corr_full_vs_legacy": lambda: check_corr_full(),
+    "time_corr": lambda: check_corr_full(batch=27, reps=5),
+    "corr_legacy_small": lambda: check_corr(legacy=True),
+    "corr_legacy_odd": lambda: check_corr(h8=23, w8=39, batch=1, legacy=True),
+    "corr_wide": lambda: check_corr(h8=17, w8=70, batch=3),
     "attn_small": lambda: check_attn(),
     "attn_tiny": lambda: check_attn(n=256, batch=1),
     "attn_one_tile_plus": lambda: check_attn(n=300, batch=3),

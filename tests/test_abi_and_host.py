@@ -90,7 +90,7 @@ def test_weight_packing_layout():
     assert wp[1, 2 * 64 + 1] == w[1, 1, 0, 2] and wp[0, 3] == 0
     assert tuple(ops.pack_rows_weight(torch.ones(4, 147)).shape) == (4, 192)
     assert ops.pad_bias(torch.ones(126)).numel() == 128
-    assert ops.pyramid_shapes(47, 154) == [(47, 154, 156), (23, 77, 80), (11, 38, 40), (5, 19, 20)]
+    assert ops.pyramid_shapes(47, 154) == [(47, 154, 160), (23, 77, 80), (11, 38, 40), (5, 19, 24)]
 
 
 def test_pose_chain_matches_oracle():

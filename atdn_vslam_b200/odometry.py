@@ -189,21 +189,38 @@ class ATDNVO(nn.Module):
     @torch.no_grad()
     def recurrent_scan(self, features):
         """Serial LSTM + heads over a [T,512] (or [T,B,512]) feature sequence, continuing from and
-        updating the module state -> (rot [T,(B,)3], tr [T,(B,)3]).  Equivalent to T forward calls."""
+        updating the module state -> (rot [T,(B,)3], tr [T,(B,)3]).  Equivalent to T forward calls.
+        One batched product for the input side of LSTM1, ONE persistent kernel for the T-step recurrence
+        (``atdn_clvo_lstm_scan``), then the regressor heads as batched products over all T hidden states."""
         L.require_cuda(features)
         p = self._weights(features.device)
         squeeze = features.dim() == 2
-        f = features.unsqueeze(1) if squeeze else features
+        f = (features.unsqueeze(1) if squeeze else features).float().contiguous()
         t_steps, b = f.shape[0], f.shape[1]
-        state = [getattr(self, n).to(f.device).expand(b, -1).contiguous().clone()
-                 for n in ("lstm1_h", "lstm1_c", "lstm2_h", "lstm2_c")]
-        gates, tmp = self._tmp(b, f.device)
-        rots, trs = [], []
-        f = f.contiguous()
-        for t in range(t_steps):
-            r, tr = self._step(p, f[t], state, gates, tmp)
-            rots.append(r)
-            trs.append(tr)
-        self.lstm1_h, self.lstm1_c, self.lstm2_h, self.lstm2_c = state
-        rot, tr = torch.stack(rots), torch.stack(trs)
+        dev = f.device
+        if t_steps == 0:
+            z = torch.empty((0, 3) if squeeze else (0, b, 3), dtype=torch.float32, device=dev)
+            return z, z.clone()
+        if b > 32:
+            raise NotImplementedError("recurrent_scan: batch > 32 (atdn_clvo_lstm_scan keeps one cell state per thread)")
+        h1, c1, h2, c2 = [getattr(self, n).to(dev).expand(b, -1).float().contiguous().clone()
+                          for n in ("lstm1_h", "lstm1_c", "lstm2_h", "lstm2_c")]
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        p1 = new(t_steps * b, 2048)
+        ops.linear32(f.view(t_steps * b, 512), p.lstm[0][0], p.lstm[0][2], p1, act=0)
+        h1_all, h2_all, x2 = new(t_steps, b, 512), new(t_steps, b, 512), new(b, 512)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        ops.clvo_lstm_scan(p1, p.lstm[0], (p.ll_w, p.ll_b), p.lstm[1], h1, c1, h2, c2, h1_all, h2_all, x2, counter)
+        outs = []
+        hh = h2_all.view(t_steps * b, 512)
+        for h in ("rotation_regressor", "translation_regressor"):
+            w0, b0, w1, b1, w2 = p.heads[h]
+            a, bb, o = new(t_steps * b, 128), new(t_steps * b, 64), new(t_steps * b, 3)
+            ops.linear32(hh, w0, b0, a, act=1)
+            ops.linear32(a, w1, b1, bb, act=1)
+            ops.linear32(bb, w2, None, o, act=0)
+            outs.append(o.view(t_steps, b, 3))
+        self.lstm1_h, self.lstm1_c = h1_all[-1].clone(), c1
+        self.lstm2_h, self.lstm2_c = h2_all[-1].clone(), c2
+        rot, tr = outs
         return (rot[:, 0], tr[:, 0]) if squeeze else (rot, tr)

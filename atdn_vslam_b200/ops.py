@@ -350,6 +350,16 @@ def lstm_cell(x, w_ih, w_hh, b_ih, b_hh, h, c, gates):
 
 
 @_profiled
+def clvo_lstm_scan(p1, lstm1, ll, lstm2, h1_0, c1, h2_0, c2, h1_all, h2_all, x2, counter):
+    """Persistent LSTM scan (odometry/network.py:137-140); lstm* = (w_ih, w_hh, b_ih, b_hh), ll = (w, b)."""
+    steps, batch = h1_all.shape[0], h1_all.shape[1]
+    L.check(L.load().atdn_clvo_lstm_scan(L.ptr(p1), L.ptr(lstm1[1]), L.ptr(lstm1[3]), L.ptr(ll[0]), L.ptr(ll[1]),
+                                         L.ptr(lstm2[0]), L.ptr(lstm2[1]), L.ptr(lstm2[2]), L.ptr(lstm2[3]),
+                                         L.ptr(h1_0), L.ptr(c1), L.ptr(h2_0), L.ptr(c2), L.ptr(h1_all), L.ptr(h2_all),
+                                         L.ptr(x2), L.ptr(counter), steps, batch, L.stream_ptr()), "atdn_clvo_lstm_scan")
+
+
+@_profiled
 def keyframe_search(emb, code, dist, index):
     L.check(L.load().atdn_keyframe_search(L.ptr(emb), L.ptr(code), L.ptr(dist), L.ptr(index), C.c_int64(emb.shape[0]),
                                           emb.shape[1], L.stream_ptr()), "atdn_keyframe_search", 2)

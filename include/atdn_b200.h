@@ -229,6 +229,20 @@ int atdn_lstm_cell(const float* x, const float* w_ih, const float* w_hh, const f
                    float* h, float* c, float* gates_scratch, int32_t batch, int32_t in_f, int32_t hidden,
                    void* stream);
 
+/* Persistent recurrent scan of the pose network (odometry/network.py:137-140) over `steps` time steps in ONE
+ * cooperative kernel (128 CTAs, weights resident in shared memory, two grid barriers per step):
+ *   (h1,c1) = LSTMCell1(feat[t], (h1,c1)); x2 = mish(W_ll h1 + b_ll); (h2,c2) = LSTMCell2(x2, (h2,c2)).
+ * p1 = feat W_ih1^T + b_ih1 for all steps, fp32 [steps, batch, 2048] (one atdn_linear32 call); hidden = 512.
+ * h1_0 / h2_0: initial hidden states [batch,512] (read only); c1 / c2: cell states [batch,512], updated in
+ * place; h1_all / h2_all: fp32 [steps, batch, 512] hidden states of every step (h*_all[steps-1] is the new
+ * state; h2_all feeds the regressor heads).  x2_scratch: fp32 [batch,512]; counter: one uint32 (the call
+ * zeroes it on the stream).  batch <= 32.                                                                     */
+int atdn_clvo_lstm_scan(const float* p1, const float* w_hh1, const float* b_hh1, const float* w_ll,
+                        const float* b_ll, const float* w_ih2, const float* w_hh2, const float* b_ih2,
+                        const float* b_hh2, const float* h1_0, float* c1, const float* h2_0, float* c2,
+                        float* h1_all, float* h2_all, float* x2_scratch, uint32_t* counter, int32_t steps,
+                        int32_t batch, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Keyframe search -- atdn_vslam/slam_framework/neural_slam.py:373-384:
  * dist[k] = || emb[k, :] - code ||_2 ; *index = first arg-min.  emb fp32 [K, dim] (row pitch = dim).

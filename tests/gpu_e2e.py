@@ -146,6 +146,64 @@ def check_atdnvo():
     return ok
 
 
+def check_scan_long(t_steps=270, batch=1):
+    """Persistent scan kernel vs the per-step kernels (lstm_cell / linear32) and vs the oracle LSTM on a long
+    random feature sequence; scanning in two pieces must continue the state exactly."""
+    import time
+    import torch
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.odometry import ATDNVO
+    from oracle import clvo_oracle
+    sd = synth.atdnvo_state_dict()
+    vo = ATDNVO(batch_size=batch)
+    vo.load_state_dict(sd)
+    vo = vo.to("cuda").eval()
+    g = torch.Generator().manual_seed(12)
+    feats = torch.randn(t_steps, batch, 512, generator=g) * 0.7
+    fd = feats.cuda()
+    # reference 1: the per-step kernels
+    p = vo._weights(fd.device)
+    state = [torch.zeros(batch, 512, device="cuda") for _ in range(4)]
+    gates, tmp = vo._tmp(batch, fd.device)
+    rs, ts = [], []
+    for t in range(t_steps):
+        r, x = vo._step(p, fd[t], state, gates, tmp)
+        rs.append(r)
+        ts.append(x)
+    r_ref, t_ref = torch.stack(rs), torch.stack(ts)
+    vo.reset_lstm()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r1, t1 = vo.recurrent_scan(fd if batch > 1 else fd[:, 0])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if batch == 1:
+        r1, t1 = r1.unsqueeze(1), t1.unsqueeze(1)
+    ok = _stat(f"scan T={t_steps} B={batch} rot vs per-step kernels ({dt * 1e3:.2f} ms wall)", r1, r_ref, 1e-5)
+    ok &= _stat("scan tr vs per-step kernels", t1, t_ref, 1e-5)
+    ok &= _stat("scan final h2", vo.lstm2_h, state[2], 1e-5) and _stat("scan final c2", vo.lstm2_c, state[3], 1e-5)
+    # reference 2: the oracle (torch CPU fp32 restatement of the reference module) on a prefix
+    n = min(t_steps, 16)
+    st = clvo_oracle.zero_state(batch)
+    o_r = []
+    for t in range(n):
+        rr, _ = clvo_oracle.atdnvo_recurrent(sd, feats[t], st)
+        o_r.append(rr)
+    ok &= _stat("scan rot vs oracle (first 16 steps)", r1[:n], torch.stack(o_r), 1e-4)
+    # two-piece scan continues the state
+    vo.reset_lstm()
+    k = t_steps // 3
+    f2 = fd if batch > 1 else fd[:, 0]
+    ra, _ = vo.recurrent_scan(f2[:k])
+    rb, _ = vo.recurrent_scan(f2[k:])
+    rc = torch.cat([ra, rb], 0)
+    if batch == 1:
+        rc = rc.unsqueeze(1)
+    ok &= bool(torch.equal(rc, r1))
+    print(("PASS" if torch.equal(rc, r1) else "FAIL") + " two-piece scan is bit-identical to one scan", flush=True)
+    return ok
+
+
 def check_localization():
     import numpy as np
     import torch

@@ -39,6 +39,11 @@ def test_atdnvo_vs_reference_golden():
     assert gpu_e2e.check_atdnvo()
 
 
+@pytest.mark.parametrize("t_steps,batch", [(270, 1), (6, 24), (1, 1)])
+def test_persistent_lstm_scan(t_steps, batch):
+    assert gpu_e2e.check_scan_long(t_steps, batch)
+
+
 def test_localization_vs_reference_golden():
     assert gpu_e2e.check_localization()
 

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libatdn_b200.so")
 SOURCES = ["api.cu", "tc_gemm.cu", "tc_conv.cu", "tc_attn.cu", "tc_corr.cu", "flow_ops.cu", "small_nets.cu", "clvo_scan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O2", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "--use_fast_math=false"]
 
 
 def _newer(a, b):

@@ -68,8 +68,34 @@ class PoseChain:
         return is_key
 
     def extend(self, rots, trs):
-        rots = rots.detach().to("cpu", torch.float32)
-        trs = trs.detach().to("cpu", torch.float32)
-        for t in range(rots.shape[0]):
-            self.push(rots[t], trs[t])
-        return torch.stack(self.poses), list(self.keyframes)
+        """Whole-sequence form: ONE device->host copy of all relative poses, then the native host loop
+        ``atdn_pose_chain`` (same fp32 formulas; 270 poses in microseconds instead of ~0.1 ms each through
+        per-element torch calls).  Only valid on a fresh chain; ``push`` remains for incremental use."""
+        rots = rots.detach().to("cpu", torch.float32).contiguous()
+        trs = trs.detach().to("cpu", torch.float32).contiguous()
+        if self._frame != 0:
+            for t in range(rots.shape[0]):
+                self.push(rots[t], trs[t])
+            return torch.stack(self.poses), list(self.keyframes)
+        import ctypes as C
+        from . import _lib as L
+        n = rots.shape[0]
+        poses = torch.empty(n + 1, 4, 4, dtype=torch.float32)
+        is_key = torch.empty(n + 1, dtype=torch.int32)
+        cs = torch.cat([torch.cos(rots), torch.sin(rots)], 1).contiguous()     # torch's cos/sin: bit-identical to transform()
+        code = L.load().atdn_pose_chain(C.c_void_p(rots.data_ptr()), C.c_void_p(cs.data_ptr()), C.c_void_p(trs.data_ptr()), C.c_int64(n),
+                                        C.c_float(self.rotation_threshold), C.c_float(self.translation_threshold),
+                                        C.c_void_p(poses.data_ptr()), C.c_void_p(is_key.data_ptr()))
+        if code != 0:
+            raise RuntimeError(f"atdn_pose_chain failed with code {code}: {L.load().atdn_last_error().decode(errors='replace')}")
+        self.poses = list(poses)
+        self.keyframes = torch.nonzero(is_key).flatten().tolist()
+        self._frame = n
+        self.current_pose = poses[-1].clone()
+        # propagation since the last keyframe (so that push() can continue the chain)
+        prop = torch.eye(4, dtype=torch.float32)
+        last = self.keyframes[-1]
+        if last < n:
+            prop = torch.linalg.inv(poses[last].double()).float() @ poses[-1]
+        self.propagation = prop
+        return poses, list(self.keyframes)

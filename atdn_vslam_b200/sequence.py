@@ -62,6 +62,7 @@ class OdometryPipeline:
         self.flow_net, self.odometry_net = flow_net, odometry_net
         self.batch_pairs, self.iters, self.use_graphs = batch_pairs, iters, use_graphs
         self._graphs = {}
+        self._copy_stream, self._staging, self._staging_key = None, None, None
 
     def _batch_eager(self, frames):
         _, flow_up = self.flow_net.forward_frames(frames, iters=self.iters, test_mode=True)
@@ -88,7 +89,12 @@ class OdometryPipeline:
 
     @torch.no_grad()
     def pair_features(self, frames):
-        """frames [T,3,376,1232] on the device -> CLVO features [T-1,512] (pair-parallel part)."""
+        """frames [T,3,H,W] -> CLVO features [T-1,512] (pair-parallel part).  Device frames are consumed in
+        place; HOST frames (pinned memory) are streamed: the host->device copy of batch k+1 runs on a copy
+        stream while batch k computes, through two staging buffers."""
+        if not frames.is_cuda:
+            return self._pair_features_streamed(frames)
+        frames = preprocess(frames)
         t = frames.shape[0]
         feats = []
         s = 0
@@ -98,12 +104,54 @@ class OdometryPipeline:
             s = e
         return torch.cat(feats, 0) if feats else torch.empty(0, 512, device=frames.device)
 
+    def _pair_features_streamed(self, host_frames):
+        dev = next(self.flow_net.parameters()).device
+        t = host_frames.shape[0]
+        if t < 2:
+            return torch.empty(0, 512, device=dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        nb = self.batch_pairs + 1
+        key = (nb,) + tuple(host_frames.shape[1:]) + (host_frames.dtype,)
+        if self._staging_key != key:
+            self._staging = [torch.empty((nb,) + tuple(host_frames.shape[1:]), dtype=host_frames.dtype, device=dev) for _ in range(2)]
+            self._staging_key = key
+        main = torch.cuda.current_stream(dev)
+        ranges, s = [], 0
+        while s < t - 1:
+            e = min(t - 1, s + self.batch_pairs)
+            ranges.append((s, e))
+            s = e
+        ready = [torch.cuda.Event() for _ in ranges]
+        consumed = [torch.cuda.Event() for _ in ranges]
+
+        def enqueue_copy(k):
+            s, e = ranges[k]
+            with torch.cuda.stream(self._copy_stream):
+                if k >= 2:
+                    self._copy_stream.wait_event(consumed[k - 2])       # the staging buffer is free again
+                else:
+                    self._copy_stream.wait_stream(main)                  # ... or was last used by an earlier call
+                self._staging[k & 1][: e - s + 1].copy_(host_frames[s:e + 1], non_blocking=True)
+                ready[k].record(self._copy_stream)
+
+        feats = []
+        enqueue_copy(0)
+        for k, (s, e) in enumerate(ranges):
+            if k + 1 < len(ranges):
+                enqueue_copy(k + 1)
+            main.wait_event(ready[k])
+            feats.append(self._batch(preprocess(self._staging[k & 1][: e - s + 1].float())))
+            consumed[k].record(main)
+        return torch.cat(feats, 0)
+
     @torch.no_grad()
     def run(self, local_frames, num_pairs=None, group=None, chain=True):
-        """``local_frames``: this rank's frames (its pair range plus the one-frame halo).  Returns
+        """``local_frames``: this rank's frames (its pair range plus the one-frame halo), on the device or in
+        (pinned) host memory -- host frames are streamed batch by batch under the compute.  Returns
         (rot [P,3], tr [P,3], poses [P+1,4,4] or None, keyframe indices or None); the LSTM scan and
         pose chain run redundantly on every rank (they are microseconds per pair)."""
-        feats = self.pair_features(preprocess(local_frames))
+        feats = self.pair_features(local_frames)
         total = feats.shape[0] if num_pairs is None else num_pairs
         feats = gather_features(feats, total, group)
         rot, tr = self.odometry_net.recurrent_scan(feats)

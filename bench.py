@@ -218,7 +218,7 @@ def run_ours(args):
 
     def step_e2e():
         vo.reset_lstm()
-        rot, tr, poses, keys = pipe.run(host_frames.to(dev, non_blocking=True), num_pairs=total_pairs,
+        rot, tr, poses, keys = pipe.run(host_frames, num_pairs=total_pairs,
                                         group=None if world == 1 else dist.group.WORLD)
         return poses, keys
 

@@ -250,6 +250,19 @@ int atdn_clvo_lstm_scan(const float* p1, const float* w_hh1, const float* b_hh1,
 int atdn_keyframe_search(const float* emb, const float* code, float* dist, int32_t* index, int64_t num,
                          int32_t dim, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HOST function (all pointers are HOST pointers, no device work): pose chaining and the keyframe rule over the
+ * relative poses of `num` consecutive pairs -- atdn_vslam/utils/transforms.py:54-119 (euler2matrix 'yxz',
+ * matrix2euler, transform) and slam_framework/neural_slam.py:204-215 (current_pose @= T), :288-302
+ * (__decide_keyframe: propagation @= T; keyframe when ||euler(propagation)|| > rot_threshold or
+ * ||t(propagation)|| > tr_threshold, then propagation = I).  fp32, operation order of the reference formulas.
+ * rot, tr: [num, 3] Euler angles / translations; cos_sin_or_null: optional [num, 6] = (cos(rot), sin(rot)) computed
+ * by the caller's math library (then the poses are bit-identical to that library's chain), else libm is used.
+ * poses: [num+1, 4, 4] row-major (poses[0] = I); is_key: [num+1] (is_key[0] = 1).
+ * ---------------------------------------------------------------------------------------------- */
+int atdn_pose_chain(const float* rot, const float* cos_sin_or_null, const float* tr, int64_t num,
+                    float rot_threshold_rad, float tr_threshold, float* poses, int32_t* is_key);
+
 #ifdef __cplusplus
 }
 #endif

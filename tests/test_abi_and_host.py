@@ -102,6 +102,24 @@ def test_pose_chain_matches_oracle():
     assert keys == o_keys and len(keys) > 2
     assert torch.equal(poses, o_poses)
     assert torch.equal(transform(rots[0], trs[0]), clvo_oracle.transform(rots[0], trs[0]))
+    # the native whole-sequence loop (atdn_pose_chain, a HOST function of the C ABI) == the per-step push() loop,
+    # and a chain built by extend() can be continued with push()
+    inc = PoseChain()
+    for t in range(40):
+        inc.push(rots[t], trs[t])
+    assert inc.keyframes == keys and torch.equal(torch.stack(inc.poses), poses)
+    mixed = PoseChain()
+    mixed.extend(rots[:25], trs[:25])
+    for t in range(25, 40):
+        mixed.push(rots[t], trs[t])
+    assert mixed.keyframes == keys
+    assert (torch.stack(mixed.poses) - poses).abs().max() <= 1e-5 * poses.abs().max()
+    # long sequence (KITTI seq 00 length): same keyframes, poses within 1e-6 relative of the oracle chain
+    rots = torch.randn(4540, 3, generator=g) * 0.02
+    trs = torch.randn(4540, 3, generator=g) * 1.2
+    poses, keys = PoseChain().extend(rots, trs)
+    o_poses, o_keys = clvo_oracle.chain_and_keyframes(rots, trs)
+    assert keys == o_keys and (poses - o_poses).norm() <= 1e-6 * o_poses.norm()
 
 
 def test_shard_ranges_and_minima_merge():

@@ -117,6 +117,27 @@ def test_sequence_pipeline_matches_per_pair_calls_and_keyframes():
     assert keys == o_keys and torch.equal(poses, o_poses)
 
 
+def test_host_streamed_frames_equal_device_frames():
+    """pipe.run on pinned HOST frames (H2D streamed under the compute, raw 376x1241 size -> resize) must give
+    bit-identical poses to the same frames already on the device."""
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.odometry import ATDNVO
+    from atdn_vslam_b200.sequence import OdometryPipeline
+    m, _ = gpu_e2e._gma()
+    vo = ATDNVO()
+    vo.load_state_dict(synth.atdnvo_state_dict())
+    vo = vo.to("cuda").eval()
+    host = synth.frame_sequence(8, 376, 1241, seed=41).pin_memory()
+    pipe = OdometryPipeline(m, vo, batch_pairs=3, iters=4, use_graphs=True)
+    rot_d, tr_d, poses_d, keys_d = pipe.run(host.cuda())
+    vo.reset_lstm()
+    rot_h, tr_h, poses_h, keys_h = pipe.run(host)
+    assert torch.equal(rot_d, rot_h) and torch.equal(tr_d, tr_h) and torch.equal(poses_d, poses_h) and keys_d == keys_h
+    vo.reset_lstm()
+    rot_h2, _, _, _ = pipe.run(host)      # staging buffers are reused across calls
+    assert torch.equal(rot_h2, rot_h)
+
+
 def test_pose_from_flow_vs_oracle_end_to_end():
     """Relative pose from OUR flow vs the oracle's pose from the ORACLE's flow on one full-size pair
     (reported; the 1e-4 relative bound applies to the pose net given the same flow, tested above)."""

@@ -8,9 +8,12 @@
 namespace atdn {
 
 __device__ __forceinline__ float mishf(float x) {
-  // x * tanh(softplus(x)); softplus with the same threshold (20) as torch
-  const float sp = x > 20.0f ? x : log1pf(expf(x));
-  return x * tanhf(sp);
+  // x * tanh(softplus(x)) with softplus thresholded at 20 like torch.  tanh(log(1 + e^x)) = (n^2 + 2n) / (n^2 + 2n + 2),
+  // n = e^x: one MUFU exponential and one division (~2 ulp, all terms positive: no cancellation) instead of
+  // expf + log1pf + tanhf (~100 instructions, which made the 16-channel conv layers epilogue-bound).
+  const float n = __expf(x);
+  const float t = n * (n + 2.0f);
+  return x > 20.0f ? x : x * __fdividef(t, t + 2.0f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -95,6 +98,184 @@ __global__ void __launch_bounds__(256) conv32_kernel(Conv32Params p) {
     }
     p.y[o] = v;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Register-tiled direct convolution for the 16-output-channel layers of the CLVO encoder (the per-pair hot
+// ones: 7x7/2 stem on the flow, 3x3/1 and 3x3/2 of the residual blocks).  The generic kernel above issues one
+// scalar + four 128-bit shared loads per 16 FMAs (LSU-bound, 9 TFLOP/s); here
+//   * CTA = 64 x 8 output pixels x 16 output channels, 128 threads, thread = 4 consecutive pixels x 16 channels
+//     (64 fp32 accumulators): per (input channel, filter row) a thread loads its 4*S+K-S input values once
+//     (128-bit loads) and reuses them for K taps x 16 channels; the 16 weights of a tap are 4 broadcast loads
+//     feeding 64 FMAs;
+//   * stride-2 layers stage the input tile de-interleaved (even | odd columns) so the per-thread runs stay
+//     contiguous and conflict-free.
+// fp32 throughout (1e-4 relative pose tolerance, north star), same epilogue as the generic kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kC16TW = 64, kC16TH = 8, kC16Threads = 128;
+
+template <int K, int S>
+struct C16Geom {
+  static constexpr int IH = (kC16TH - 1) * S + K;
+  static constexpr int IW = (kC16TW - 1) * S + K;
+  static constexpr int NV = 3 * S + K;                       // input values per thread and filter row
+  // stride 1: one row of IW (padded to a multiple of 4); stride 2: even columns then odd columns, each padded
+  static constexpr int HALF = ((IW + 1) / 2 + 3) / 4 * 4 + 4;
+  static constexpr int PITCH = S == 1 ? (IW + 3) / 4 * 4 + 4 : 2 * HALF;
+};
+
+template <int K, int S, int CIT>
+__global__ void __launch_bounds__(kC16Threads) conv16_kernel(Conv32Params p) {
+  using G = C16Geom<K, S>;
+  extern __shared__ float sm[];
+  float* s_in = sm;                                 // [CIT][IH][PITCH]
+  float* s_w = sm + CIT * G::IH * G::PITCH;         // [CIT][K*K][16]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int tile_x = blockIdx.x % p.tiles_x, tile_y = blockIdx.x / p.tiles_x;
+  const int b = blockIdx.z;
+  const int ox0 = tile_x * kC16TW + tx * 4, oy = tile_y * kC16TH + ty;
+  const int ix0 = tile_x * kC16TW * S - p.pad, iy0 = tile_y * kC16TH * S - p.pad;
+  float acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[i][c] = 0.0f;
+
+  for (int ci0 = 0; ci0 < p.Cin; ci0 += CIT) {
+    __syncthreads();
+    // 8 independent global loads in flight per thread before the first shared store (a load -> store loop
+    // serialises one L2 round trip per element: measured 3x slower end to end)
+    constexpr int kN = CIT * G::IH * G::IW;
+    for (int i0 = threadIdx.x; i0 < kN; i0 += kC16Threads * 8) {
+      float v[8];
+      int dst[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * kC16Threads;
+        v[u] = 0.0f;
+        dst[u] = -1;
+        if (i < kN) {
+          const int c = i / (G::IH * G::IW), r = i - c * (G::IH * G::IW);
+          const int ry = r / G::IW, rx = r - ry * G::IW;
+          const int yy = iy0 + ry, xx = ix0 + rx, ci = ci0 + c;
+          dst[u] = (c * G::IH + ry) * G::PITCH + (S == 1 ? rx : (rx & 1) * G::HALF + (rx >> 1));
+          if (ci < p.Cin && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+            v[u] = __ldg(p.x + ((static_cast<long long>(b) * p.Cin + ci) * p.H + yy) * p.W + xx);
+            if (p.in_scale) v[u] = v[u] * __ldg(p.in_scale + ci) + __ldg(p.in_shift + ci);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (dst[u] >= 0) s_in[dst[u]] = v[u];
+    }
+    for (int i = threadIdx.x; i < CIT * K * K * 16; i += kC16Threads) {
+      const int co = i & 15, t = (i >> 4) % (K * K), c = i / (16 * K * K);
+      const int ci = ci0 + c;
+      s_w[i] = ci < p.Cin ? __ldg(p.w + (static_cast<long long>(co) * p.Cin + ci) * (K * K) + t) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < CIT; ++c) {
+#pragma unroll 1
+      for (int ky = 0; ky < K; ++ky) {
+        const float* row = s_in + (c * G::IH + ty * S + ky) * G::PITCH;
+        float in[G::NV + 3];
+        if (S == 1) {
+#pragma unroll
+          for (int q = 0; q < (G::NV + 3) / 4; ++q) {
+            const float4 f = *reinterpret_cast<const float4*>(row + tx * 4 + q * 4);
+            in[4 * q] = f.x; in[4 * q + 1] = f.y; in[4 * q + 2] = f.z; in[4 * q + 3] = f.w;
+          }
+        } else {
+          constexpr int NE = (G::NV + 1) / 2, NO = G::NV / 2;      // even / odd values needed
+          float ev[(NE + 3) / 4 * 4], od[(NO + 3) / 4 * 4];
+#pragma unroll
+          for (int q = 0; q < (NE + 3) / 4; ++q) {
+            const float4 f = *reinterpret_cast<const float4*>(row + tx * 4 + q * 4);
+            ev[4 * q] = f.x; ev[4 * q + 1] = f.y; ev[4 * q + 2] = f.z; ev[4 * q + 3] = f.w;
+          }
+#pragma unroll
+          for (int q = 0; q < (NO + 3) / 4; ++q) {
+            const float4 f = *reinterpret_cast<const float4*>(row + G::HALF + tx * 4 + q * 4);
+            od[4 * q] = f.x; od[4 * q + 1] = f.y; od[4 * q + 2] = f.z; od[4 * q + 3] = f.w;
+          }
+#pragma unroll
+          for (int j = 0; j < G::NV; ++j) in[j] = (j & 1) ? od[j >> 1] : ev[j >> 1];
+        }
+        const float4* w4 = reinterpret_cast<const float4*>(s_w + (c * K * K + ky * K) * 16);
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          float w[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 f = w4[kx * 4 + q];
+            w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float v = in[i * S + kx];
+#pragma unroll
+            for (int co = 0; co < 16; ++co) acc[i][co] += v * w[co];
+          }
+        }
+      }
+    }
+  }
+  if (oy >= p.OH) return;
+  const bool vec = (p.OW & 3) == 0 && ox0 + 4 <= p.OW;
+#pragma unroll
+  for (int co = 0; co < 16; ++co) {
+    const long long o = ((static_cast<long long>(b) * 16 + co) * p.OH + oy) * p.OW + ox0;
+    const float bias = p.bias ? __ldg(p.bias + co) : 0.0f;
+    const float s1 = p.bn_scale ? __ldg(p.bn_scale + co) : 1.0f, h1 = p.bn_scale ? __ldg(p.bn_shift + co) : 0.0f;
+    const float s2 = p.bn2_scale ? __ldg(p.bn2_scale + co) : 1.0f, h2 = p.bn2_scale ? __ldg(p.bn2_shift + co) : 0.0f;
+    float v[4], sk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (p.skip) {
+      if (vec) {
+        const float4 f = *reinterpret_cast<const float4*>(p.skip + o);
+        sk[0] = f.x; sk[1] = f.y; sk[2] = f.z; sk[3] = f.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ox0 + i < p.OW) sk[i] = p.skip[o + i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t = acc[i][co] + bias;
+      if (p.mish) t = mishf(t);
+      if (p.bn_scale) t = t * s1 + h1;
+      if (p.skip) {
+        t = mishf(t + sk[i]);
+        if (p.bn2_scale) t = t * s2 + h2;
+      }
+      v[i] = t;
+    }
+    if (vec) {
+      *reinterpret_cast<float4*>(p.y + o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (ox0 + i < p.OW) p.y[o + i] = v[i];
+    }
+  }
+}
+
+template <int K, int S, int CIT>
+static int launch_conv16(Conv32Params p, cudaStream_t stream) {
+  using G = C16Geom<K, S>;
+  constexpr int smem = (CIT * G::IH * G::PITCH + CIT * K * K * 16) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    if (smem > 48 * 1024) ATDN_CUDA(cudaFuncSetAttribute(conv16_kernel<K, S, CIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  p.tiles_x = ceil_div(p.OW, kC16TW);
+  dim3 grid(p.tiles_x * ceil_div(p.OH, kC16TH), 1, p.B);
+  conv16_kernel<K, S, CIT><<<grid, kC16Threads, smem, stream>>>(p);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -225,6 +406,12 @@ extern "C" int atdn_conv32(const atdn_conv32_desc* d, void* stream) {
   p.OH = (d->in_h + 2 * d->pad - d->k) / d->stride + 1;
   p.OW = (d->in_w + 2 * d->pad - d->k) / d->stride + 1;
   ATDN_REQUIRE(p.OH >= 1 && p.OW >= 1, ATDN_ERR_ARG, "atdn_conv32: empty output");
+  if (d->cout == 16 && d->cin <= 16 && p.OW >= 32) {   // CLVO encoder hot layers: register-tiled kernel
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->k == 3 && d->stride == 1) return launch_conv16<3, 1, 8>(p, st);
+    if (d->k == 3 && d->stride == 2) return launch_conv16<3, 2, 4>(p, st);
+    if (d->k == 7 && d->stride == 2 && d->cin <= 2) return launch_conv16<7, 2, 2>(p, st);
+  }
   p.tiles_x = ceil_div(p.OW, kTile);
   p.in_tile = (kTile - 1) * d->stride + d->k;
   const int smem = (kCiT * p.in_tile * p.in_tile + kCiT * d->k * d->k * kCoT) * (int)sizeof(float);

@@ -11,7 +11,7 @@
 //     absolute shared-memory address, so row-shifted starts and group pitches that are not multiples of
 //     1024 B read exactly what TMA wrote (verified by tools/umma_shift_test.cu on B200);
 //   * each weight stage (BN x 64 fp16) feeds MT MMAs chains, so weight bytes per pixel drop MT-fold;
-//   * the kernel is persistent (grid = #SMs, static tile striding) with the 512 TMEM columns split into two
+//   * the kernel is persistent (grid = #SMs, one contiguous tile range per CTA) with the 512 TMEM columns split into two
 //     accumulator buffers: 8 epilogue warps drain tile i while the MMA warp accumulates tile i+1;
 //   * A and B have independent producer threads and mbarrier rings (A advances per chunk, B per tap).
 #include <stdio.h>
@@ -101,6 +101,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
   const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
   const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+  // contiguous tile range per CTA (cluster): neighbouring halo boxes and the weight tiles stay hot in L2
+  const int t_begin = static_cast<int>(static_cast<long long>(cid) * p.total_tiles / ncl);
+  const int t_end = static_cast<int>(static_cast<long long>(cid + 1) * p.total_tiles / ncl);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     // ===== A producer (whole warp loops, one elected lane issues): one halo box per (tile, 64-channel chunk) =====
     int sa = 0;
     uint32_t pa = 0;
-    for (int t = cid; t < p.total_tiles; t += ncl) {
+    for (int t = t_begin; t < t_end; ++t) {
       const TileCoord tc = decode_tile<CL>(p, t, rank, kSubW * MT, BN);
       const int cw = tc.w0 - p.pad_w, ch = tc.h0 - p.pad_h;
       for (int c = 0; c < chunks; ++c) {
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     int sb = 0;
     uint32_t pb = 0;
     const int taps = p.taps_h * p.taps_w;
-    for (int t = cid; t < p.total_tiles; t += ncl) {
+    for (int t = t_begin; t < t_end; ++t) {
       const int n0 = (t % p.n_tiles) * BN + rank * (BN / CL);
       for (int c = 0; c < chunks; ++c) {
         int k0 = c * 64;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
       const uint32_t sbo = static_cast<uint32_t>(p.box_w) * 128u;
       const uint32_t smem_a_u32 = smem_u32(smem), smem_b_u32 = smem_u32(smem_b);
       int n_tile_iter = 0;
-      for (int t = cid; t < p.total_tiles; t += ncl, ++n_tile_iter) {
+      for (int t = t_begin; t < t_end; ++t, ++n_tile_iter) {
         const uint32_t pacc = buf ? pacc1 : pacc0;
         mbar_wait(&acc_empty[buf], pacc ^ 1u);
         tcgen05_fence_after();
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     int buf = 0;
     uint32_t pf0 = 0, pf1 = 0;
     int n_tile_iter = 0;
-    for (int t = cid; t < p.total_tiles; t += ncl, ++n_tile_iter) {
+    for (int t = t_begin; t < t_end; ++t, ++n_tile_iter) {
       const TileCoord tc = decode_tile<CL>(p, t, rank, kSubW * MT, BN);
       const uint32_t pf = buf ? pf1 : pf0;
       mbar_wait(&acc_full[buf], pf);

@@ -32,25 +32,35 @@ __device__ __forceinline__ float grid_round_trip(float x, int size) {
 }
 
 constexpr int kLkWarps = 8;
-constexpr int kLkWin = 12;                       // staged window edge (texels)
+constexpr int kLkWinW = 16, kLkWinH = 10;        // staged window: 10 rows x up to 16 columns (column base aligned to 4 texels)
 
+// One WARP per query pixel, 8 queries per CTA.  The first version of this layout (scalar window loads, per-tap index
+// arithmetic in the blend loop) executed ~1200 instructions per lane and query and was issue-bound at 21% of the HBM
+// roofline (ncu: SM throughput 81%).  Now
+//   2. the window base is aligned to 4 texels, so the 10 x 10 texels the taps touch arrive as (at most) two 128-bit
+//      loads per lane, all issued before the first use;
+//      texels outside the image (incl. the row pad) are zeroed = grid_sample's zero padding;
+//   3. lane (b, a0) blends 3 x-taps of one y-tap per level (27 lanes): the y coordinate / weight is fetched once per
+//      level, results go to shared memory and leave as 16-byte vectors of 8 consecutive channels.
 __global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_kernel(LookupParams p, const float* __restrict__ coords,
                                                                     __half* __restrict__ out16, long long out_pitch,
                                                                     float* __restrict__ out32, long long nq) {
-  __shared__ float win[kLkWarps][4][kLkWin * kLkWin];
+  // win doubles as the output staging buffer (324 floats) once the blend results sit in registers
+  __shared__ __align__(16) float win[kLkWarps][4][kLkWinH * kLkWinW];
   __shared__ float cfr[kLkWarps][72];            // fractional part of the 4 x (9 x + 9 y) tap coordinates
   __shared__ int cin[kLkWarps][72];              // integer part (floor), clamped to [-2, size]
-  __shared__ int org[kLkWarps][8];               // window origin (x, y) per level
   const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long q = static_cast<long long>(blockIdx.x) * kLkWarps + wq;
   if (q >= nq) return;
-  const float cx = coords[q * 2], cy = coords[q * 2 + 1];
+  const float2 cxy = *reinterpret_cast<const float2*>(coords + q * 2);
+  const float cx = cxy.x, cy = cxy.y;
+  const int h0 = p.h[0], w0 = p.w[0];            // level l is (h0 >> l) x (w0 >> l): no indexed parameter reads
 
   // 1. tap coordinates: idx = level * 18 + axis * 9 + k
   for (int idx = lane; idx < 72; idx += 32) {
     const int l = idx / 18, rem = idx - l * 18, axis = rem / 9, k = rem - axis * 9;
     const float inv = 1.0f / static_cast<float>(1 << l);     // exact: division by a power of two
-    const int size = axis ? p.h[l] : p.w[l];
+    const int size = (axis ? h0 : w0) >> l;
     const float c = (axis ? cy : cx) * inv;
     const float v = grid_round_trip(__fadd_rn(c, static_cast<float>(k - 4)), size);
     const float vf = floorf(v);
@@ -58,64 +68,129 @@ __global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_kernel(LookupParams
     // clamp before the int conversion so that far-away coordinates cannot overflow
     cin[wq][idx] = static_cast<int>(fminf(fmaxf(vf, -2.0f), static_cast<float>(size)));
   }
-  if (lane < 8) {
-    const int l = lane >> 1, axis = lane & 1;
-    const float inv = 1.0f / static_cast<float>(1 << l);
-    const int size = axis ? p.h[l] : p.w[l];
-    const float c = floorf((axis ? cy : cx) * inv);
-    org[wq][lane] = static_cast<int>(fminf(fmaxf(c, -16.0f), static_cast<float>(size + 16))) - 5;
-  }
-  __syncwarp();
-
-  // 2. stage the windows (zero outside the image)
+  // 2. window loads: lane -> (row = lane / 4 [+ 8], 4-texel segment = lane % 4); every lane derives the origins itself
+  //    and ALL loads are issued before the first use
+  float4 v[4][2];
+  int xa[4], y0w[4];
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
-    const int H = p.h[l], W = p.w[l], pitch = p.pitch[l];
-    const float* __restrict__ base = p.lvl[l] + q * static_cast<long long>(H) * pitch;
-    const int X0 = org[wq][2 * l], Y0 = org[wq][2 * l + 1];
+    const float inv = 1.0f / static_cast<float>(1 << l);
+    const int H = h0 >> l, W = w0 >> l;
+    // the 81 taps touch texels floor(c) - 4 .. floor(c) + 5 on each axis; a coordinate that the normalised-grid round
+    // trip pushes across an integer (1 ulp) falls outside this window and takes the exact direct-load path below
+    const int ox = static_cast<int>(fminf(fmaxf(floorf(cx * inv), -16.0f), static_cast<float>(W + 16))) - 4;
+    const int oy = static_cast<int>(fminf(fmaxf(floorf(cy * inv), -16.0f), static_cast<float>(H + 16))) - 4;
+    xa[l] = ox & ~3;                              // aligned down to a multiple of 4 (two's complement floor)
+    y0w[l] = oy;
+    const int pitch = l == 0 ? p.pitch[0] : l == 1 ? p.pitch[1] : l == 2 ? p.pitch[2] : p.pitch[3];
+    const float* lv = l == 0 ? p.lvl[0] : l == 1 ? p.lvl[1] : l == 2 ? p.lvl[2] : p.lvl[3];
+    const float* __restrict__ base = lv + q * static_cast<long long>(H) * pitch;
+    const int x = xa[l] + (lane & 3) * 4;
 #pragma unroll
-    for (int i = 0; i < (kLkWin * kLkWin + 31) / 32; ++i) {
-      const int idx = lane + i * 32;
-      if (idx < kLkWin * kLkWin) {
-        const int ry = idx / kLkWin, rx = idx - ry * kLkWin;
-        const int y = Y0 + ry, x = X0 + rx;
-        float v = 0.0f;
-        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(base + static_cast<long long>(y) * pitch + x);
-        win[wq][l][idx] = v;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 8 + (lane >> 2);
+      const int y = oy + r;
+      v[l][pass] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (r < kLkWinH && y >= 0 && y < H && x >= 0 && x + 4 <= pitch && x < ox + 10)   // segments right of the taps are never read
+        v[l][pass] = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(y) * pitch + x));
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int W = w0 >> l;
+    const int x = xa[l] + (lane & 3) * 4;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 8 + (lane >> 2);
+      if (r < kLkWinH) {
+        float4 t = v[l][pass];
+        if (x + 3 >= W) {                          // row pad (and the columns TMA clipping left behind) is not image
+          if (x >= W) t.x = 0.0f;
+          if (x + 1 >= W) t.y = 0.0f;
+          if (x + 2 >= W) t.z = 0.0f;
+          t.w = 0.0f;
+        }
+        *reinterpret_cast<float4*>(&win[wq][l][r * kLkWinW + (lane & 3) * 4]) = t;
       }
     }
   }
   __syncwarp();
 
-  // 3. blend: channel ch = l * 81 + a * 9 + b  (a offsets x, b offsets y -- corr.py:40-46)
-  for (int c2 = lane; c2 < 162; c2 += 32) {
-    float val[2];
+  // 3. blend: channel ch = l * 81 + a * 9 + b  (a offsets x, b offsets y -- corr.py:40-46); lane -> (b, a0..a0+2)
+  float res[4][3];
+  const int b = lane / 3, a0 = (lane - b * 3) * 3;
+  if (lane < 27) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int ch = c2 * 2 + j;
-      const int l = ch / 81, t = ch - l * 81, a = t / 9, b = t - a * 9;
-      const int x0 = cin[wq][l * 18 + a], y0 = cin[wq][l * 18 + 9 + b];
-      const float fx = cfr[wq][l * 18 + a], fy = cfr[wq][l * 18 + 9 + b];
-      const int wx = x0 - org[wq][2 * l], wy = y0 - org[wq][2 * l + 1];
-      float v00, v01, v10, v11;
-      if (wx >= 0 && wx + 1 < kLkWin && wy >= 0 && wy + 1 < kLkWin) {
-        const float* wp = &win[wq][l][wy * kLkWin + wx];
-        v00 = wp[0]; v01 = wp[1]; v10 = wp[kLkWin]; v11 = wp[kLkWin + 1];
-      } else {   // not reachable for finite coordinates near the image; kept exact for robustness
-        const int H = p.h[l], W = p.w[l], pitch = p.pitch[l];
-        const float* base = p.lvl[l] + q * static_cast<long long>(H) * pitch;
-        const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
-        const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
-        const float* r0 = base + static_cast<long long>(y0) * pitch + x0;
-        v00 = (xin0 && yin0) ? __ldg(r0) : 0.0f;
-        v01 = (xin1 && yin0) ? __ldg(r0 + 1) : 0.0f;
-        v10 = (xin0 && yin1) ? __ldg(r0 + pitch) : 0.0f;
-        v11 = (xin1 && yin1) ? __ldg(r0 + pitch + 1) : 0.0f;
+    for (int l = 0; l < 4; ++l) {
+      const int y0 = cin[wq][l * 18 + 9 + b];
+      const float fy = cfr[wq][l * 18 + 9 + b];
+      const int XA = xa[l], wy = y0 - y0w[l];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int a = a0 + i;
+        const int x0 = cin[wq][l * 18 + a];
+        const float fx = cfr[wq][l * 18 + a];
+        const int wx = x0 - XA;
+        float v00, v01, v10, v11;
+        if (wx >= 0 && wx + 1 < kLkWinW && wy >= 0 && wy + 1 < kLkWinH) {
+          const float* wp = &win[wq][l][wy * kLkWinW + wx];
+          v00 = wp[0]; v01 = wp[1]; v10 = wp[kLkWinW]; v11 = wp[kLkWinW + 1];
+        } else {   // not reachable for finite coordinates near the image; kept exact for robustness
+          const int H = h0 >> l, W = w0 >> l;
+          const int pitch = l == 0 ? p.pitch[0] : l == 1 ? p.pitch[1] : l == 2 ? p.pitch[2] : p.pitch[3];
+          const float* lv = l == 0 ? p.lvl[0] : l == 1 ? p.lvl[1] : l == 2 ? p.lvl[2] : p.lvl[3];
+          const float* base = lv + q * static_cast<long long>(H) * pitch;
+          const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
+          const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
+          const float* r0 = base + static_cast<long long>(y0) * pitch + x0;
+          v00 = (xin0 && yin0) ? __ldg(r0) : 0.0f;
+          v01 = (xin1 && yin0) ? __ldg(r0 + 1) : 0.0f;
+          v10 = (xin0 && yin1) ? __ldg(r0 + pitch) : 0.0f;
+          v11 = (xin1 && yin1) ? __ldg(r0 + pitch + 1) : 0.0f;
+        }
+        res[l][i] = v00 * ((1.0f - fx) * (1.0f - fy)) + v01 * (fx * (1.0f - fy)) + v10 * ((1.0f - fx) * fy) + v11 * (fx * fy);
       }
-      val[j] = v00 * ((1.0f - fx) * (1.0f - fy)) + v01 * (fx * (1.0f - fy)) + v10 * ((1.0f - fx) * fy) + v11 * (fx * fy);
     }
-    if (out16) *reinterpret_cast<__half2*>(out16 + q * out_pitch + c2 * 2) = __floats2half2_rn(val[0], val[1]);
-    if (out32) *reinterpret_cast<float2*>(out32 + q * 324 + c2 * 2) = make_float2(val[0], val[1]);
+  }
+  __syncwarp();                                    // every lane is done with the windows: reuse them as output staging
+  float* outs = &win[wq][0][0];
+  if (lane < 27) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) outs[l * 81 + (a0 + i) * 9 + b] = res[l][i];
+  }
+  __syncwarp();
+
+  // 4. coalesced output: 8 consecutive channels per lane and store
+  for (int c8 = lane; c8 < 41; c8 += 32) {
+    const float4 f0 = *reinterpret_cast<const float4*>(&outs[c8 * 8]);
+    if (c8 < 40) {
+      const float4 f1 = *reinterpret_cast<const float4*>(&outs[c8 * 8 + 4]);
+      if (out16) {
+        __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
+        __half2 h2 = __floats2half2_rn(f1.x, f1.y), h3 = __floats2half2_rn(f1.z, f1.w);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(out16 + q * out_pitch + c8 * 8) = u;
+      }
+      if (out32) {
+        *reinterpret_cast<float4*>(out32 + q * 324 + c8 * 8) = f0;
+        *reinterpret_cast<float4*>(out32 + q * 324 + c8 * 8 + 4) = f1;
+      }
+    } else {   // channels 320..323
+      if (out16) {
+        __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(out16 + q * out_pitch + 320) = u;
+      }
+      if (out32) *reinterpret_cast<float4*>(out32 + q * 324 + 320) = f0;
+    }
   }
 }
 
@@ -591,7 +666,10 @@ extern "C" int atdn_corr_lookup(const float* const lvl[4], const int32_t lvl_pit
     w /= 2;
   }
   const long long nq = static_cast<long long>(batch) * h8 * w8;
-  ATDN_REQUIRE(!out16 || (out_pitch % 2 == 0 && (reinterpret_cast<uintptr_t>(out16) & 3u) == 0), ATDN_ERR_ALIGN, "atdn_corr_lookup: out16 must be 4-byte aligned with an even pitch");
+  ATDN_REQUIRE(!out16 || (out_pitch % 8 == 0 && aligned16(out16)), ATDN_ERR_ALIGN, "atdn_corr_lookup: out16 must be 16-byte aligned with a pitch that is a multiple of 8");
+  ATDN_REQUIRE(!out32 || aligned16(out32), ATDN_ERR_ALIGN, "atdn_corr_lookup: out32 must be 16-byte aligned");
+  for (int l = 0; l < 4; ++l)
+    ATDN_REQUIRE(lvl_pitch[l] % 4 == 0 && aligned16(lvl[l]), ATDN_ERR_ALIGN, "atdn_corr_lookup: level %d must be 16-byte aligned with a pitch that is a multiple of 4", l);
   corr_lookup_kernel<<<static_cast<unsigned>((nq + kLkWarps - 1) / kLkWarps), kLkWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       p, coords, static_cast<__half*>(out16), out_pitch, out32, nq);
   ATDN_CUDA(cudaGetLastError());

@@ -47,6 +47,7 @@ class Conv32Desc(C.Structure):
         ("bn2_scale", C.c_void_p), ("bn2_shift", C.c_void_p),
         ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
         ("k", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("mish", C.c_int32),
+        ("w_host", C.c_void_p),
     ]
 
 

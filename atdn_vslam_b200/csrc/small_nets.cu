@@ -279,6 +279,183 @@ static int launch_conv16(Conv32Params p, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Same tiling with the WEIGHTS IN THE CONSTANT BANK: the whole filter ([ci][ky][kx][16 co], <= 9 KiB) travels as a
+// __grid_constant__ kernel parameter, every FFMA takes its weight through the uniform datapath (ULDC -> UR operand)
+// and shared memory only carries the input tile.  conv16_kernel spends one 128-bit shared load per 16 FMAs on the
+// weights, which caps it at half the FP32 rate (shared-memory bandwidth: 4 clk per LDS.128 vs 4 clk for 16 warp-wide
+// FFMAs on the four schedulers); here the only shared loads are the (PX-1)*S+K inputs per filter row.
+//   CTA = 128 threads = (64/PX) x (2*PX) threads, tile = 64 x (2*PX) output pixels, thread = PX consecutive pixels x 16
+//   channels.  Needs a HOST copy of the weights at launch (atdn_conv32_desc.w_host).
+// ------------------------------------------------------------------------------------------------
+template <int K, int CIN>
+struct alignas(16) C16Weights {
+  float w[CIN * K * K * 16];
+};
+
+template <int K, int S, int PX>
+struct C16cGeom {
+  static constexpr int TXN = 64 / PX, TH = kC16Threads / TXN;
+  static constexpr int IH = (TH - 1) * S + K;
+  static constexpr int IW = 63 * S + K;
+  static constexpr int NV = (PX - 1) * S + K;                // input values per thread and filter row
+  static constexpr int HALF = ((IW + 1) / 2 + 3) / 4 * 4 + 4;
+  static constexpr int PITCH = S == 1 ? (IW + 3) / 4 * 4 + 4 : 2 * HALF;
+};
+
+template <int K, int S, int CIN, int CIT, int PX>
+__global__ void __launch_bounds__(kC16Threads) conv16c_kernel(const __grid_constant__ Conv32Params p,
+                                                              const __grid_constant__ C16Weights<K, CIN> wt) {
+  using G = C16cGeom<K, S, PX>;
+  static_assert(CIN % CIT == 0, "input channels are staged in whole chunks");
+  extern __shared__ float sm[];
+  float* s_in = sm;                                 // [CIT][IH][PITCH]
+  const int tx = threadIdx.x % G::TXN, ty = threadIdx.x / G::TXN;
+  const int tile_x = blockIdx.x % p.tiles_x, tile_y = blockIdx.x / p.tiles_x;
+  const int b = blockIdx.z;
+  const int ox0 = tile_x * 64 + tx * PX, oy = tile_y * G::TH + ty;
+  const int ix0 = tile_x * 64 * S - p.pad, iy0 = tile_y * G::TH * S - p.pad;
+  float acc[PX][16];
+#pragma unroll
+  for (int i = 0; i < PX; ++i)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[i][c] = 0.0f;
+
+#pragma unroll 1
+  for (int ci0 = 0; ci0 < CIN; ci0 += CIT) {
+    if (ci0) __syncthreads();
+    constexpr int kN = CIT * G::IH * G::IW;
+    for (int i0 = threadIdx.x; i0 < kN; i0 += kC16Threads * 8) {
+      float v[8];
+      int dst[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * kC16Threads;
+        v[u] = 0.0f;
+        dst[u] = -1;
+        if (i < kN) {
+          const int c = i / (G::IH * G::IW), r = i - c * (G::IH * G::IW);
+          const int ry = r / G::IW, rx = r - ry * G::IW;
+          const int yy = iy0 + ry, xx = ix0 + rx, ci = ci0 + c;
+          dst[u] = (c * G::IH + ry) * G::PITCH + (S == 1 ? rx : (rx & 1) * G::HALF + (rx >> 1));
+          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+            v[u] = __ldg(p.x + ((static_cast<long long>(b) * CIN + ci) * p.H + yy) * p.W + xx);
+            if (p.in_scale) v[u] = v[u] * __ldg(p.in_scale + ci) + __ldg(p.in_shift + ci);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (dst[u] >= 0) s_in[dst[u]] = v[u];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < CIT; ++c) {
+      const float* wc = wt.w + (ci0 + c) * (K * K * 16);     // warp-uniform: constant-bank operands
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const float* row = s_in + (c * G::IH + ty * S + ky) * G::PITCH;
+        float in[(G::NV + 3) / 4 * 4 + 4];
+        if (S == 1) {
+#pragma unroll
+          for (int q = 0; q < (G::NV + 3) / 4; ++q) {
+            const float4 f = *reinterpret_cast<const float4*>(row + tx * PX + q * 4);
+            in[4 * q] = f.x; in[4 * q + 1] = f.y; in[4 * q + 2] = f.z; in[4 * q + 3] = f.w;
+          }
+        } else {
+          constexpr int NE = (G::NV + 1) / 2, NO = G::NV / 2;      // even / odd values needed
+          float ev[(NE + 3) / 4 * 4], od[(NO + 3) / 4 * 4];
+#pragma unroll
+          for (int q = 0; q < (NE + 3) / 4; ++q) {
+            const float4 f = *reinterpret_cast<const float4*>(row + tx * PX + q * 4);
+            ev[4 * q] = f.x; ev[4 * q + 1] = f.y; ev[4 * q + 2] = f.z; ev[4 * q + 3] = f.w;
+          }
+#pragma unroll
+          for (int q = 0; q < (NO + 3) / 4; ++q) {
+            const float4 f = *reinterpret_cast<const float4*>(row + G::HALF + tx * PX + q * 4);
+            od[4 * q] = f.x; od[4 * q + 1] = f.y; od[4 * q + 2] = f.z; od[4 * q + 3] = f.w;
+          }
+#pragma unroll
+          for (int j = 0; j < G::NV; ++j) in[j] = (j & 1) ? od[j >> 1] : ev[j >> 1];
+        }
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+#pragma unroll
+          for (int co = 0; co < 16; ++co) {
+            const float w = wc[(ky * K + kx) * 16 + co];
+#pragma unroll
+            for (int i = 0; i < PX; ++i) acc[i][co] = fmaf(in[i * S + kx], w, acc[i][co]);
+          }
+        }
+      }
+    }
+  }
+  if (oy >= p.OH) return;
+  const bool vec = (p.OW & 3) == 0;
+#pragma unroll
+  for (int co = 0; co < 16; ++co) {
+    const long long o = ((static_cast<long long>(b) * 16 + co) * p.OH + oy) * p.OW + ox0;
+    const float bias = p.bias ? __ldg(p.bias + co) : 0.0f;
+    const float s1 = p.bn_scale ? __ldg(p.bn_scale + co) : 1.0f, h1 = p.bn_scale ? __ldg(p.bn_shift + co) : 0.0f;
+    const float s2 = p.bn2_scale ? __ldg(p.bn2_scale + co) : 1.0f, h2 = p.bn2_scale ? __ldg(p.bn2_shift + co) : 0.0f;
+#pragma unroll
+    for (int g = 0; g < PX / 4; ++g) {
+      const int ox = ox0 + g * 4;
+      const bool v4 = vec && ox + 4 <= p.OW;
+      float v[4], sk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (p.skip) {
+        if (v4) {
+          const float4 f = *reinterpret_cast<const float4*>(p.skip + o + g * 4);
+          sk[0] = f.x; sk[1] = f.y; sk[2] = f.z; sk[3] = f.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (ox + i < p.OW) sk[i] = p.skip[o + g * 4 + i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float t = acc[g * 4 + i][co] + bias;
+        if (p.mish) t = mishf(t);
+        if (p.bn_scale) t = t * s1 + h1;
+        if (p.skip) {
+          t = mishf(t + sk[i]);
+          if (p.bn2_scale) t = t * s2 + h2;
+        }
+        v[i] = t;
+      }
+      if (v4) {
+        *reinterpret_cast<float4*>(p.y + o + g * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ox + i < p.OW) p.y[o + g * 4 + i] = v[i];
+      }
+    }
+  }
+}
+
+template <int K, int S, int CIN, int CIT, int PX>
+static int launch_conv16c(Conv32Params p, const float* w_host, cudaStream_t stream) {
+  using G = C16cGeom<K, S, PX>;
+  constexpr int smem = CIT * G::IH * G::PITCH * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    if (smem > 48 * 1024)
+      ATDN_CUDA(cudaFuncSetAttribute(conv16c_kernel<K, S, CIN, CIT, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  C16Weights<K, CIN> wt;                             // [co][ci][ky][kx] (PyTorch) -> [ci][ky][kx][co]
+  for (int co = 0; co < 16; ++co)
+    for (int ci = 0; ci < CIN; ++ci)
+      for (int t = 0; t < K * K; ++t) wt.w[(ci * K * K + t) * 16 + co] = w_host[(co * CIN + ci) * K * K + t];
+  p.tiles_x = ceil_div(p.OW, 64);
+  dim3 grid(p.tiles_x * ceil_div(p.OH, G::TH), 1, p.B);
+  conv16c_kernel<K, S, CIN, CIT, PX><<<grid, kC16Threads, smem, stream>>>(p, wt);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Linear (+Mish) and LSTM cell: one warp per output row, looping over the batch
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear32_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -406,8 +583,13 @@ extern "C" int atdn_conv32(const atdn_conv32_desc* d, void* stream) {
   p.OH = (d->in_h + 2 * d->pad - d->k) / d->stride + 1;
   p.OW = (d->in_w + 2 * d->pad - d->k) / d->stride + 1;
   ATDN_REQUIRE(p.OH >= 1 && p.OW >= 1, ATDN_ERR_ARG, "atdn_conv32: empty output");
-  if (d->cout == 16 && d->cin <= 16 && p.OW >= 32) {   // CLVO encoder hot layers: register-tiled kernel
+  if (d->cout == 16 && d->cin <= 16 && p.OW >= 32) {   // CLVO encoder hot layers: register-tiled kernels
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->w_host) {                                     // weights through the constant bank
+      if (d->k == 3 && d->stride == 1 && d->cin == 16) return launch_conv16c<3, 1, 16, 8, 4>(p, d->w_host, st);
+      if (d->k == 3 && d->stride == 2 && d->cin == 16) return launch_conv16c<3, 2, 16, 4, 4>(p, d->w_host, st);
+      if (d->k == 7 && d->stride == 2 && d->cin == 2) return launch_conv16c<7, 2, 2, 2, 4>(p, d->w_host, st);
+    }
     if (d->k == 3 && d->stride == 1) return launch_conv16<3, 1, 8>(p, st);
     if (d->k == 3 && d->stride == 2) return launch_conv16<3, 2, 4>(p, st);
     if (d->k == 7 && d->stride == 2 && d->cin <= 2) return launch_conv16<7, 2, 2>(p, st);

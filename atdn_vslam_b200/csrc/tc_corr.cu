@@ -18,11 +18,18 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_fp16.h>
+
 #include "common.h"
 #include "tc_host.cuh"
 #include "tc_ptx.cuh"
 
 namespace atdn {
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 constexpr int kCorrThreads = 384;
 constexpr int kCorrBStages = 3;                    // ring of 256 x 64 fp16 chunks of the target tile (32 KiB each)
@@ -38,8 +45,11 @@ struct alignas(64) CorrParams {
   int dbg;                // experiment switches (ATDN_CORR_DBG): 1 = no level 1..3 stores, 2 = no stores, 4 = LSU level-0 stores
   float* l0;
   int n, pitch0;
+  __half* l3;             // HALF: level 3 is stored by the threads directly
+  int pitch3;
 };
 
+template <bool HALF>
 __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __grid_constant__ CorrParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full, b_full[kCorrBStages], b_empty[kCorrBStages], acc_full[2], acc_empty[2];
@@ -65,7 +75,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
   if (warp == 2 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    for (int l = 0; l < 4; ++l) tma_prefetch_desc(&p.tmL[l]);
+    for (int l = 0; l < (HALF ? 3 : 4); ++l) tma_prefetch_desc(&p.tmL[l]);
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
   tcgen05_fence_before();
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
         float c[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) c[j] = p.alpha * __uint_as_float(v[j]);
-        if (p.dbg & 4) {
+        if (!HALF && (p.dbg & 4)) {
           // LSU path: transpose through the swizzled slot, then 8 lanes write one 128-byte row segment
           const int off = (nstore & 1) * kCorrSlotBytes;
           ++nstore;
@@ -192,11 +202,20 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
           }
         } else if (!(p.dbg & 2)) {
           const int off = acquire();
+          if constexpr (HALF) {
+            // 64 bytes per query, 64B swizzle: 16-byte chunk index ^= (row / 2) & 3 (conflict-free across 8 lanes)
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
-            st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4),
-                         make_uint4(__float_as_uint(c[4 * ch]), __float_as_uint(c[4 * ch + 1]), __float_as_uint(c[4 * ch + 2]),
-                                    __float_as_uint(c[4 * ch + 3])));
+            for (int ch = 0; ch < 4; ++ch)
+              st_shared_v4(st_u32 + off + lane * 64 + ((static_cast<uint32_t>(ch) ^ (static_cast<uint32_t>(lane >> 1) & 3u)) << 4),
+                           make_uint4(pack_half2(c[8 * ch], c[8 * ch + 1]), pack_half2(c[8 * ch + 2], c[8 * ch + 3]),
+                                      pack_half2(c[8 * ch + 4], c[8 * ch + 5]), pack_half2(c[8 * ch + 6], c[8 * ch + 7])));
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4),
+                           make_uint4(__float_as_uint(c[4 * ch]), __float_as_uint(c[4 * ch + 1]), __float_as_uint(c[4 * ch + 2]),
+                                      __float_as_uint(c[4 * ch + 3])));
+          }
           commit(&p.tmL[0], off, bw0, h);
         }
         if ((hl & 1) == 0) {
@@ -209,11 +228,20 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
           const int r1 = h >> 1;
           if (r1 < H1 && !(p.dbg & 3)) {
             const int off = acquire();
+            if constexpr (HALF) {
+              // 32 bytes per query, 32B swizzle: chunk index ^= (row / 4) & 1
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-              st_shared_v4(st_u32 + off + lane * 64 + ch * 16,
-                           make_uint4(__float_as_uint(l1[4 * ch]), __float_as_uint(l1[4 * ch + 1]), __float_as_uint(l1[4 * ch + 2]),
-                                      __float_as_uint(l1[4 * ch + 3])));
+              for (int ch = 0; ch < 2; ++ch)
+                st_shared_v4(st_u32 + off + lane * 32 + ((static_cast<uint32_t>(ch) ^ (static_cast<uint32_t>(lane >> 2) & 1u)) << 4),
+                             make_uint4(pack_half2(l1[8 * ch], l1[8 * ch + 1]), pack_half2(l1[8 * ch + 2], l1[8 * ch + 3]),
+                                        pack_half2(l1[8 * ch + 4], l1[8 * ch + 5]), pack_half2(l1[8 * ch + 6], l1[8 * ch + 7])));
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch)
+                st_shared_v4(st_u32 + off + lane * 64 + ch * 16,
+                             make_uint4(__float_as_uint(l1[4 * ch]), __float_as_uint(l1[4 * ch + 1]), __float_as_uint(l1[4 * ch + 2]),
+                                        __float_as_uint(l1[4 * ch + 3])));
+            }
             commit(&p.tmL[1], off, bw0 >> 1, r1);
           }
           if ((hl & 3) == 1) {
@@ -226,11 +254,16 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
             const int r2 = h >> 2;
             if (r2 < H2 && !(p.dbg & 3)) {
               const int off = acquire();
+              if constexpr (HALF) {
+                st_shared_v4(st_u32 + off + lane * 16,
+                             make_uint4(pack_half2(l2[0], l2[1]), pack_half2(l2[2], l2[3]), pack_half2(l2[4], l2[5]), pack_half2(l2[6], l2[7])));
+              } else {
 #pragma unroll
-              for (int ch = 0; ch < 2; ++ch)
-                st_shared_v4(st_u32 + off + lane * 32 + ch * 16,
-                             make_uint4(__float_as_uint(l2[4 * ch]), __float_as_uint(l2[4 * ch + 1]), __float_as_uint(l2[4 * ch + 2]),
-                                        __float_as_uint(l2[4 * ch + 3])));
+                for (int ch = 0; ch < 2; ++ch)
+                  st_shared_v4(st_u32 + off + lane * 32 + ch * 16,
+                               make_uint4(__float_as_uint(l2[4 * ch]), __float_as_uint(l2[4 * ch + 1]), __float_as_uint(l2[4 * ch + 2]),
+                                          __float_as_uint(l2[4 * ch + 3])));
+              }
               commit(&p.tmL[2], off, bw0 >> 2, r2);
             }
             if (hl == 3) {
@@ -238,11 +271,18 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
               for (int j = 0; j < 4; ++j) hs3[j] = l2[2 * j] + l2[2 * j + 1];
             } else {
               const int r3 = h >> 3;
-              if (r3 < H3 && !(p.dbg & 3)) {
+              const float l3a = (hs3[0] + (l2[0] + l2[1])) * 0.25f, l3b = (hs3[1] + (l2[2] + l2[3])) * 0.25f;
+              const float l3c = (hs3[2] + (l2[4] + l2[5])) * 0.25f, l3d = (hs3[3] + (l2[6] + l2[7])) * 0.25f;
+              if constexpr (HALF) {
+                // 4 fp16 = 8 bytes per query: below the 16-byte TMA box granularity, so every thread stores its own
+                // (1% of the pyramid bytes; neighbouring tiles complete the 32-byte sectors while they sit in L2)
+                if (r3 < H3 && qrow + lane < p.n && !(p.dbg & 3))
+                  *reinterpret_cast<uint2*>(p.l3 + ((static_cast<long long>(batch) * p.n + qrow + lane) * H3 + r3) * p.pitch3 + (bw0 >> 3)) =
+                      make_uint2(pack_half2(l3a, l3b), pack_half2(l3c, l3d));
+              } else if (r3 < H3 && !(p.dbg & 3)) {
                 const int off = acquire();
                 st_shared_v4(st_u32 + off + lane * 16,
-                             make_uint4(__float_as_uint((hs3[0] + (l2[0] + l2[1])) * 0.25f), __float_as_uint((hs3[1] + (l2[2] + l2[3])) * 0.25f),
-                                        __float_as_uint((hs3[2] + (l2[4] + l2[5])) * 0.25f), __float_as_uint((hs3[3] + (l2[6] + l2[7])) * 0.25f)));
+                             make_uint4(__float_as_uint(l3a), __float_as_uint(l3b), __float_as_uint(l3c), __float_as_uint(l3d)));
                 commit(&p.tmL[3], off, bw0 >> 3, r3);
               }
             }
@@ -271,11 +311,12 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
 using namespace atdn;
 
 extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t fmap_pitch, int32_t channels,
-                                 float* const lvl[4], const int32_t lvl_pitch[4], int32_t batch, int32_t h8, int32_t w8,
-                                 float alpha, void* stream_) {
+                                 void* const lvl[4], const int32_t lvl_pitch[4], int32_t half_levels, int32_t batch,
+                                 int32_t h8, int32_t w8, float alpha, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int e = require_sm100()) return e;
   ATDN_REQUIRE(fmap1 && fmap2 && lvl && lvl_pitch && batch > 0, ATDN_ERR_ARG, "atdn_corr_pyramid: null / empty argument");
+  ATDN_REQUIRE(half_levels == 0 || half_levels == 4, ATDN_ERR_UNSUP, "atdn_corr_pyramid: half_levels must be 0 (fp32 pyramid) or 4 (fp16 pyramid), got %d", half_levels);
   ATDN_REQUIRE(channels == 256, ATDN_ERR_UNSUP, "atdn_corr_pyramid: %d feature channels (the GMA feature net has 256)", channels);
   ATDN_REQUIRE(h8 >= 16 && w8 >= 16, ATDN_ERR_ARG, "atdn_corr_pyramid: grid %dx%d is smaller than 16x16 (level 3 would be < 2x2)", h8, w8);
   ATDN_REQUIRE(fmap_pitch >= channels && fmap_pitch % 8 == 0, ATDN_ERR_ALIGN, "atdn_corr_pyramid: fmap_pitch %lld", (long long)fmap_pitch);
@@ -291,7 +332,9 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
     const char* dbg = getenv("ATDN_CORR_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
   }
-  p.l0 = lvl[0];
+  p.l0 = static_cast<float*>(lvl[0]);
+  p.l3 = static_cast<__half*>(lvl[3]);
+  p.pitch3 = lvl_pitch[3];
   p.n = n;
   p.pitch0 = lvl_pitch[0];
   const uint32_t ones[4] = {1, 1, 1, 1};
@@ -309,20 +352,30 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
   }
   int hl = h8, wl = w8;
   for (int l = 0; l < 4; ++l) {
-    ATDN_REQUIRE(lvl[l] != nullptr && lvl_pitch[l] % 4 == 0 && lvl_pitch[l] >= wl, ATDN_ERR_ALIGN, "atdn_corr_pyramid: level %d pitch %d", l, lvl_pitch[l]);
+    const bool half = l < half_levels;
+    ATDN_REQUIRE(lvl[l] != nullptr && lvl_pitch[l] % (half ? 8 : 4) == 0 && lvl_pitch[l] >= wl, ATDN_ERR_ALIGN, "atdn_corr_pyramid: level %d pitch %d", l, lvl_pitch[l]);
     const int64_t dims[4] = {wl, hl, n, batch};
     const int64_t str[3] = {lvl_pitch[l], (int64_t)hl * lvl_pitch[l], (int64_t)n * hl * lvl_pitch[l]};
     const uint32_t box[4] = {32u >> l, 1, 32, 1};
-    if (int e = make_map(&p.tmL[l], 4, l == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, lvl[l], dims, str, box, ones, "pyramid level")) return e;
+    // staging layouts of the epilogue: fp32 level 0 = 128-byte rows (128B swizzle); fp16 level 0 / 1 = 64 / 32-byte rows
+    // (64B / 32B swizzle), fp16 level 2 = 16-byte rows; everything else is stored unswizzled
+    const CUtensorMapSwizzle swz = half ? (l == 0 ? CU_TENSOR_MAP_SWIZZLE_64B : l == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)
+                                        : (l == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (half && l == 3) break;                     // 8-byte rows: stored without TMA
+    if (int e = make_map(&p.tmL[l], half ? 2 : 4, swz, lvl[l], dims, str, box, ones, "pyramid level")) return e;
     hl /= 2;
     wl /= 2;
   }
   static bool configured = false;
   if (!configured) {
-    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
+    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
+    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
     configured = true;
   }
-  corr_pyramid_kernel<<<dim3(ceil_div(n, 128), batch), kCorrThreads, kCorrSmem, stream>>>(p);
+  if (half_levels)
+    corr_pyramid_kernel<true><<<dim3(ceil_div(n, 128), batch), kCorrThreads, kCorrSmem, stream>>>(p);
+  else
+    corr_pyramid_kernel<false><<<dim3(ceil_div(n, 128), batch), kCorrThreads, kCorrSmem, stream>>>(p);
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }

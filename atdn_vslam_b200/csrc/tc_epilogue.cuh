@@ -52,6 +52,19 @@ __device__ __forceinline__ void unpack8_f16(const uint4& u, float* y) {
   y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y; y[4] = c.x; y[5] = c.y; y[6] = d.x; y[7] = d.y;
 }
 
+// The fp32 recurrent state (h32: GRU hidden state master copy, z32: update gate) lives in a TILED layout so that the
+// thread-per-accumulator-row epilogues access it coalesced: a warp of the halo kernel owns 32 pixels of one 16 x 8
+// sub-tile (r = q * 32 + lane, pixel = (r >> 3, r & 7)), and with the natural [pixel][128] layout every one of its
+// float4 accesses touched 32 different 512-byte rows (the GRU_Q epilogue ran 46K cycles per tile against 25K for the
+// MMAs: L1 transaction bound).  Layout: float4 index = ((sub-tile * 4 + q) * 32 + c4) * 32 + lane for channels
+// 4*c4 .. 4*c4+3, sub-tile = (batch * ceil(H/16) + h/16) * ceil(W/8) + w/8: one warp access = 512 contiguous bytes.
+// Size: batch * ceil(H/16)*16 * ceil(W/8)*8 * 128 floats.
+__device__ __forceinline__ long long state_index(int b, int h, int w, int img_h, int img_w) {
+  const int th_n = (img_h + 15) >> 4, tw_n = (img_w + 7) >> 3;
+  const int r = ((h & 15) << 3) | (w & 7);
+  return ((((static_cast<long long>(b) * th_n + (h >> 4)) * tw_n + (w >> 3)) * 4 + (r >> 5)) * 32) * 32 + (r & 31);
+}
+
 // fp16 store of `ng` complete 8-column groups followed by `tail` (< 8) single columns
 __device__ __forceinline__ void store_row_f16(__half* dst, const float (&y)[32], int ng, int tail) {
 #pragma unroll
@@ -68,10 +81,18 @@ __device__ __forceinline__ void store_row_f16(__half* dst, const float (&y)[32],
   }
 }
 
+// sidx: state_index() of the pixel (float4 units), or < 0 to derive it from pix = (b * img_h + h) * img_w + w
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, long long pix, int n,
-                                               const uint32_t (&v)[32]) {
+                                               const uint32_t (&v)[32], long long sidx = -1) {
   if (n >= p.n_valid) return;
+  if constexpr (EPI == ATDN_EPI_STORE16 || EPI == ATDN_EPI_GRU_ZR || EPI == ATDN_EPI_GRU_Q) {
+    if (sidx < 0 && valid && (EPI != ATDN_EPI_STORE16 || (p.flags & ATDN_F_TANH_LO))) {
+      const int w = static_cast<int>(pix % p.img_w);
+      const long long t = pix / p.img_w;
+      sidx = state_index(static_cast<int>(t / p.img_h), static_cast<int>(t % p.img_h), w, p.img_h, p.img_w);
+    }
+  }
   const int nv = min(32, p.n_valid - n);   // valid columns of this chunk
   const int ng = nv >> 3, tail = nv & 7;
   float y[32];
@@ -105,9 +126,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       if (n < 128) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] = tanh_fast(y[j]);
-        float4* h = reinterpret_cast<float4*>(p.h32 + pix * 128 + n);
+        float4* h = reinterpret_cast<float4*>(p.h32) + sidx + (n >> 2) * 32;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+        for (int i = 0; i < 8; ++i) h[i * 32] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
@@ -148,15 +169,15 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
     }
   } else if constexpr (EPI == ATDN_EPI_GRU_ZR) {
     if (n < 128) {
-      float4* z = reinterpret_cast<float4*>(p.z32 + pix * 128 + n);
+      float4* z = reinterpret_cast<float4*>(p.z32) + sidx + (n >> 2) * 32;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        z[i] = make_float4(sigmoid_fast(y[4 * i]), sigmoid_fast(y[4 * i + 1]), sigmoid_fast(y[4 * i + 2]), sigmoid_fast(y[4 * i + 3]));
+        z[i * 32] = make_float4(sigmoid_fast(y[4 * i]), sigmoid_fast(y[4 * i + 1]), sigmoid_fast(y[4 * i + 2]), sigmoid_fast(y[4 * i + 3]));
     } else {
-      const float4* h = reinterpret_cast<const float4*>(p.h32 + pix * 128 + (n - 128));
+      const float4* h = reinterpret_cast<const float4*>(p.h32) + sidx + ((n - 128) >> 2) * 32;
       float4 hv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) hv[i] = h[i];
+      for (int i = 0; i < 8; ++i) hv[i] = h[i * 32];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         y[4 * i + 0] = sigmoid_fast(y[4 * i + 0]) * hv[i].x;
@@ -169,11 +190,11 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       for (int g = 0; g < 4; ++g) dst[g] = pack8_f16(&y[g * 8]);
     }
   } else if constexpr (EPI == ATDN_EPI_GRU_Q) {
-    float4* h = reinterpret_cast<float4*>(p.h32 + pix * 128 + n);
-    const float4* z = reinterpret_cast<const float4*>(p.z32 + pix * 128 + n);
+    float4* h = reinterpret_cast<float4*>(p.h32) + sidx + (n >> 2) * 32;
+    const float4* z = reinterpret_cast<const float4*>(p.z32) + sidx + (n >> 2) * 32;
     float4 hv[8], zv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { hv[i] = h[i]; zv[i] = z[i]; }
+    for (int i = 0; i < 8; ++i) { hv[i] = h[i * 32]; zv[i] = z[i * 32]; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       y[4 * i + 0] = (1.0f - zv[i].x) * hv[i].x + zv[i].x * tanh_fast(y[4 * i + 0]);
@@ -182,7 +203,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       y[4 * i + 3] = (1.0f - zv[i].w) * hv[i].w + zv[i].w * tanh_fast(y[4 * i + 3]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    for (int i = 0; i < 8; ++i) h[i * 32] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n);
 #pragma unroll
     for (int g = 0; g < 4; ++g) dst[g] = pack8_f16(&y[g * 8]);

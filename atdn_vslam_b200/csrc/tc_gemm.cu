@@ -517,6 +517,8 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
   p.e.rh16 = static_cast<__half*>(d->rh16);
   p.e.aux32 = d->aux32;
   p.e.gamma = d->gamma;
+  p.e.img_h = d->out_h > 0 ? d->out_h : 1;   // pixel decode of the tiled recurrent-state layout (tc_epilogue.cuh)
+  p.e.img_w = d->out_w > 0 ? d->out_w : 1;
   ATDN_REQUIRE(p.e.out != nullptr || d->epi == ATDN_EPI_GRU_ZR, ATDN_ERR_ARG, "atdn_tc_gemm: null output");
 
   const uint32_t ones[4] = {1, 1, 1, 1};

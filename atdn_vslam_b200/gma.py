@@ -10,8 +10,10 @@ Data layout in HBM (per batch of B pairs, 1/8-resolution grid H8 x W8, N = H8*W8
   HX  [B,H8,W8,512] fp16 : [0:128] GRU hidden state h | [128:256] context inp | [256:384] motion
                           features | [384:512] globally aggregated motion features  (the reference's
                           torch.cat([net, inp, mf, mfg]) materialised once, never copied)
-  h32 [B*N,128]    fp32 master copy of the hidden state (recurrent precision)
-  corr pyramid     fp32 [B*N, H_l, pitch_l] for l = 0..3 (pitch = W_l rounded up to 32/16/8/8 floats: sector-aligned store boxes)
+  h32, z32         fp32 master copy of the hidden state (recurrent precision) and the update gate, in the tiled
+                   layout of csrc/tc_epilogue.cuh (one warp access = 512 contiguous bytes; ops.state_alloc)
+  corr pyramid     fp16 [B*N, H_l, pitch_l] for l = 0..3 (pitch = W_l rounded up to 32/16/8/8 elements: sector-aligned
+                   store boxes), pooled in fp32 and rounded once on store; CorrBlock keeps the reference's fp32 pyramid
   P   [B,N,Np]     fp16 un-normalised attention probabilities exp(s - max), Np = N rounded up to 64
                    (written by the fused q.k^T/softmax kernel: the fp32 logits never reach HBM);
   inv_sum [B*N]    fp32 1/sum(P) applied in the P.V epilogue
@@ -185,10 +187,10 @@ class _Plan:
         self.enc = {}          # encoder scratch keyed by number of images
         h8, w8 = self.h8, self.w8
         self.hx = f16(b, h8, w8, 512)
-        self.h32 = f32(b * n, 128)
-        self.z32 = f32(b * n, 128)
+        self.h32 = ops.state_alloc(b, h8, w8, dev)     # tiled fp32 state layout (csrc/tc_epilogue.cuh)
+        self.z32 = ops.state_alloc(b, h8, w8, dev)
         self.rh = f16(b, h8, w8, 128)
-        self.pyr = ops.alloc_pyramid(b, h8, w8, dev)
+        self.pyr = ops.alloc_pyramid(b, h8, w8, dev, half_levels=4)
         self.qk = f16(b, h8, w8, 256)
         self.p16 = f16(b, n, self.np_)
         self.inv_sum = f32(b * n)
@@ -362,7 +364,7 @@ class RAFTGMA(nn.Module):
         b, h, w = plan.b, plan.h, plan.w
         h8, w8, n, np_ = plan.h8, plan.w8, plan.n, plan.np_
         m_tiles = b * math.ceil(h8 / 8) * math.ceil(w8 / 16)
-        # fp32-accumulated all-pairs correlation pyramid (corr.py:16-30)
+        # fp32-accumulated all-pairs correlation pyramid (corr.py:16-30), rounded to fp16 on store
         ops.corr_pyramid_build(fmap1, fmap2, plan.pyr)
 
         # context network: net = tanh(.) -> HX[0:128] + h32, inp = relu(.) -> HX[128:256]

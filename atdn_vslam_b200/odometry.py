@@ -33,6 +33,7 @@ class _ConvBlock:
 
     def __init__(self, sd, p):
         self.w = sd[p + "conv.weight"].float().contiguous()
+        self.w_host = self.w.cpu().contiguous()      # constant-bank path of atdn_conv32 (kernel-parameter weights)
         self.b = sd[p + "conv.bias"].float().contiguous()
         self.bn_s, self.bn_b = _bn_affine(sd, p + "bn")
 
@@ -59,7 +60,7 @@ def run_conv_block(x, blk, stride, pad, in_scale=None, in_shift=None, skip=None,
                     dtype=torch.float32, device=x.device)
     ops.conv32(x, blk.w, blk.b, y, stride=stride, pad=pad, mish=True, in_scale=in_scale, in_shift=in_shift,
                bn_scale=blk.bn_s, bn_shift=blk.bn_b, skip=skip, bn2_scale=bn2[0] if bn2 else None,
-               bn2_shift=bn2[1] if bn2 else None)
+               bn2_shift=bn2[1] if bn2 else None, w_host=blk.w_host)
     return y
 
 

@@ -149,6 +149,34 @@ def gemm_rows(a, a_k, a_rows, a_pitch, batch, b, b_rows, b_pitch, out_ptr, out_p
 
 
 # ----------------------------------------------------------------------------------------------
+# fp32 recurrent state (GRU hidden state master copy h32, update gate z32): tiled layout of tc_epilogue.cuh
+# ----------------------------------------------------------------------------------------------
+def state_alloc(b, h8, w8, device):
+    """Uninitialised fp32 state buffer for a [b, h8, w8, 128] map in the epilogues' tiled layout:
+    [b, ceil(h8/16), ceil(w8/8), 4 (32-pixel quarter), 32 (channel group), 32 (pixel), 4 (channel)]."""
+    return torch.empty(b, (h8 + 15) // 16, (w8 + 7) // 8, 4, 32, 32, 4, dtype=torch.float32, device=device)
+
+
+def state_from_nhwc(x):
+    """[B, H, W, 128] fp32 -> tiled state buffer (pad pixels zero)."""
+    b, h, w, c = x.shape
+    assert c == 128
+    th, tw = (h + 15) // 16, (w + 7) // 8
+    xp = torch.zeros(b, th * 16, tw * 8, 128, dtype=torch.float32, device=x.device)
+    xp[:, :h, :w] = x.float()
+    # (b, th, q, rh_lo, tw, rw, c4, ci) -> (b, th, tw, q, c4, rh_lo, rw, ci)
+    t = xp.view(b, th, 4, 4, tw, 8, 32, 4).permute(0, 1, 4, 2, 6, 3, 5, 7).contiguous()
+    return t.view(b, th, tw, 4, 32, 32, 4)
+
+
+def state_to_nhwc(t, h, w):
+    """Tiled state buffer -> [B, h, w, 128] fp32."""
+    b, th, tw = t.shape[:3]
+    x = t.view(b, th, tw, 4, 32, 4, 8, 4).permute(0, 1, 3, 5, 2, 6, 4, 7).reshape(b, th * 16, tw * 8, 128)
+    return x[:, :h, :w].contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
 # correlation pyramid
 # ----------------------------------------------------------------------------------------------
 def pyramid_shapes(h8, w8):
@@ -163,9 +191,16 @@ def pyramid_shapes(h8, w8):
     return out
 
 
-def alloc_pyramid(batch, h8, w8, device):
+def alloc_pyramid(batch, h8, w8, device, half_levels=0):
+    """The four pyramid levels; ``half_levels=4`` stores them as fp16 (the sequence pipeline's layout), 0 keeps the
+    reference's fp32 pyramid (``CorrBlock`` drop-in)."""
     n = h8 * w8
-    return [torch.empty(batch * n, h, p, dtype=torch.float32, device=device) for (h, w, p) in pyramid_shapes(h8, w8)]
+    return [torch.empty(batch * n, h, p, dtype=torch.float16 if l < half_levels else torch.float32, device=device)
+            for l, (h, w, p) in enumerate(pyramid_shapes(h8, w8))]
+
+
+def _half_levels(levels):
+    return sum(1 for t in levels if t.dtype == torch.float16)
 
 
 def corr_pyramid_build(fmap1, fmap2, levels, legacy=False, pair=False):
@@ -178,11 +213,11 @@ def corr_pyramid_build(fmap1, fmap2, levels, legacy=False, pair=False):
         lp = (C.c_int32 * 4)(*[t.shape[2] for t in levels])
 
         def go():
-            L.check(L.load().atdn_corr_pyramid(fmap1.ptr(), fmap2.ptr(), C.c_int64(fmap1.pitch), fmap1.c, lv, lp, b, h8, w8,
+            L.check(L.load().atdn_corr_pyramid(fmap1.ptr(), fmap2.ptr(), C.c_int64(fmap1.pitch), fmap1.c, lv, lp, _half_levels(levels), b, h8, w8,
                                                C.c_float(1.0 / math.sqrt(fmap1.c)), L.stream_ptr()), "atdn_corr_pyramid")
         if L.PROFILER is not None:
-            # algorithmic: 2*N*N*C flop; bytes = the four fp32 levels written + both feature maps read once
-            nbytes = sum(4.0 * b * n * (h8 >> l) * (w8 >> l) for l in range(4)) + 2.0 * b * n * fmap1.c * 2
+            # algorithmic: 2*N*N*C flop; bytes = the four levels written + both feature maps read once
+            nbytes = sum(float(levels[l].element_size()) * b * n * (h8 >> l) * (w8 >> l) for l in range(4)) + 2.0 * b * n * fmap1.c * 2
             with L.PROFILER("corr_pyramid", 2.0 * b * n * n * fmap1.c, nbytes):
                 go()
             return
@@ -213,18 +248,20 @@ def corr_lookup(levels, coords, out16=None, out32=None):
     b, h8, w8, _ = coords.shape
     lv = (C.c_void_p * 4)(*[t.data_ptr() for t in levels])
     lp = (C.c_int32 * 4)(*[t.shape[2] for t in levels])
+    hl = _half_levels(levels)
+
+    def go():
+        L.check(L.load().atdn_corr_lookup(lv, lp, hl, L.ptr(coords), out16.ptr() if out16 is not None else None,
+                                          C.c_int64(out16.pitch if out16 is not None else 0), L.ptr(out32),
+                                          b, h8, w8, L.stream_ptr()), "atdn_corr_lookup")
     if L.PROFILER is not None:
-        # algorithmic bytes: <= 4 levels x 10x10 texels x 4 B read + coords + 324 outputs written per query
+        # algorithmic bytes: <= 4 levels x 10x10 texels read + coords + 324 outputs written per query
         q = b * h8 * w8
-        nbytes = q * (4 * 100 * 4 + 8 + 324 * (2 if out16 is not None else 4))
+        nbytes = q * (100 * sum(t.element_size() for t in levels) + 8 + 324 * (2 if out16 is not None else 4))
         with L.PROFILER("corr_lookup", 0.0, float(nbytes)):
-            L.check(L.load().atdn_corr_lookup(lv, lp, L.ptr(coords), out16.ptr() if out16 is not None else None,
-                                              C.c_int64(out16.pitch if out16 is not None else 0), L.ptr(out32),
-                                              b, h8, w8, L.stream_ptr()), "atdn_corr_lookup")
+            go()
         return
-    L.check(L.load().atdn_corr_lookup(lv, lp, L.ptr(coords), out16.ptr() if out16 is not None else None,
-                                      C.c_int64(out16.pitch if out16 is not None else 0), L.ptr(out32),
-                                      b, h8, w8, L.stream_ptr()), "atdn_corr_lookup")
+    go()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -325,7 +362,7 @@ def coords_init(coords1, flow, flow_init=None):
 # ----------------------------------------------------------------------------------------------
 @_profiled
 def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shift=None, skip=None, bn_scale=None,
-           bn_shift=None, bn2_scale=None, bn2_shift=None):
+           bn_shift=None, bn2_scale=None, bn2_shift=None, w_host=None):
     d = L.Conv32Desc()
     b, cin, h, wd = x.shape
     cout, _, k, _ = w.shape
@@ -334,6 +371,9 @@ def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shif
     d.bn_scale, d.bn_shift = L.ptr(bn_scale), L.ptr(bn_shift)
     d.bn2_scale, d.bn2_shift = L.ptr(bn2_scale), L.ptr(bn2_shift)
     d.batch, d.cin, d.cout, d.in_h, d.in_w, d.k, d.stride, d.pad, d.mish = b, cin, cout, h, wd, k, stride, pad, int(mish)
+    if w_host is not None:   # host copy of w: lets the 16-channel layers read their filter from the constant bank
+        assert w_host.device.type == "cpu" and w_host.dtype == torch.float32 and w_host.is_contiguous() and w_host.shape == w.shape
+        d.w_host = w_host.data_ptr()
     L.check(L.load().atdn_conv32(C.byref(d), L.stream_ptr()), "atdn_conv32")
 
 

@@ -104,8 +104,11 @@ typedef struct atdn_tc_desc {
   int64_t out_ch_off;
   const void* resid16;    /* STORE16|RESID, PV: fp16 [pix, resid_pitch] at resid_ch_off             */
   int64_t resid_pitch, resid_ch_off;
-  float* h32;             /* GRU_*: fp32 hidden state [pix,128]; STORE16|TANH_LO: written           */
-  float* z32;             /* GRU_ZR writes / GRU_Q reads: fp32 [pix,128]                            */
+  /* fp32 recurrent state, 128 channels per pixel, in the TILED layout the epilogue warps access coalesced:
+   *   float index = ((((b*ceil(H/16) + h/16)*ceil(W/8) + w/8)*4 + r/32)*32 + c/4)*128 + (r%32)*4 + c%4,
+   *   r = (h%16)*8 + w%8  (H, W = out_h, out_w); size batch*ceil(H/16)*16*ceil(W/8)*8*128 floats.              */
+  float* h32;             /* GRU_*: hidden state master copy; STORE16|TANH_LO: written (FLOW: coords1)   */
+  float* z32;             /* GRU_ZR writes / GRU_Q reads the update gate            (FLOW: flow)         */
   void* rh16;             /* GRU_ZR: fp16 [pix,128] = r*h                                           */
   const float* aux32;     /* FLOWTAIL: fp32 flow [pix,2]; PV: row_scale [pix]                       */
   const float* gamma;     /* PV: pointer to the scalar Aggregate.gamma                              */
@@ -133,10 +136,15 @@ int atdn_tc_gemm(const atdn_tc_desc* desc, void* stream);
  * One persistent-style kernel: tcgen05 MMAs into two TMEM accumulators, fp32 boxes staged in shared memory
  * and written with TMA stores (full 128-byte runs per query row); columns [W_l, ceil4(W_l)) of a row may be
  * overwritten with pad values (16-byte store granularity).
+ * half_levels = 0: all four levels fp32 (the reference's corr_pyramid, bit-for-bit layout of its values).
+ * half_levels = 4: all levels are stored as fp16 (pitch a multiple of 8), each pooled from the un-rounded fp32
+ *   values of the level below and rounded once.  The kernel is bound by its HBM stores, so this halves its time
+ *   (and the lookup's read traffic); the end-to-end flow moves by 8e-4 px mean
+ *   (tools/fp16_pyramid_sensitivity.py), inside the 1e-2 px bar.
  * ---------------------------------------------------------------------------------------------- */
 int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t fmap_pitch, int32_t channels,
-                      float* const lvl[4], const int32_t lvl_pitch[4], int32_t batch, int32_t h8, int32_t w8,
-                      float alpha, void* stream);
+                      void* const lvl[4], const int32_t lvl_pitch[4], int32_t half_levels, int32_t batch,
+                      int32_t h8, int32_t w8, float alpha, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused attention probabilities -- GMA.whl!/GMA/core/gma.py:66-73 (q k^T * scale, softmax over keys);
@@ -152,10 +160,12 @@ int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, int64_t p_pit
 
 /* ------------------------------------------------------------------------------------------------
  * Correlation lookup -- GMA.whl!/GMA/core/corr.py:32-53 + utils/utils.py:59-73 (grid_sample).
- * coords: fp32 [B, H8, W8, 2] (x, y); levels as written by ATDN_EPI_CORR;
+ * coords: fp32 [B, H8, W8, 2] (x, y); levels and half_levels (0 or 4) as written by atdn_corr_pyramid;
+ * the fp16 path blends the 10x10 window separably with one fractional offset per level (grid_sample's per-tap
+ * coordinate round trip, an ulp-level perturbation, is dropped);
  * out: fp16 [B*H8*W8, out_pitch], channel = level*81 + a*9 + b  (a offsets x, b offsets y).
  * ---------------------------------------------------------------------------------------------- */
-int atdn_corr_lookup(const float* const lvl[4], const int32_t lvl_pitch[4], const float* coords,
+int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitch[4], int32_t half_levels, const float* coords,
                      void* out16, int64_t out_pitch, float* out32_or_null,
                      int32_t batch, int32_t h8, int32_t w8, void* stream);
 
@@ -217,6 +227,9 @@ typedef struct atdn_conv32_desc {
   const float* skip;      /* [B, cout, oh, ow] or NULL: enables post2                               */
   const float* bn2_scale; const float* bn2_shift;  /* [cout] batch norm of post2, or NULL           */
   int32_t batch, cin, cout, in_h, in_w, k, stride, pad, mish;
+  const float* w_host;    /* optional HOST copy of w: the 16-channel CLVO layers (7x7/2 stem, 3x3/1, 3x3/2 on
+                             maps >= 32 wide) then read their filter from the constant bank (kernel parameter)
+                             instead of shared memory; NULL = always stage weights from device memory          */
 } atdn_conv32_desc;
 int atdn_conv32(const atdn_conv32_desc* desc, void* stream);
 

@@ -102,12 +102,13 @@ def check_gru(mt=2, kind="zr", h=37, w=45, batch=2, taps=(1, 5), pair=False, bn=
         ref = F.conv2d(hx.permute(0, 3, 1, 2).float(), wt.float(), bias, padding=pad).permute(0, 2, 3, 1).reshape(-1, 256)
         z_ref = torch.sigmoid(ref[:, :128])
         rh_ref = torch.sigmoid(ref[:, 128:]) * h32
-        z32 = torch.full((batch * h * w, 128), float("nan"), device="cuda")
+        z32 = ops.state_alloc(batch, h, w, "cuda").fill_(float("nan"))     # tiled fp32 state layout (tc_epilogue.cuh)
         rh = torch.full((batch, h, w, 128), float("nan"), dtype=torch.half, device="cuda")
         ops.conv_tc(ops.View(hx.cuda()), ops.pack_conv_weight(wt.float().cuda()), ops.pad_bias(bias.cuda()), None, cout=256,
-                    taps=taps, pad=pad, bn=bn, epi=L.EPI_GRU_ZR, h32=h32.cuda(), z32=z32, rh16=rh, mt=mt, flags=L.F_PAIR if pair else 0)
+                    taps=taps, pad=pad, bn=bn, epi=L.EPI_GRU_ZR, h32=ops.state_from_nhwc(h32.view(batch, h, w, 128).cuda()), z32=z32,
+                    rh16=rh, mt=mt, flags=L.F_PAIR if pair else 0)
         torch.cuda.synchronize()
-        ok &= _cmp(f"gru_zr z mt={mt} taps={taps} pair={pair} bn={bn}", z32, z_ref, 2e-3)
+        ok &= _cmp(f"gru_zr z mt={mt} taps={taps} pair={pair} bn={bn}", ops.state_to_nhwc(z32, h, w).reshape(-1, 128), z_ref, 2e-3)
         ok &= _cmp(f"gru_zr r*h mt={mt} taps={taps} pair={pair} bn={bn}", rh.reshape(-1, 128), rh_ref, 2e-3)
     else:
         wt = (torch.randn(128, 512, *taps, generator=g) / (512 * 5) ** 0.5).half()
@@ -117,14 +118,14 @@ def check_gru(mt=2, kind="zr", h=37, w=45, batch=2, taps=(1, 5), pair=False, bn=
         xin = torch.cat([rhx, hx[..., 128:]], -1)
         ref = F.conv2d(xin.permute(0, 3, 1, 2).float(), wt.float(), bias, padding=pad).permute(0, 2, 3, 1).reshape(-1, 128)
         h_ref = (1 - z) * h32 + z * torch.tanh(ref)
-        h32d = h32.cuda()
+        h32d = ops.state_from_nhwc(h32.view(batch, h, w, 128).cuda())
         hxd = hx.cuda()
         out = torch.full((batch, h, w, 128), float("nan"), dtype=torch.half, device="cuda")
         ops.conv_tc(ops.View(rhx.cuda()), ops.pack_conv_weight(wt.float().cuda()), ops.pad_bias(bias.cuda()), ops.View(out), cout=128,
-                    taps=taps, pad=pad, bn=128 if mt <= 2 else 64, epi=L.EPI_GRU_Q, a2=ops.View(hxd, 128, 384), h32=h32d, z32=z.cuda(), mt=mt,
-                    flags=L.F_PAIR if pair else 0)
+                    taps=taps, pad=pad, bn=128 if mt <= 2 else 64, epi=L.EPI_GRU_Q, a2=ops.View(hxd, 128, 384), h32=h32d,
+                    z32=ops.state_from_nhwc(z.view(batch, h, w, 128).cuda()), mt=mt, flags=L.F_PAIR if pair else 0)
         torch.cuda.synchronize()
-        ok &= _cmp(f"gru_q h32 mt={mt} taps={taps} pair={pair}", h32d, h_ref, 2e-3)
+        ok &= _cmp(f"gru_q h32 mt={mt} taps={taps} pair={pair}", ops.state_to_nhwc(h32d, h, w).reshape(-1, 128), h_ref, 2e-3)
         ok &= _cmp(f"gru_q h16 mt={mt} taps={taps} pair={pair}", out.reshape(-1, 128), h_ref, 2e-3)
     return ok
 
@@ -140,8 +141,8 @@ def bench_conv(name, cin, cout, taps, bn, mt, batch=6, h=47, w=154, reps=20, epi
     wp = ops.pack_conv_weight((torch.randn(cout, cin, *taps, generator=g) / 50).cuda())
     bias = ops.pad_bias(torch.zeros(cout).cuda())
     out = torch.empty(batch, h, w, cout, dtype=torch.half, device="cuda")
-    h32 = torch.randn(batch * h * w, 128, generator=g).cuda()
-    z32 = torch.rand(batch * h * w, 128, generator=g).cuda()
+    h32 = ops.state_from_nhwc(torch.randn(batch, h, w, 128, generator=g).cuda())
+    z32 = ops.state_from_nhwc(torch.rand(batch, h, w, 128, generator=g).cuda())
     rh = torch.empty(batch, h, w, 128, dtype=torch.half, device="cuda")
     st = torch.zeros(64, dtype=torch.int64, device="cuda") if stamps else None
     fp = L.F_PAIR if pair else 0
@@ -291,8 +292,8 @@ def bench_gru(pair, bn, kind="zr", batch=6, h=47, w=154, reps=20):
     hx = torch.randn(batch, h, w, 512, generator=g).half().cuda()
     wp = ops.pack_conv_weight((torch.randn(cout, 512, 1, 5, generator=g) / 50).cuda())
     bias = ops.pad_bias(torch.zeros(cout).cuda())
-    h32 = torch.randn(batch * h * w, 128, generator=g).cuda()
-    z32 = torch.rand(batch * h * w, 128, generator=g).cuda()
+    h32 = ops.state_from_nhwc(torch.randn(batch, h, w, 128, generator=g).cuda())
+    z32 = ops.state_from_nhwc(torch.rand(batch, h, w, 128, generator=g).cuda())
     rh = torch.empty(batch, h, w, 128, dtype=torch.half, device="cuda")
     out = torch.empty(batch, h, w, 128, dtype=torch.half, device="cuda")
     fl = L.F_PAIR if pair else 0

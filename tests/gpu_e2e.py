@@ -76,7 +76,7 @@ def check_gma_stages():
     """Stage-by-stage comparison against the oracle's intermediates (localises a failing kernel)."""
     import numpy as np
     import torch
-    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200 import ops, synth
     from oracle import gma_oracle
     g = np.load(os.path.join(GOLD, "gma_small.npz"))
     m, sd = _gma()
@@ -89,7 +89,7 @@ def check_gma_stages():
         torch.cuda.synchronize()
         plan = next(iter(m._plans.values()))
         ok &= _stat(f"iters={iters} lookup corr (last iter)", plan.corrfeat[..., :324].float().permute(0, 3, 1, 2), it["corr"][-1], 5e-3)
-        ok &= _stat(f"iters={iters} net", plan.h32.view(1, 16, 20, 128).permute(0, 3, 1, 2), it["net"], 3e-2)
+        ok &= _stat(f"iters={iters} net", ops.state_to_nhwc(plan.h32, 16, 20).permute(0, 3, 1, 2), it["net"], 3e-2)
         ok &= _stat(f"iters={iters} mask", plan.mask32.view(1, 16, 20, 576).permute(0, 3, 1, 2), it["mask"], 5e-3)
         ok &= _epe(f"iters={iters} flow_lo", lo, lo_o, 1e-3)
         ok &= _epe(f"iters={iters} flow_up", up, up_o, 5e-3)

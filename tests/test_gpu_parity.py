@@ -4,7 +4,7 @@ C ABI and compares with the oracle / the golden fixtures of the reference.
 Tolerances (written here, from BASELINE.json north_star):
   * tensor-core GEMMs with fp32 output: 2e-5 relative (fp16 products are exact, fp32 accumulation)
   * fp16-stored conv outputs: 2e-3 relative (one fp16 rounding of the output)
-  * corr pyramid / lookup (fp32 islands): 1e-5 relative
+  * corr pyramid / lookup (fp32 islands): 1e-5 relative; fp16 pyramid: one fp16 rounding, lookup on it 2e-5
   * final flow (flow_up): mean end-point error <= 1e-2 px against the reference fp32 path
   * CLVO features / poses / VAE embedding (fp32 kernels): 1e-4 relative
   * keyframe arg-min: bit-exact index
@@ -73,6 +73,42 @@ def test_corrblock_dropin_api():
     ref = gma_oracle.corr_lookup(pyr, coords)
     assert out.shape == ref.shape == (1, 324, 47, 154)
     assert (out.cpu() - ref).abs().max() <= 1e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("h8,w8,batch", [(47, 154, 1), (23, 39, 2), (16, 20, 3)])
+def test_half_level_pyramid_and_lookup(h8, w8, batch):
+    """half_levels=4 (the sequence pipeline's layout): every level is the fp32 pyramid (pooled from un-rounded
+    values) rounded ONCE to fp16; the separable lookup on it equals the oracle lookup on the same rounded pyramid
+    to fp32 round-off, including integer coordinates (iteration 0) and windows hanging over every border."""
+    from atdn_vslam_b200 import ops
+    from oracle import gma_oracle
+    g = torch.Generator().manual_seed(h8 * 1000 + w8)
+    f1 = torch.randn(batch, 256, h8, w8, generator=g).half()
+    f2 = torch.randn(batch, 256, h8, w8, generator=g).half()
+    pyr = gma_oracle.corr_pyramid(f1.float(), f2.float())
+    lv = ops.alloc_pyramid(batch, h8, w8, "cuda", half_levels=4)
+    for t in lv:
+        t.fill_(float("nan"))
+    ops.corr_pyramid_build(ops.View(f1.permute(0, 2, 3, 1).contiguous().cuda()), ops.View(f2.permute(0, 2, 3, 1).contiguous().cuda()), lv)
+    assert all(t.dtype == torch.float16 for t in lv)
+    rounded = []
+    for t, r in zip(lv, pyr):
+        got = t[:, :, : r.shape[-1]].float().cpu().reshape(r.shape)
+        assert not torch.isnan(got).any()
+        # one fp16 rounding of a value that matches the fp32 oracle to 1e-5: at most 1 fp16 ulp apart (rounding ties)
+        want = r.half().float()
+        assert (got - want).abs().max() <= 2.0 ** -10 * r.abs().max()
+        assert ((got - want).abs() > 1e-5 * r.abs().max()).float().mean() < 1e-2
+        rounded.append(got)
+    base = gma_oracle.coords_grid(batch, h8, w8)
+    for coords in (base + 6.0 * torch.randn(batch, 2, h8, w8, generator=g),       # sub-pixel, windows over the borders
+                   base.clone(),                                                  # integer coordinates (iteration 0)
+                   base + 40.0 * torch.randn(batch, 2, h8, w8, generator=g)):     # mostly outside the map
+        out32 = torch.empty(batch * h8 * w8, 324, dtype=torch.float32, device="cuda")
+        ops.corr_lookup(lv, coords.permute(0, 2, 3, 1).contiguous().cuda(), out32=out32)
+        ref = gma_oracle.corr_lookup(rounded, coords)
+        got = out32.view(batch, h8, w8, 324).permute(0, 3, 1, 2).cpu()
+        assert (got - ref).abs().max() <= 2e-5 * ref.abs().max()
 
 
 def test_padded_direct_call_376x1248():

@@ -47,7 +47,7 @@ class Conv32Desc(C.Structure):
         ("bn2_scale", C.c_void_p), ("bn2_shift", C.c_void_p),
         ("batch", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
         ("k", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("mish", C.c_int32),
-        ("w_host", C.c_void_p),
+        ("x_pitch", C.c_int32), ("y_pitch", C.c_int32),
     ]
 
 
@@ -102,7 +102,10 @@ def require_cuda(*tensors):
 
 
 def tc_label(d: TcDesc):
-    """(label, flops) of one tensor-core launch, derived from its descriptor (profiling only)."""
+    """(label, flops, bytes) of one tensor-core launch, derived from its descriptor (profiling only).  Bytes are
+    only given where HBM is the binding roofline: the P.V aggregation re-reads the fp16 probabilities every
+    iteration (N x Np x 2 B per pair)."""
+    nbytes = 0.0
     if d.a_mode == MODE_PATCH:
         cin = d.a_dims[0] + (d.a2_dims[0] if d.a_split_chunk else 0)
         flops = 2.0 * d.out_h * d.out_w * d.a_dims[3] * d.n_valid * d.taps_h * d.taps_w * cin   # algorithmic (n_valid, not the padded tile)
@@ -110,15 +113,17 @@ def tc_label(d: TcDesc):
     else:
         batch = d.b_dims[3] if (d.flags & F_A_SHARED) else d.a_dims[3]
         flops = 2.0 * d.a_dims[1] * d.n_valid * d.a_dims[0] * batch
+        if d.epi == EPI_PV:   # P [rows, pitch] + V^T [128, pitch] read, residual read + output written (fp16)
+            nbytes = batch * 2.0 * (d.a_dims[1] * d.a_strides[0] + d.n_valid * d.b_strides[0] + 2 * d.a_dims[1] * d.n_valid)
         name = {EPI_CORR: "corr_gemm", EPI_PV: "attn_pv", EPI_STORE32: "attn_qk"}.get(
             d.epi, "to_v" if (d.flags & F_A_SHARED) else f"rows_k{d.a_dims[0]}to{d.n_valid}")
-    return name, flops
+    return name, flops, nbytes
 
 
 def tc_gemm(desc: TcDesc):
     if PROFILER is not None:
-        name, flops = tc_label(desc)
-        with PROFILER(name, flops, 0.0):
+        name, flops, nbytes = tc_label(desc)
+        with PROFILER(name, flops, nbytes):
             check(load().atdn_tc_gemm(C.byref(desc), stream_ptr()), "atdn_tc_gemm")
         return
     check(load().atdn_tc_gemm(C.byref(desc), stream_ptr()), "atdn_tc_gemm")

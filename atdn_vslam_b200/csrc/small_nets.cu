@@ -2,8 +2,11 @@
 // MappingVAE keyframe encoder, and the keyframe L2 search.  These layers have 2..128 channels on
 // small maps: memory/latency-bound, not tensor-core work.
 #include <math.h>
+#include <string.h>
 
 #include "common.h"
+#include "tc_host.cuh"
+#include "tc_ptx.cuh"
 
 namespace atdn {
 
@@ -26,6 +29,7 @@ struct Conv32Params {
   const float *x, *w, *bias, *in_scale, *in_shift, *skip, *bn_scale, *bn_shift, *bn2_scale, *bn2_shift;
   float* y;
   int B, Cin, Cout, H, W, OH, OW, K, stride, pad, mish, tiles_x, in_tile;
+  int xp, yp;             // row pitch (elements) of x and of y / skip: W / OW when dense
 };
 
 __global__ void __launch_bounds__(256) conv32_kernel(Conv32Params p) {
@@ -51,7 +55,7 @@ __global__ void __launch_bounds__(256) conv32_kernel(Conv32Params p) {
       float v = 0.0f;
       const int ci = ci0 + c;
       if (ci < p.Cin && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-        v = __ldg(p.x + ((static_cast<long long>(b) * p.Cin + ci) * p.H + yy) * p.W + xx);
+        v = __ldg(p.x + ((static_cast<long long>(b) * p.Cin + ci) * p.H + yy) * p.xp + xx);
         if (p.in_scale) v = v * __ldg(p.in_scale + ci) + __ldg(p.in_shift + ci);
       }
       s_in[i] = v;
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(256) conv32_kernel(Conv32Params p) {
   for (int i = 0; i < kCoT; ++i) {
     const int co = co0 + i;
     if (co >= p.Cout) break;
-    const long long o = ((static_cast<long long>(b) * p.Cout + co) * p.OH + oy) * p.OW + ox;
+    const long long o = ((static_cast<long long>(b) * p.Cout + co) * p.OH + oy) * p.yp + ox;
     float v = acc[i] + (p.bias ? __ldg(p.bias + co) : 0.0f);
     if (p.mish) v = mishf(v);
     if (p.bn_scale) v = v * __ldg(p.bn_scale + co) + __ldg(p.bn_shift + co);
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kC16Threads) conv16_kernel(Conv32Params p) {
           const int yy = iy0 + ry, xx = ix0 + rx, ci = ci0 + c;
           dst[u] = (c * G::IH + ry) * G::PITCH + (S == 1 ? rx : (rx & 1) * G::HALF + (rx >> 1));
           if (ci < p.Cin && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-            v[u] = __ldg(p.x + ((static_cast<long long>(b) * p.Cin + ci) * p.H + yy) * p.W + xx);
+            v[u] = __ldg(p.x + ((static_cast<long long>(b) * p.Cin + ci) * p.H + yy) * p.xp + xx);
             if (p.in_scale) v[u] = v[u] * __ldg(p.in_scale + ci) + __ldg(p.in_shift + ci);
           }
         }
@@ -223,10 +227,10 @@ __global__ void __launch_bounds__(kC16Threads) conv16_kernel(Conv32Params p) {
     }
   }
   if (oy >= p.OH) return;
-  const bool vec = (p.OW & 3) == 0 && ox0 + 4 <= p.OW;
+  const bool vec = (p.yp & 3) == 0 && ox0 + 4 <= p.yp;
 #pragma unroll
   for (int co = 0; co < 16; ++co) {
-    const long long o = ((static_cast<long long>(b) * 16 + co) * p.OH + oy) * p.OW + ox0;
+    const long long o = ((static_cast<long long>(b) * 16 + co) * p.OH + oy) * p.yp + ox0;
     const float bias = p.bias ? __ldg(p.bias + co) : 0.0f;
     const float s1 = p.bn_scale ? __ldg(p.bn_scale + co) : 1.0f, h1 = p.bn_scale ? __ldg(p.bn_shift + co) : 0.0f;
     const float s2 = p.bn2_scale ? __ldg(p.bn2_scale + co) : 1.0f, h2 = p.bn2_scale ? __ldg(p.bn2_shift + co) : 0.0f;
@@ -279,180 +283,252 @@ static int launch_conv16(Conv32Params p, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Same tiling with the WEIGHTS IN THE CONSTANT BANK: the whole filter ([ci][ky][kx][16 co], <= 9 KiB) travels as a
-// __grid_constant__ kernel parameter, every FFMA takes its weight through the uniform datapath (ULDC -> UR operand)
-// and shared memory only carries the input tile.  conv16_kernel spends one 128-bit shared load per 16 FMAs on the
-// weights, which caps it at half the FP32 rate (shared-memory bandwidth: 4 clk per LDS.128 vs 4 clk for 16 warp-wide
-// FFMAs on the four schedulers); here the only shared loads are the (PX-1)*S+K inputs per filter row.
-//   CTA = 128 threads = (64/PX) x (2*PX) threads, tile = 64 x (2*PX) output pixels, thread = PX consecutive pixels x 16
-//   channels.  Needs a HOST copy of the weights at launch (atdn_conv32_desc.w_host).
+// TMA-fed variant with the weights in the constant bank (the per-pair hot layers of the CLVO encoder).
+//
+// ncu on conv16_kernel (B200, 27 pairs, 3x3/1 at 188x616): 20K instructions per thread for 9.2K FFMAs, issue slots
+// 52% busy, 42% of the stall samples on the first use of the staged global loads (long scoreboard) -- the per-element
+// global->shared staging (index arithmetic, bounds checks, exposed L2 latency) costs more than the weights.  Here
+//   * the input tile arrives by TMA: one cp.async.bulk.tensor box {68 columns, IH rows, CIT channels} of the NCHW
+//     fp32 input per stage (zero fill outside the image = the conv zero padding, negative coordinates included),
+//     double-buffered over channel chunks behind an mbarrier pair.  No thread executes a staging instruction;
+//     every thread reads its (3 S + K)-value row segment with aligned 128-bit shared loads.  Needs a row pitch
+//     that is a multiple of 4 floats (16-byte TMA strides): the encoder pads its intermediate maps
+//     (154 -> 156, 77 -> 80, 39 -> 40 columns);
+//   * the whole filter ([ci][ky][kx][16 co], <= 9 KiB) is staged once per CTA while the first tile is in flight
+//     and read as warp-wide broadcasts (4 x LDS.128 per 64 FFMAs);
+//   * AFFINE (the stem): x * in_scale[c] + in_shift[c] is applied to the in-bounds elements of the landed tile.
+// CTA = 128 threads = 16 x 8, tile = 64 x 8 output pixels, thread = 4 consecutive pixels x 16 channels.
 // ------------------------------------------------------------------------------------------------
-template <int K, int CIN>
-struct alignas(16) C16Weights {
-  float w[CIN * K * K * 16];
+template <int K, int S, int PAD>
+struct C16tGeom {
+  static constexpr int IH = (kC16TH - 1) * S + K;
+  // TMA boxes of an fp32 NCHW map must START on a 16-byte boundary (x coordinate a multiple of 4: verified with
+  // tools/tma_f32_test.cu, a box at x = -1 faults), so the box begins OFF columns left of the first tap
+  static constexpr int OFF = (4 - PAD % 4) % 4;
+  static constexpr int NV = 3 * S + K;                        // input values per thread and filter row
+  static constexpr int NL = (OFF + NV + 3) / 4;               // 128-bit shared loads per thread and filter row
+  static constexpr int ROW = (OFF + 63 * S + K + 3) / 4 * 4;  // floats per staged row
+  static_assert(15 * 4 * S + 4 * NL <= ROW, "a thread's row segment must stay inside the staged row");
+  static_assert(ROW <= 256, "TMA box limit");
 };
 
-template <int K, int S, int PX>
-struct C16cGeom {
-  static constexpr int TXN = 64 / PX, TH = kC16Threads / TXN;
-  static constexpr int IH = (TH - 1) * S + K;
-  static constexpr int IW = 63 * S + K;
-  static constexpr int NV = (PX - 1) * S + K;                // input values per thread and filter row
-  static constexpr int HALF = ((IW + 1) / 2 + 3) / 4 * 4 + 4;
-  static constexpr int PITCH = S == 1 ? (IW + 3) / 4 * 4 + 4 : 2 * HALF;
-};
-
-template <int K, int S, int CIN, int CIT, int PX>
-__global__ void __launch_bounds__(kC16Threads) conv16c_kernel(const __grid_constant__ Conv32Params p,
-                                                              const __grid_constant__ C16Weights<K, CIN> wt) {
-  using G = C16cGeom<K, S, PX>;
+template <int K, int S, int PAD, int CIN, int CIT, bool AFFINE>
+__global__ void __launch_bounds__(kC16Threads) conv16t_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                              const __grid_constant__ Conv32Params p) {
+  using G = C16tGeom<K, S, PAD>;
   static_assert(CIN % CIT == 0, "input channels are staged in whole chunks");
-  extern __shared__ float sm[];
-  float* s_in = sm;                                 // [CIT][IH][PITCH]
-  const int tx = threadIdx.x % G::TXN, ty = threadIdx.x / G::TXN;
+  constexpr int NCH = CIN / CIT;
+  constexpr int BOX_FLOATS = CIT * G::IH * G::ROW;            // one TMA box: [CIT][IH][ROW]
+  constexpr int STAGE_FLOATS = (BOX_FLOATS + 31) / 32 * 32;   // TMA destinations are 128-byte aligned
+  constexpr int NSTAGE = NCH > 1 ? 2 : 1;
+  extern __shared__ uint8_t smem_raw16[];
+  __shared__ __align__(8) uint64_t full[2];
+  float* s_in = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw16) + 127) & ~uintptr_t(127));
+  float* s_w = s_in + NSTAGE * STAGE_FLOATS;        // [CIN][K*K][16]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int tile_x = blockIdx.x % p.tiles_x, tile_y = blockIdx.x / p.tiles_x;
   const int b = blockIdx.z;
-  const int ox0 = tile_x * 64 + tx * PX, oy = tile_y * G::TH + ty;
-  const int ix0 = tile_x * 64 * S - p.pad, iy0 = tile_y * G::TH * S - p.pad;
-  float acc[PX][16];
+  const int ox0 = tile_x * kC16TW + tx * 4, oy = tile_y * kC16TH + ty;
+  const int bx0 = tile_x * kC16TW * S - PAD - G::OFF, iy0 = tile_y * kC16TH * S - PAD;   // bx0 is a multiple of 4
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int chunk) {
+    uint64_t* bar = &full[chunk % NSTAGE];
+    mbar_arrive_expect_tx(bar, BOX_FLOATS * 4);
+    tma_load_4d(s_in + (chunk % NSTAGE) * STAGE_FLOATS, &tmx, bar, bx0, iy0, chunk * CIT, b);
+  };
+  // TMA issue follows the pattern of the tensor-core kernels: a warp-uniform branch, one elected lane
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      tma_prefetch_desc(&tmx);
+      issue(0);
+    }
+    __syncwarp();
+  }
+  for (int i = threadIdx.x; i < CIN * K * K * 16; i += kC16Threads) {   // [co][ci][tap] (PyTorch) -> [ci][tap][co]
+    const int co = i & 15, t = (i >> 4) % (K * K), ci = i / (16 * K * K);
+    s_w[i] = __ldg(p.w + (co * CIN + ci) * (K * K) + t);
+  }
+  __syncthreads();
+
+  float acc[4][16];
 #pragma unroll
-  for (int i = 0; i < PX; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[i][c] = 0.0f;
 
 #pragma unroll 1
-  for (int ci0 = 0; ci0 < CIN; ci0 += CIT) {
-    if (ci0) __syncthreads();
-    constexpr int kN = CIT * G::IH * G::IW;
-    for (int i0 = threadIdx.x; i0 < kN; i0 += kC16Threads * 8) {
-      float v[8];
-      int dst[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * kC16Threads;
-        v[u] = 0.0f;
-        dst[u] = -1;
-        if (i < kN) {
-          const int c = i / (G::IH * G::IW), r = i - c * (G::IH * G::IW);
-          const int ry = r / G::IW, rx = r - ry * G::IW;
-          const int yy = iy0 + ry, xx = ix0 + rx, ci = ci0 + c;
-          dst[u] = (c * G::IH + ry) * G::PITCH + (S == 1 ? rx : (rx & 1) * G::HALF + (rx >> 1));
-          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-            v[u] = __ldg(p.x + ((static_cast<long long>(b) * CIN + ci) * p.H + yy) * p.W + xx);
-            if (p.in_scale) v[u] = v[u] * __ldg(p.in_scale + ci) + __ldg(p.in_shift + ci);
-          }
+  for (int chunk = 0; chunk < NCH; ++chunk) {
+    if (warp == 0 && chunk + 1 < NCH) {            // the other stage was released by the barrier at the end of the loop
+      if (elect_one_sync()) issue(chunk + 1);
+      __syncwarp();
+    }
+    mbar_wait(&full[chunk % NSTAGE], static_cast<uint32_t>((chunk / NSTAGE) & 1));
+    float* st = s_in + (chunk % NSTAGE) * STAGE_FLOATS;
+    if constexpr (AFFINE) {
+      for (int e = threadIdx.x; e < BOX_FLOATS; e += kC16Threads) {
+        const int j = e % G::ROW;
+        const int r = e / G::ROW;
+        const int ry = r % G::IH, c = r / G::IH;
+        const int xx = bx0 + j, yy = iy0 + ry;
+        if (xx >= 0 && xx < p.W && yy >= 0 && yy < p.H) {
+          const int ci = chunk * CIT + c;
+          st[e] = st[e] * __ldg(p.in_scale + ci) + __ldg(p.in_shift + ci);
         }
       }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (dst[u] >= 0) s_in[dst[u]] = v[u];
+      __syncthreads();
     }
-    __syncthreads();
 #pragma unroll 1
     for (int c = 0; c < CIT; ++c) {
-      const float* wc = wt.w + (ci0 + c) * (K * K * 16);     // warp-uniform: constant-bank operands
-#pragma unroll
+      const float4* wc = reinterpret_cast<const float4*>(s_w + (chunk * CIT + c) * (K * K * 16));   // warp-wide broadcasts
+#pragma unroll K == 3 ? 3 : 1
       for (int ky = 0; ky < K; ++ky) {
-        const float* row = s_in + (c * G::IH + ty * S + ky) * G::PITCH;
-        float in[(G::NV + 3) / 4 * 4 + 4];
-        if (S == 1) {
+        const float* row = st + (c * G::IH + ty * S + ky) * G::ROW + tx * 4 * S;
+        float buf[4 * G::NL];
 #pragma unroll
-          for (int q = 0; q < (G::NV + 3) / 4; ++q) {
-            const float4 f = *reinterpret_cast<const float4*>(row + tx * PX + q * 4);
-            in[4 * q] = f.x; in[4 * q + 1] = f.y; in[4 * q + 2] = f.z; in[4 * q + 3] = f.w;
-          }
-        } else {
-          constexpr int NE = (G::NV + 1) / 2, NO = G::NV / 2;      // even / odd values needed
-          float ev[(NE + 3) / 4 * 4], od[(NO + 3) / 4 * 4];
-#pragma unroll
-          for (int q = 0; q < (NE + 3) / 4; ++q) {
-            const float4 f = *reinterpret_cast<const float4*>(row + tx * PX + q * 4);
-            ev[4 * q] = f.x; ev[4 * q + 1] = f.y; ev[4 * q + 2] = f.z; ev[4 * q + 3] = f.w;
-          }
-#pragma unroll
-          for (int q = 0; q < (NO + 3) / 4; ++q) {
-            const float4 f = *reinterpret_cast<const float4*>(row + G::HALF + tx * PX + q * 4);
-            od[4 * q] = f.x; od[4 * q + 1] = f.y; od[4 * q + 2] = f.z; od[4 * q + 3] = f.w;
-          }
-#pragma unroll
-          for (int j = 0; j < G::NV; ++j) in[j] = (j & 1) ? od[j >> 1] : ev[j >> 1];
+        for (int q = 0; q < G::NL; ++q) {
+          const float4 f = *reinterpret_cast<const float4*>(row + q * 4);
+          buf[4 * q] = f.x; buf[4 * q + 1] = f.y; buf[4 * q + 2] = f.z; buf[4 * q + 3] = f.w;
         }
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
+          float w[16];
 #pragma unroll
-          for (int co = 0; co < 16; ++co) {
-            const float w = wc[(ky * K + kx) * 16 + co];
+          for (int q = 0; q < 4; ++q) {
+            const float4 f = wc[(ky * K + kx) * 4 + q];
+            w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+          }
 #pragma unroll
-            for (int i = 0; i < PX; ++i) acc[i][co] = fmaf(in[i * S + kx], w, acc[i][co]);
+          for (int i = 0; i < 4; ++i) {
+            const float v = buf[G::OFF + i * S + kx];
+#pragma unroll
+            for (int co = 0; co < 16; ++co) acc[i][co] = fmaf(v, w[co], acc[i][co]);
           }
         }
       }
     }
+    if (chunk + 1 < NCH) __syncthreads();          // all reads of this stage are done before it is refilled
   }
   if (oy >= p.OH) return;
-  const bool vec = (p.OW & 3) == 0;
+  const bool v4 = (p.yp & 3) == 0 && ox0 + 4 <= p.yp;
 #pragma unroll
   for (int co = 0; co < 16; ++co) {
-    const long long o = ((static_cast<long long>(b) * 16 + co) * p.OH + oy) * p.OW + ox0;
+    const long long o = ((static_cast<long long>(b) * 16 + co) * p.OH + oy) * p.yp + ox0;
     const float bias = p.bias ? __ldg(p.bias + co) : 0.0f;
     const float s1 = p.bn_scale ? __ldg(p.bn_scale + co) : 1.0f, h1 = p.bn_scale ? __ldg(p.bn_shift + co) : 0.0f;
     const float s2 = p.bn2_scale ? __ldg(p.bn2_scale + co) : 1.0f, h2 = p.bn2_scale ? __ldg(p.bn2_shift + co) : 0.0f;
-#pragma unroll
-    for (int g = 0; g < PX / 4; ++g) {
-      const int ox = ox0 + g * 4;
-      const bool v4 = vec && ox + 4 <= p.OW;
-      float v[4], sk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      if (p.skip) {
-        if (v4) {
-          const float4 f = *reinterpret_cast<const float4*>(p.skip + o + g * 4);
-          sk[0] = f.x; sk[1] = f.y; sk[2] = f.z; sk[3] = f.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (ox + i < p.OW) sk[i] = p.skip[o + g * 4 + i];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float t = acc[g * 4 + i][co] + bias;
-        if (p.mish) t = mishf(t);
-        if (p.bn_scale) t = t * s1 + h1;
-        if (p.skip) {
-          t = mishf(t + sk[i]);
-          if (p.bn2_scale) t = t * s2 + h2;
-        }
-        v[i] = t;
-      }
+    float v[4], sk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (p.skip) {
       if (v4) {
-        *reinterpret_cast<float4*>(p.y + o + g * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        const float4 f = *reinterpret_cast<const float4*>(p.skip + o);
+        sk[0] = f.x; sk[1] = f.y; sk[2] = f.z; sk[3] = f.w;
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (ox + i < p.OW) p.y[o + g * 4 + i] = v[i];
+          if (ox0 + i < p.OW) sk[i] = p.skip[o + i];
       }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t = acc[i][co] + bias;
+      if (p.mish) t = mishf(t);
+      if (p.bn_scale) t = t * s1 + h1;
+      if (p.skip) {
+        t = mishf(t + sk[i]);
+        if (p.bn2_scale) t = t * s2 + h2;
+      }
+      v[i] = t;
+    }
+    if (v4) {
+      *reinterpret_cast<float4*>(p.y + o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (ox0 + i < p.OW) p.y[o + i] = v[i];
     }
   }
 }
 
-template <int K, int S, int CIN, int CIT, int PX>
-static int launch_conv16c(Conv32Params p, const float* w_host, cudaStream_t stream) {
-  using G = C16cGeom<K, S, PX>;
-  constexpr int smem = CIT * G::IH * G::PITCH * (int)sizeof(float);
+template <int K, int S, int PAD, int CIN, int CIT, bool AFFINE>
+static int launch_conv16t(Conv32Params p, cudaStream_t stream) {
+  using G = C16tGeom<K, S, PAD>;
+  constexpr int NSTAGE = CIN / CIT > 1 ? 2 : 1;
+  constexpr int STAGE_FLOATS = (CIT * G::IH * G::ROW + 31) / 32 * 32;
+  constexpr int smem = (NSTAGE * STAGE_FLOATS + CIN * K * K * 16) * (int)sizeof(float) + 128;
   static bool configured = false;
   if (!configured) {
     if (smem > 48 * 1024)
-      ATDN_CUDA(cudaFuncSetAttribute(conv16c_kernel<K, S, CIN, CIT, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      ATDN_CUDA(cudaFuncSetAttribute(conv16t_kernel<K, S, PAD, CIN, CIT, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  C16Weights<K, CIN> wt;                             // [co][ci][ky][kx] (PyTorch) -> [ci][ky][kx][co]
-  for (int co = 0; co < 16; ++co)
-    for (int ci = 0; ci < CIN; ++ci)
-      for (int t = 0; t < K * K; ++t) wt.w[(ci * K * K + t) * 16 + co] = w_host[(co * CIN + ci) * K * K + t];
-  p.tiles_x = ceil_div(p.OW, 64);
-  dim3 grid(p.tiles_x * ceil_div(p.OH, G::TH), 1, p.B);
-  conv16c_kernel<K, S, CIN, CIT, PX><<<grid, kC16Threads, smem, stream>>>(p, wt);
+  CUtensorMap tmx;
+  {
+    const int64_t dims[4] = {p.W, p.H, CIN, p.B};
+    const int64_t str[3] = {p.xp, (int64_t)p.H * p.xp, (int64_t)CIN * p.H * p.xp};
+    const uint32_t box[4] = {(uint32_t)G::ROW, (uint32_t)G::IH, (uint32_t)CIT, 1};
+    const uint32_t ones[4] = {1, 1, 1, 1};
+    if (int e = make_map(&tmx, 4, CU_TENSOR_MAP_SWIZZLE_NONE, p.x, dims, str, box, ones, "conv16 input")) return e;
+  }
+  p.tiles_x = ceil_div(p.OW, kC16TW);
+  dim3 grid(p.tiles_x * ceil_div(p.OH, kC16TH), 1, p.B);
+  conv16t_kernel<K, S, PAD, CIN, CIT, AFFINE><<<grid, kC16Threads, smem, stream>>>(tmx, p);
   ATDN_CUDA(cudaGetLastError());
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ResidualConv skip path (layers/conv.py:86): 1x1 stride-2 convolution 16 -> 16 channels, bias only.  The generic
+// kernel above stages a 31 x 31 input tile per 16 x 16 outputs and took 0.3 ms per 27 pairs at 188x616 (as long as
+// the 3x3/2 convolution next to it); this one is a pure streaming kernel: thread = 2 adjacent output pixels,
+// 16 strided input loads each, 256 weights in shared memory, coalesced 8-byte stores per output channel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) skip16_kernel(Conv32Params p) {
+  __shared__ float s_w[16 * 16];                       // [ci][co]
+  __shared__ float s_b[16];
+  s_w[threadIdx.x] = __ldg(p.w + (threadIdx.x & 15) * 16 + (threadIdx.x >> 4));
+  if (threadIdx.x < 16) s_b[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.0f;
+  __syncthreads();
+  const int ow2 = (p.OW + 1) >> 1;                     // pixel pairs per output row
+  const long long total = static_cast<long long>(p.B) * p.OH * ow2;
+  for (long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; t < total; t += static_cast<long long>(gridDim.x) * 256) {
+    const int xp2 = static_cast<int>(t % ow2);
+    const long long r = t / ow2;
+    const int oy = static_cast<int>(r % p.OH), b = static_cast<int>(r / p.OH);
+    const int ox = 2 * xp2;
+    const bool two = ox + 1 < p.OW;
+    const float* xin = p.x + (static_cast<long long>(b) * 16 * p.H + 2 * oy) * p.xp + 2 * ox;
+    float v0[16], v1[16];
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) {
+      const float* px = xin + static_cast<long long>(ci) * p.H * p.xp;
+      v0[ci] = __ldg(px);
+      v1[ci] = two ? __ldg(px + 2) : 0.0f;
+    }
+    float* yo = p.y + (static_cast<long long>(b) * 16 * p.OH + oy) * p.yp + ox;
+#pragma unroll
+    for (int co = 0; co < 16; ++co) {
+      float a0 = s_b[co], a1 = s_b[co];
+#pragma unroll
+      for (int ci = 0; ci < 16; ++ci) {
+        const float w = s_w[ci * 16 + co];
+        a0 = fmaf(v0[ci], w, a0);
+        a1 = fmaf(v1[ci], w, a1);
+      }
+      float* dst = yo + static_cast<long long>(co) * p.OH * p.yp;
+      if (two && (p.yp & 1) == 0) {
+        *reinterpret_cast<float2*>(dst) = make_float2(a0, a1);
+      } else {
+        dst[0] = a0;
+        if (two) dst[1] = a1;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -582,13 +658,24 @@ extern "C" int atdn_conv32(const atdn_conv32_desc* d, void* stream) {
   p.pad = d->pad; p.mish = d->mish;
   p.OH = (d->in_h + 2 * d->pad - d->k) / d->stride + 1;
   p.OW = (d->in_w + 2 * d->pad - d->k) / d->stride + 1;
+  p.xp = d->x_pitch > 0 ? d->x_pitch : d->in_w;
+  p.yp = d->y_pitch > 0 ? d->y_pitch : p.OW;
+  ATDN_REQUIRE(p.xp >= d->in_w && p.yp >= p.OW, ATDN_ERR_ARG, "atdn_conv32: row pitch smaller than the row");
   ATDN_REQUIRE(p.OH >= 1 && p.OW >= 1, ATDN_ERR_ARG, "atdn_conv32: empty output");
-  if (d->cout == 16 && d->cin <= 16 && p.OW >= 32) {   // CLVO encoder hot layers: register-tiled kernels
+  if (d->cout == 16 && d->cin == 16 && d->k == 1 && d->stride == 2 && d->pad == 0 && !d->mish && !d->in_scale && !d->bn_scale &&
+      !d->skip && (reinterpret_cast<uintptr_t>(d->y) & 7u) == 0) {   // ResidualConv skip path
+    const long long total = static_cast<long long>(p.B) * p.OH * ((p.OW + 1) / 2);
+    const long long blocks = (total + 255) / 256;
+    skip16_kernel<<<static_cast<unsigned>(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ATDN_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (d->cout == 16 && d->cin <= 16 && p.OW >= 24) {   // CLVO encoder layers: register-tiled kernels
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (d->w_host) {                                     // weights through the constant bank
-      if (d->k == 3 && d->stride == 1 && d->cin == 16) return launch_conv16c<3, 1, 16, 8, 4>(p, d->w_host, st);
-      if (d->k == 3 && d->stride == 2 && d->cin == 16) return launch_conv16c<3, 2, 16, 4, 4>(p, d->w_host, st);
-      if (d->k == 7 && d->stride == 2 && d->cin == 2) return launch_conv16c<7, 2, 2, 2, 4>(p, d->w_host, st);
+    if (p.xp % 4 == 0 && aligned16(d->x)) {               // 16-byte rows: TMA-fed tiles
+      if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->cin == 16 && !d->in_scale) return launch_conv16t<3, 1, 1, 16, 8, false>(p, st);
+      if (d->k == 3 && d->stride == 2 && d->pad == 1 && d->cin == 16 && !d->in_scale) return launch_conv16t<3, 2, 1, 16, 4, false>(p, st);
+      if (d->k == 7 && d->stride == 2 && d->pad == 3 && d->cin == 2 && d->in_scale) return launch_conv16t<7, 2, 3, 2, 2, true>(p, st);
     }
     if (d->k == 3 && d->stride == 1) return launch_conv16<3, 1, 8>(p, st);
     if (d->k == 3 && d->stride == 2) return launch_conv16<3, 2, 4>(p, st);

@@ -135,6 +135,51 @@ class KeyframeIndex:
         return merge_shard_minima([(float(t[0]), int(t[1])) for t in allb])
 
 
+class Relocalizer:
+    """Relocalisation + refinement (``neural_slam.py:355-370, 387-399``) on the B200 path, as one stream of
+    kernels: embed the query (encoder only -- the reference also runs the unused VAE decoder), search the keyframe
+    database, run flow + pose between the closest keyframe's image and the query, compose
+    ``refined = initial @ transform(rot, tr)``.  Keyframe images live in device memory here (the reference
+    ``torch.load``s ``rgb/%06d.pth`` per query); poses stay on the host like ``Frame.pose``.
+
+    ``flow_net`` / ``odometry_net`` / ``mapping_net``: ``RAFTGMA``, ``ATDNVO``, ``MappingEncoder`` on one device.
+    The odometry net's LSTM state advances exactly as in the reference, which calls the same stateful network."""
+
+    def __init__(self, flow_net, odometry_net, mapping_net, iters=12):
+        self.flow_net, self.odometry_net, self.mapping_net, self.iters = flow_net, odometry_net, mapping_net, iters
+        self.index = None
+        self.images, self.poses = [], []
+
+    def add_keyframe(self, image, pose):
+        """image fp32/uint8 [3,H,W] (0..255, already at the SLAM size), pose [4,4]; embeds and registers it."""
+        dev = next(self.mapping_net.parameters()).device
+        img = image.to(dev).float().unsqueeze(0).contiguous()
+        mu = self.mapping_net.embed(img)
+        if self.index is None:
+            self.index = KeyframeIndex(dim=mu[0].numel(), device=dev)
+        self.index.add(mu)
+        self.images.append(img)
+        self.poses.append(pose.detach().to("cpu", torch.float32).clone())
+        return len(self.images) - 1
+
+    @torch.no_grad()
+    def relocalize(self, image):
+        """image [1,3,H,W] or [3,H,W] -> (initial_pose [4,4], refined_pose [4,4], distances [K], keyframe index)."""
+        from .poses import transform
+        if self.index is None or len(self.index) == 0:
+            raise RuntimeError("relocalisation without keyframes")
+        dev = self.index.device
+        img = image.to(dev).float()
+        img = img.unsqueeze(0) if img.dim() == 3 else img
+        mu = self.mapping_net.embed(img.contiguous())
+        k, distances = self.index.search(mu)
+        initial = self.poses[k]
+        _, flow = self.flow_net(self.images[k], img, iters=self.iters, test_mode=True)      # :395
+        rot, tr = self.odometry_net(flow)                                                    # :396
+        pose_diff = transform(rot.squeeze(), tr.squeeze())                                   # :397
+        return initial, initial @ pose_diff, distances, k
+
+
 def merge_shard_minima(pairs):
     """[(distance, global_index)] per shard -> (global_index, distance) of the first global minimum."""
     best = None

@@ -33,7 +33,6 @@ class _ConvBlock:
 
     def __init__(self, sd, p):
         self.w = sd[p + "conv.weight"].float().contiguous()
-        self.w_host = self.w.cpu().contiguous()      # constant-bank path of atdn_conv32 (kernel-parameter weights)
         self.b = sd[p + "conv.bias"].float().contiguous()
         self.bn_s, self.bn_b = _bn_affine(sd, p + "bn")
 
@@ -53,25 +52,30 @@ def conv_out(n, k, s, p):
     return (n + 2 * p - k) // s + 1
 
 
-def run_conv_block(x, blk, stride, pad, in_scale=None, in_shift=None, skip=None, bn2=None):
+def new_map(b, c, h, w, device, pad_rows):
+    """fp32 NCHW map; ``pad_rows`` rounds the row pitch up to 4 floats (16-byte rows: the TMA-fed conv kernel can
+    then load it) and returns the [..., :w] view."""
+    pw = (w + 3) // 4 * 4 if pad_rows else w
+    return torch.empty(b, c, h, pw, dtype=torch.float32, device=device)[..., :w]
+
+
+def run_conv_block(x, blk, stride, pad, in_scale=None, in_shift=None, skip=None, bn2=None, pad_rows=False):
     b, _, h, w = x.shape
     k = blk.w.shape[2]
-    y = torch.empty(b, blk.w.shape[0], conv_out(h, k, stride, pad), conv_out(w, k, stride, pad),
-                    dtype=torch.float32, device=x.device)
+    y = new_map(b, blk.w.shape[0], conv_out(h, k, stride, pad), conv_out(w, k, stride, pad), x.device, pad_rows)
     ops.conv32(x, blk.w, blk.b, y, stride=stride, pad=pad, mish=True, in_scale=in_scale, in_shift=in_shift,
                bn_scale=blk.bn_s, bn_shift=blk.bn_b, skip=skip, bn2_scale=bn2[0] if bn2 else None,
-               bn2_shift=bn2[1] if bn2 else None, w_host=blk.w_host)
+               bn2_shift=bn2[1] if bn2 else None)
     return y
 
 
-def run_residual_block(x, blk, stride):
+def run_residual_block(x, blk, stride, pad_rows=False):
     """bn(mish(conv.1(conv.0(x)) + skip_layer(x))) with conv.i = bn(mish(conv)) -- layers/conv.py:83-90."""
-    y = run_conv_block(x, blk.c0, 1, 1)
+    y = run_conv_block(x, blk.c0, 1, 1, pad_rows=pad_rows)
     b, _, h, w = x.shape
-    skip = torch.empty(b, blk.skip_w.shape[0], conv_out(h, 1, stride, 0), conv_out(w, 1, stride, 0),
-                       dtype=torch.float32, device=x.device)
+    skip = new_map(b, blk.skip_w.shape[0], conv_out(h, 1, stride, 0), conv_out(w, 1, stride, 0), x.device, pad_rows)
     ops.conv32(x, blk.skip_w, blk.skip_b, skip, stride=stride, pad=0)
-    return run_conv_block(y, blk.c1, stride, 1, skip=skip, bn2=(blk.bn_s, blk.bn_b))
+    return run_conv_block(y, blk.c1, stride, 1, skip=skip, bn2=(blk.bn_s, blk.bn_b), pad_rows=pad_rows)
 
 
 class _Packed:
@@ -141,9 +145,10 @@ class ATDNVO(nn.Module):
         L.require_cuda(flows)
         p = self._weights(flows.device)
         x = flows.float().contiguous()
-        x = run_conv_block(x, p.stem, 2, 3, in_scale=p.in_scale, in_shift=p.in_shift)
+        # intermediate maps carry 16-byte row pitches (154 -> 156, 77 -> 80, 39 -> 40 columns) for the TMA-fed kernels
+        x = run_conv_block(x, p.stem, 2, 3, in_scale=p.in_scale, in_shift=p.in_shift, pad_rows=True)
         for blk in p.res:
-            x = run_residual_block(x, blk, 2)
+            x = run_residual_block(x, blk, 2, pad_rows=True)
         x = run_conv_block(x, p.tail, 3, 0)
         x = x.flatten(1).contiguous()
         feat = torch.empty(x.shape[0], 512, dtype=torch.float32, device=x.device)

@@ -362,18 +362,25 @@ def coords_init(coords1, flow, flow_init=None):
 # ----------------------------------------------------------------------------------------------
 @_profiled
 def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shift=None, skip=None, bn_scale=None,
-           bn_shift=None, bn2_scale=None, bn2_shift=None, w_host=None):
+           bn_shift=None, bn2_scale=None, bn2_shift=None):
     d = L.Conv32Desc()
     b, cin, h, wd = x.shape
     cout, _, k, _ = w.shape
+
+    def pitch(t):
+        """Row pitch of an NCHW map that is dense except for padded rows (a [..., :w] view of a wider buffer)."""
+        bb, cc, hh, _ = t.shape
+        pt = t.stride(2)
+        assert t.stride(3) == 1 and t.stride(1) == hh * pt and t.stride(0) == cc * hh * pt, "unsupported strides"
+        return pt
     d.x, d.y, d.w, d.bias = L.ptr(x), L.ptr(y), L.ptr(w), L.ptr(bias)
     d.in_scale, d.in_shift, d.skip = L.ptr(in_scale), L.ptr(in_shift), L.ptr(skip)
     d.bn_scale, d.bn_shift = L.ptr(bn_scale), L.ptr(bn_shift)
     d.bn2_scale, d.bn2_shift = L.ptr(bn2_scale), L.ptr(bn2_shift)
     d.batch, d.cin, d.cout, d.in_h, d.in_w, d.k, d.stride, d.pad, d.mish = b, cin, cout, h, wd, k, stride, pad, int(mish)
-    if w_host is not None:   # host copy of w: lets the 16-channel layers read their filter from the constant bank
-        assert w_host.device.type == "cpu" and w_host.dtype == torch.float32 and w_host.is_contiguous() and w_host.shape == w.shape
-        d.w_host = w_host.data_ptr()
+    d.x_pitch, d.y_pitch = pitch(x), pitch(y)
+    if skip is not None:
+        assert skip.shape == y.shape and pitch(skip) == d.y_pitch, "skip must share the layout of y"
     L.check(L.load().atdn_conv32(C.byref(d), L.stream_ptr()), "atdn_conv32")
 
 

@@ -227,9 +227,8 @@ typedef struct atdn_conv32_desc {
   const float* skip;      /* [B, cout, oh, ow] or NULL: enables post2                               */
   const float* bn2_scale; const float* bn2_shift;  /* [cout] batch norm of post2, or NULL           */
   int32_t batch, cin, cout, in_h, in_w, k, stride, pad, mish;
-  const float* w_host;    /* optional HOST copy of w: the 16-channel CLVO layers (7x7/2 stem, 3x3/1, 3x3/2 on
-                             maps >= 32 wide) then read their filter from the constant bank (kernel parameter)
-                             instead of shared memory; NULL = always stage weights from device memory          */
+  int32_t x_pitch, y_pitch; /* row pitch in elements of x and of y / skip; 0 = dense (in_w / out_w).  The 16-channel
+                               CLVO layers take their input tiles by TMA when x is 16-byte aligned with x_pitch % 4 == 0 */
 } atdn_conv32_desc;
 int atdn_conv32(const atdn_conv32_desc* desc, void* stream);
 

@@ -48,6 +48,42 @@ def test_localization_vs_reference_golden():
     assert gpu_e2e.check_localization()
 
 
+def test_relocalizer_matches_oracle_composition():
+    """Relocalizer (neural_slam.py:355-399): embed -> search -> flow -> pose -> initial @ transform, against the same
+    composition of the oracle pieces; keyframe index bit-exact (planted near-duplicate), refined pose 1e-4 relative."""
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.localization import MappingEncoder, Relocalizer
+    from atdn_vslam_b200.odometry import ATDNVO
+    from oracle import clvo_oracle, gma_oracle
+    m, gsd = gpu_e2e._gma()
+    vsd, esd = synth.atdnvo_state_dict(), synth.vae_state_dict()
+    vo = ATDNVO()
+    vo.load_state_dict(vsd)
+    vo = vo.to("cuda").eval()
+    enc = MappingEncoder()
+    enc.load_state_dict(esd)
+    enc = enc.to("cuda").eval()
+    frames = synth.frame_sequence(5, 376, 1232, seed=77, max_shift=4.0)
+    poses = [torch.eye(4) for _ in range(4)]
+    for i, p in enumerate(poses):
+        p[:3, 3] = torch.tensor([1.0 * i, 0.1 * i, 15.0 * i])
+    rel = Relocalizer(m, vo, enc, iters=2)
+    for i in range(4):
+        assert rel.add_keyframe(frames[i], poses[i]) == i
+    query = frames[4]                                   # one step after keyframe 3: its nearest keyframe
+    initial, refined, dist, k = rel.relocalize(query)
+    embs = torch.stack([clvo_oracle.vae_embed(esd, frames[i:i + 1]).reshape(-1) for i in range(4)])
+    code = clvo_oracle.vae_embed(esd, query.unsqueeze(0)).reshape(-1)
+    ref_k, ref_d = clvo_oracle.keyframe_search(embs, code)
+    assert k == ref_k
+    assert (dist.cpu() - ref_d).abs().max() <= 1e-4 * ref_d.abs().max()
+    _, up = gma_oracle.raftgma_forward(gsd, frames[ref_k:ref_k + 1], query.unsqueeze(0), iters=2)
+    rot, tr = clvo_oracle.atdnvo_forward(vsd, up, clvo_oracle.zero_state())
+    ref_refined = poses[ref_k] @ clvo_oracle.transform(rot.squeeze(), tr.squeeze())
+    assert torch.equal(initial, poses[ref_k])
+    assert (refined - ref_refined).abs().max() <= 2e-3 * ref_refined.abs().max()   # flow fp16 floor -> pose; CLVO on equal flow is 1e-7
+
+
 def test_native_library_is_the_one_that_ran():
     """The CUDA extension must be loaded from the in-tree .so and must have launched kernels."""
     from atdn_vslam_b200 import _lib as L

@@ -8,8 +8,18 @@ rows = list(csv.reader(sys.stdin))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]
 ci = {k: i for i, k in enumerate(h)}
-body = [r for r in rows[hi + 1:] if len(r) >= len(h) - 1]
 key = ci["# Samples"]
+
+
+def _num(x):
+    try:
+        float(x or 0)
+        return True
+    except ValueError:
+        return False
+
+
+body = [r for r in rows[hi + 1:] if len(r) >= len(h) - 1 and _num(r[key])]   # a second table (another view) may follow
 tot = sum(float(r[key] or 0) for r in body)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 25
 stalls = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]

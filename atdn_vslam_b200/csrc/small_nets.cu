@@ -18,6 +18,16 @@ __device__ __forceinline__ float mishf(float x) {
   const float t = n * (n + 2.0f);
   return x > 20.0f ? x : x * __fdividef(t, t + 2.0f);
 }
+// Branch-free variant for the register-tiled kernels (64 calls per thread): clamping the exponent argument at the
+// softplus threshold makes t / (t + 2) round to exactly 1.0f there (t = 2.4e17), so x > 20 returns x without a select;
+// ex2.approx + rcp.approx: ~3e-7 relative.
+__device__ __forceinline__ float mish_fast(float x) {
+  const float n = ex2_approx(fminf(x, 20.0f) * 1.4426950408889634f);
+  const float t = n * (n + 2.0f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 2.0f));
+  return x * (t * r);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Direct convolution, NCHW fp32.  CTA = 16x16 output pixels x 16 output channels; input channels are
@@ -312,7 +322,7 @@ struct C16tGeom {
   static_assert(ROW <= 256, "TMA box limit");
 };
 
-template <int K, int S, int PAD, int CIN, int CIT, bool AFFINE>
+template <int K, int S, int PAD, int CIN, int CIT, bool AFFINE, bool SKIP>
 __global__ void __launch_bounds__(kC16Threads) conv16t_kernel(const __grid_constant__ CUtensorMap tmx,
                                                               const __grid_constant__ Conv32Params p) {
   using G = C16tGeom<K, S, PAD>;
@@ -415,16 +425,19 @@ __global__ void __launch_bounds__(kC16Threads) conv16t_kernel(const __grid_const
     }
     if (chunk + 1 < NCH) __syncthreads();          // all reads of this stage are done before it is refilled
   }
+  // epilogue of a Conv block (layers/conv.py:36-37: bn(mish(conv + bias))), SKIP: ResidualConv tail bn2(mish(. + skip))
   if (oy >= p.OH) return;
   const bool v4 = (p.yp & 3) == 0 && ox0 + 4 <= p.yp;
 #pragma unroll
   for (int co = 0; co < 16; ++co) {
     const long long o = ((static_cast<long long>(b) * 16 + co) * p.OH + oy) * p.yp + ox0;
-    const float bias = p.bias ? __ldg(p.bias + co) : 0.0f;
-    const float s1 = p.bn_scale ? __ldg(p.bn_scale + co) : 1.0f, h1 = p.bn_scale ? __ldg(p.bn_shift + co) : 0.0f;
-    const float s2 = p.bn2_scale ? __ldg(p.bn2_scale + co) : 1.0f, h2 = p.bn2_scale ? __ldg(p.bn2_shift + co) : 0.0f;
+    const float bias = __ldg(p.bias + co);
+    const float s1 = __ldg(p.bn_scale + co), h1 = __ldg(p.bn_shift + co);
+    float s2 = 1.0f, h2 = 0.0f;
     float v[4], sk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (p.skip) {
+    if constexpr (SKIP) {
+      s2 = __ldg(p.bn2_scale + co);
+      h2 = __ldg(p.bn2_shift + co);
       if (v4) {
         const float4 f = *reinterpret_cast<const float4*>(p.skip + o);
         sk[0] = f.x; sk[1] = f.y; sk[2] = f.z; sk[3] = f.w;
@@ -436,13 +449,8 @@ __global__ void __launch_bounds__(kC16Threads) conv16t_kernel(const __grid_const
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float t = acc[i][co] + bias;
-      if (p.mish) t = mishf(t);
-      if (p.bn_scale) t = t * s1 + h1;
-      if (p.skip) {
-        t = mishf(t + sk[i]);
-        if (p.bn2_scale) t = t * s2 + h2;
-      }
+      float t = mish_fast(acc[i][co] + bias) * s1 + h1;
+      if constexpr (SKIP) t = mish_fast(t + sk[i]) * s2 + h2;
       v[i] = t;
     }
     if (v4) {
@@ -455,7 +463,7 @@ __global__ void __launch_bounds__(kC16Threads) conv16t_kernel(const __grid_const
   }
 }
 
-template <int K, int S, int PAD, int CIN, int CIT, bool AFFINE>
+template <int K, int S, int PAD, int CIN, int CIT, bool AFFINE, bool SKIP>
 static int launch_conv16t(Conv32Params p, cudaStream_t stream) {
   using G = C16tGeom<K, S, PAD>;
   constexpr int NSTAGE = CIN / CIT > 1 ? 2 : 1;
@@ -464,7 +472,7 @@ static int launch_conv16t(Conv32Params p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     if (smem > 48 * 1024)
-      ATDN_CUDA(cudaFuncSetAttribute(conv16t_kernel<K, S, PAD, CIN, CIT, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      ATDN_CUDA(cudaFuncSetAttribute(conv16t_kernel<K, S, PAD, CIN, CIT, AFFINE, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   CUtensorMap tmx;
@@ -477,7 +485,7 @@ static int launch_conv16t(Conv32Params p, cudaStream_t stream) {
   }
   p.tiles_x = ceil_div(p.OW, kC16TW);
   dim3 grid(p.tiles_x * ceil_div(p.OH, kC16TH), 1, p.B);
-  conv16t_kernel<K, S, PAD, CIN, CIT, AFFINE><<<grid, kC16Threads, smem, stream>>>(tmx, p);
+  conv16t_kernel<K, S, PAD, CIN, CIT, AFFINE, SKIP><<<grid, kC16Threads, smem, stream>>>(tmx, p);
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -672,10 +680,16 @@ extern "C" int atdn_conv32(const atdn_conv32_desc* d, void* stream) {
   }
   if (d->cout == 16 && d->cin <= 16 && p.OW >= 24) {   // CLVO encoder layers: register-tiled kernels
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (p.xp % 4 == 0 && aligned16(d->x)) {               // 16-byte rows: TMA-fed tiles
-      if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->cin == 16 && !d->in_scale) return launch_conv16t<3, 1, 1, 16, 8, false>(p, st);
-      if (d->k == 3 && d->stride == 2 && d->pad == 1 && d->cin == 16 && !d->in_scale) return launch_conv16t<3, 2, 1, 16, 4, false>(p, st);
-      if (d->k == 7 && d->stride == 2 && d->pad == 3 && d->cin == 2 && d->in_scale) return launch_conv16t<7, 2, 3, 2, 2, true>(p, st);
+    // 16-byte rows + the Conv-block epilogue (bias, mish, bn; skip with bn2): TMA-fed tiles
+    const bool block = d->bias && d->mish && d->bn_scale && (!d->skip || d->bn2_scale);
+    if (block && p.xp % 4 == 0 && aligned16(d->x)) {
+      const bool k3 = d->k == 3 && d->pad == 1 && d->cin == 16 && !d->in_scale;
+      if (k3 && d->stride == 1 && !d->skip) return launch_conv16t<3, 1, 1, 16, 8, false, false>(p, st);
+      if (k3 && d->stride == 1 && d->skip) return launch_conv16t<3, 1, 1, 16, 8, false, true>(p, st);
+      if (k3 && d->stride == 2 && !d->skip) return launch_conv16t<3, 2, 1, 16, 4, false, false>(p, st);
+      if (k3 && d->stride == 2 && d->skip) return launch_conv16t<3, 2, 1, 16, 4, false, true>(p, st);
+      if (d->k == 7 && d->stride == 2 && d->pad == 3 && d->cin == 2 && d->in_scale && !d->skip)
+        return launch_conv16t<7, 2, 3, 2, 2, true, false>(p, st);
     }
     if (d->k == 3 && d->stride == 1) return launch_conv16<3, 1, 8>(p, st);
     if (d->k == 3 && d->stride == 2) return launch_conv16<3, 2, 4>(p, st);

@@ -147,9 +147,12 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
 
     // staging slot ring: a slot is reused once the bulk store issued two stores ago has read it
     auto acquire = [&]() -> int {
-      if (lane == 0) bulk_wait_read<1>();
+      // fp16 boxes are at most 2 KiB: the warp's 8 KiB of staging hold a ring of FOUR slots (three stores may still be
+      // reading shared memory).  Measured: no faster than two slots -- the epilogue is bound by its serial
+      // tcgen05.ld -> scale/convert -> st.shared -> fence -> store chain per row, not by slot reuse.
+      if (lane == 0) bulk_wait_read<HALF ? 3 : 1>();
       __syncwarp();
-      return (nstore & 1) * kCorrSlotBytes;
+      return HALF ? (nstore & 3) * (kCorrSlotBytes / 2) : (nstore & 1) * kCorrSlotBytes;
     };
     auto commit = [&](const CUtensorMap* m, int off, int c0, int c1) {
       fence_proxy_async_smem();

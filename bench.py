@@ -298,12 +298,17 @@ def run_ours(args):
         lab, a = max(table.items(), key=lambda kv: kv[1]["ms"])
         t_tensor = a["flops"] / (pk["tflops_sustained"] * 1e12)
         t_hbm = a["bytes"] / (pk["hbm_gbs"] * 1e9)
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from the committed ncu --set full captures
         if os.path.exists(tp):
-            ent = json.load(open(tp)).get(lab)
-            if ent and ent.get("batch_pairs") == args.batch_pairs:
-                traffic = ent["dram_bytes_per_launch"]
+            caps = json.load(open(tp)).get(lab, [])
+            exact = [c for c in caps if c.get("batch_pairs") == args.batch_pairs]
+            if exact:
+                traffic = exact[-1]["dram_bytes_per_launch"]
+            elif caps:   # the launch processes independent pairs: bytes scale with the pairs per launch
+                c = caps[-1]
+                traffic = c["dram_bytes_per_launch"] * args.batch_pairs / c["batch_pairs"]
+                traffic_note = f"scaled from the batch_pairs={c['batch_pairs']} capture"
         if t_tensor >= t_hbm:
             ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
             line["roofline"] = {"kernel": lab, "bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
@@ -313,6 +318,8 @@ def run_ours(args):
             line["roofline"] = {"kernel": lab, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                 "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"] + " copy bandwidth",
                                 "algorithmic_bytes_per_launch": a["bytes"] / a["launches"], "launches": a["launches"]}
+        if traffic_note:
+            line["roofline"]["traffic_note"] = traffic_note
         # ---- CPU baseline (oracle port of the reference device=cpu path) on a bounded sample
         if world == 1 and not args.no_cpu_baseline:
             v, dt = cpu_pairs_per_s(args.cpu_pairs, warm=1)
@@ -331,7 +338,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES)
-    ap.add_argument("--batch-pairs", type=int, default=27)
+    ap.add_argument("--batch-pairs", type=int, default=54)
     ap.add_argument("--cpu-pairs", type=int, default=6)
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -21,12 +21,14 @@ for (cin, k, s, pad, h, w, affine) in [(16, 3, 1, 1, 40, 156, False), (16, 3, 2,
     y.fill_(float("nan"))
     t0 = time.time()
     try:
-        ops.conv32(x, wt, bias, y, stride=s, pad=pad, mish=False, in_scale=sc, in_shift=sh)
+        bs, bh = (torch.rand(16, generator=g) + 0.5).cuda(), torch.randn(16, generator=g).cuda()
+        ops.conv32(x, wt, bias, y, stride=s, pad=pad, mish=True, in_scale=sc, in_shift=sh, bn_scale=bs, bn_shift=bh)
         torch.cuda.synchronize()
     except Exception as e:
         print("FAIL", cin, k, s, h, w, str(e)[:100], f"{time.time()-t0:.2f}s")
         break
     xin = x if not affine else x * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
-    ref = F.conv2d(xin.contiguous().double(), wt.double(), bias.double(), stride=s, padding=pad).float()
+    ref = F.conv2d(xin.contiguous().double(), wt.double(), bias.double(), stride=s, padding=pad)
+    ref = (F.mish(ref) * bs.double().view(1, -1, 1, 1) + bh.double().view(1, -1, 1, 1)).float()
     err = (y - ref).abs().max().item()
     print(f"cin={cin} k={k} s={s} {h}x{w}: max err {err:.3e} (ref max {ref.abs().max().item():.2f}) {time.time()-t0:.2f}s", flush=True)

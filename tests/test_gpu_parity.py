@@ -84,6 +84,23 @@ def test_relocalizer_matches_oracle_composition():
     assert (refined - ref_refined).abs().max() <= 2e-3 * ref_refined.abs().max()   # flow fp16 floor -> pose; CLVO on equal flow is 1e-7
 
 
+def test_write_flows_matches_dataset_format(tmp_path):
+    """Flow pre-computation producer: flows2/<seq>/%06d.pt, fp16 [1,2,376,W] (odometry/datasets.py:113-123), equal to
+    the per-pair forward rounded to fp16."""
+    import os
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.keyframes import write_flows
+    m, _ = gpu_e2e._gma()
+    frames = synth.frame_sequence(4, 376, 1232, seed=3).cuda()
+    n = write_flows(m, frames, str(tmp_path), batch_pairs=2, iters=2, start_index=10)
+    assert n == 3 and sorted(os.listdir(tmp_path)) == ["000010.pt", "000011.pt", "000012.pt"]
+    for t in range(3):
+        f = torch.load(os.path.join(tmp_path, f"{10 + t:06d}.pt"))
+        assert f.dtype == torch.float16 and tuple(f.shape) == (1, 2, 376, 1232)
+        _, up = m(frames[t:t + 1], frames[t + 1:t + 2], iters=2, test_mode=True)
+        assert (f.float() - up.cpu()).abs().max() <= 2e-2       # fp16 rounding of |flow| <= 16 px + batch-composition noise
+
+
 def test_native_library_is_the_one_that_ran():
     """The CUDA extension must be loaded from the in-tree .so and must have launched kernels."""
     from atdn_vslam_b200 import _lib as L

@@ -15,6 +15,7 @@
 //     accumulator buffers: 8 epilogue warps drain tile i while the MMA warp accumulates tile i+1;
 //   * A and B have independent producer threads and mbarrier rings (A advances per chunk, B per tap).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -25,13 +26,13 @@
 namespace atdn {
 
 constexpr int kConvThreads = 384;   // warp 0: A producer, 1: B producer, 2: TMEM alloc + MMA, 3: idle, 4-11: epilogue
-constexpr int kMaxAStages = 4;
-constexpr int kMaxBStages = 8;
+constexpr int kMaxAStages = 8;
+constexpr int kMaxBStages = 12;
 constexpr int kSubH = 16, kSubW = 8;   // one M = 128 sub-tile: 16 x 8 output pixels
 constexpr int kMaxDynSmem = 232448 - 1024;   // 227 KiB per CTA minus the static shared memory (barriers)
 
 struct alignas(64) ConvParams {
-  CUtensorMap tmA, tmA2, tmB;
+  CUtensorMap tmA, tmA2, tmB, tmOut;
   EpiParams e;
   int tiles_w, tiles_h, n_tiles, total_tiles;
   int out_h, out_w;
@@ -39,6 +40,8 @@ struct alignas(64) ConvParams {
   int chunks_a, chunks_a2, c_a, c_a2;
   int box_w;                         // halo box width in pixels
   int a_stage_bytes, a_tx_bytes, a_stages, b_stages;
+  int out_tma;                       // STORE16: fp16 output boxes staged in shared memory and written by TMA stores
+  int b_resident;                    // all (chunk, tap) weight tiles fit shared memory: loaded once per CTA, never recycled
   long long* stamps;                 // optional clock64 stamps of CTA 0 (timing experiments), or null
 };
 
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
+  uint8_t* smem_out = smem_b + p.b_stages * kBBytes;   // out_tma: 8 epilogue warps x 2 slots x 2 KiB (1 KiB aligned)
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler as well
   const int lane = threadIdx.x & 31;
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     if (p.chunks_a2 > 0) tma_prefetch_desc(&p.tmA2);
+    if (p.out_tma) tma_prefetch_desc(&p.tmOut);
   }
   if (warp == 2) {
     if constexpr (PAIR) tmem_alloc_pair(&tmem_base_smem, 512);
@@ -153,6 +158,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===== B producer: one (BN / CL) x 64 weight tile per (tile, chunk, tap) =====
+    // b_resident: the whole filter of this N tile stays in shared memory (stage = chunk * taps + tap), so the weights
+    // cross L2 -> SM once per CTA instead of once per tile (a 1x1 conv moves 2 weight bytes per activation byte otherwise)
     int sb = 0;
     uint32_t pb = 0;
     const int taps = p.taps_h * p.taps_w;
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
       for (int c = 0; c < chunks; ++c) {
         int k0 = c * 64;
         for (int tap = 0; tap < taps; ++tap, k0 += chunks * 64) {
-          mbar_wait(&b_empty[sb], pb ^ 1u);
+          if (!p.b_resident) mbar_wait(&b_empty[sb], pb ^ 1u);
           if (elect_one_sync()) {
             if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], CL * kBBytes);
             if constexpr (PAIR) tma_load_4d_pair(smem_b + sb * kBBytes, &p.tmB, &b_full[sb], k0, n0, 0, 0);
@@ -171,6 +178,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
           if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
         }
       }
+      if (p.b_resident) break;
     }
   } else if (warp == 2) {
     // ===== MMA issuer (leader CTA only in PAIR mode); warp-uniform loop, one elected lane issues =====
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
           uint32_t row_off = 0;   // (dy * WB + dx) * 128 B >> 4
           for (int dy = 0; dy < p.taps_h; ++dy, row_off += static_cast<uint32_t>(p.box_w - p.taps_w) * 8u) {
             for (int dx = 0; dx < p.taps_w; ++dx, row_off += 8u) {
-              mbar_wait(&b_full[sb], pb);
+              mbar_wait(&b_full[sb], p.b_resident ? 0u : pb);   // resident tiles complete phase 0 once and stay
               tcgen05_fence_after();
               const uint64_t a_desc = a_desc_stage + row_off;
               const uint64_t b_desc = make_smem_desc_sw128(smem_b_u32 + sb * kBBytes);
@@ -221,7 +229,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
                     }
                   }
                 }
-                if constexpr (PAIR) umma_commit_pair(&b_empty[sb]); else umma_commit(&b_empty[sb]);
+                if (!p.b_resident) {
+                  if constexpr (PAIR) umma_commit_pair(&b_empty[sb]); else umma_commit(&b_empty[sb]);
+                }
                 if (dy == p.taps_h - 1 && dx == p.taps_w - 1) {
                   if constexpr (PAIR) umma_commit_pair(&a_empty[sa]); else umma_commit(&a_empty[sa]);
                   if (c == chunks - 1) {
@@ -249,6 +259,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     int buf = 0;
     uint32_t pf0 = 0, pf1 = 0;
     int n_tile_iter = 0;
+    int n_out = 0;                                            // out_tma: staging slots used so far by this warp
     for (int t = t_begin; t < t_end; ++t, ++n_tile_iter) {
       const TileCoord tc = decode_tile<CL>(p, t, rank, kSubW * MT, BN);
       const uint32_t pf = buf ? pf1 : pf0;
@@ -270,6 +281,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
         uint32_t v[32];
         tmem_ld_32x32(trow + s * BN + cc * 32, v);
         tmem_ld_wait();
+        if constexpr (EPI == ATDN_EPI_STORE16 || EPI == ATDN_EPI_GRU_Q || EPI == ATDN_EPI_GRU_ZR) {
+          // fp16 outputs: out16 (STORE16, GRU_Q: the new hidden state) or r*h (GRU_ZR, accumulator columns 128..255)
+          if (p.out_tma && (EPI != ATDN_EPI_GRU_ZR || tc.n0 + cc * 32 >= 128)) {
+            // The warp's 32 accumulator rows are a 4 x 8 pixel patch: its [32 pixels][32 channels] fp16 chunk is one TMA
+            // box {32, 8, 4, 1}.  Thread-per-row global stores touched 32 different rows per instruction (16 bytes each:
+            // half sectors), which made every 1x1 convolution epilogue-bound (9K cycles per 128 x 256 tile vs 1-2.7K of MMAs).
+            const int n = tc.n0 + cc * 32;
+            if (n < p.e.n_valid) {                           // warp-uniform
+              uint8_t* slot = smem_out + ((warp - 4) * 2 + (n_out & 1)) * 2048;
+              if (lane == 0) bulk_wait_read<1>();            // the store issued two chunks ago has read this slot
+              __syncwarp();
+              epilogue_chunk<EPI>(p.e, valid, pix, n, v, sidx, smem_u32(slot) + lane * 64, static_cast<uint32_t>(lane >> 1) & 3u);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&p.tmOut, slot, EPI == ATDN_EPI_GRU_ZR ? n - 128 : n, tc.w0 + s * kSubW, tc.h0 + q * 4, tc.batch);
+                bulk_commit();
+              }
+              ++n_out;
+            }
+            continue;
+          }
+        }
         epilogue_chunk<EPI>(p.e, valid, pix, tc.n0 + cc * 32, v, sidx);
       }
       tcgen05_fence_before();
@@ -280,6 +314,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
       }
       if (stamp && threadIdx.x == 128 && n_tile_iter < 8) p.stamps[24 + n_tile_iter] = clock64();
       buf ^= 1;
+    }
+    if (n_out > 0) {                                          // shared memory stays valid until the last store has read it
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
     }
   }
 
@@ -418,13 +456,46 @@ int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream) {
   p.a_tx_bytes = box_w * box_h * 128;
   p.a_stage_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;
   const int b_bytes = (bn / cl) * 128;
-  const int avail = kMaxDynSmem - 1024;   // 1 KiB alignment slack
+  {
+    const char* off = getenv("ATDN_NO_OUT_TMA");
+    const void* o16 = d->epi == ATDN_EPI_GRU_ZR ? d->rh16 : d->out;
+    p.out_tma = (d->epi == ATDN_EPI_STORE16 || d->epi == ATDN_EPI_GRU_Q || d->epi == ATDN_EPI_GRU_ZR) && o16 != nullptr &&
+                !(off && off[0] == '1') && aligned16(o16);
+  }
+  const int out_bytes = p.out_tma ? 8 * 2 * 2048 + 1024 : 0;   // staging slots (+ alignment of the slot base to 1 KiB)
+  const int avail = kMaxDynSmem - 1024 - out_bytes;   // 1 KiB alignment slack
   p.a_stages = (3 * p.a_stage_bytes + 4 * b_bytes <= avail) ? 3 : 2;
+  if (d->taps_h * d->taps_w == 1) {
+    // 1x1: one A box per weight tile, both rings drain at the same rate -- and an A box is 128 scattered 128-byte
+    // rows whose TMA latency (not bandwidth) bounds the kernel with 3 boxes in flight: split shared memory evenly
+    const int n = avail / (p.a_stage_bytes + b_bytes);
+    p.a_stages = n > kMaxAStages ? kMaxAStages : (n < 2 ? 2 : n);
+  }
   int bs = (avail - p.a_stages * p.a_stage_bytes) / b_bytes;
   p.b_stages = bs > kMaxBStages ? kMaxBStages : bs;
+  {
+    // resident weights: every (chunk, tap) tile of the single N tile in shared memory next to >= 2 A stages
+    const int need = chunks * d->taps_h * d->taps_w;
+    const char* off = getenv("ATDN_NO_B_RESIDENT");
+    if (!(off && off[0] == '1') && p.n_tiles == 1 && need <= kMaxBStages && 2 * p.a_stage_bytes + need * b_bytes <= avail) {
+      p.b_resident = 1;
+      p.b_stages = need;
+      const int as = (avail - need * b_bytes) / p.a_stage_bytes;
+      p.a_stages = as > kMaxAStages ? kMaxAStages : as;
+    }
+  }
   ATDN_REQUIRE(p.b_stages >= 2, ATDN_ERR_UNSUP, "atdn_tc_gemm: halo conv (mt=%d, bn=%d, taps %dx%d) does not fit shared memory", mt, bn, d->taps_h, d->taps_w);
-  const int smem = p.a_stages * p.a_stage_bytes + p.b_stages * b_bytes + 1024;
+  const int smem = p.a_stages * p.a_stage_bytes + p.b_stages * b_bytes + 1024 + out_bytes;
 
+  if (p.out_tma) {
+    const bool zr = d->epi == ATDN_EPI_GRU_ZR;                 // r*h: dense [pix, 128]
+    const int64_t opitch = zr ? 128 : d->out_pitch;
+    const int64_t odims[4] = {zr ? 128 : d->n_valid, d->out_w, d->out_h, d->a_dims[3]};
+    const int64_t ostr[3] = {opitch, (int64_t)d->out_w * opitch, (int64_t)d->out_h * d->out_w * opitch};
+    const uint32_t obox[4] = {32, (uint32_t)kSubW, 4, 1};
+    const __half* obase = zr ? static_cast<const __half*>(d->rh16) : static_cast<const __half*>(d->out) + d->out_ch_off;
+    if (int e = make_map(&p.tmOut, 2, CU_TENSOR_MAP_SWIZZLE_64B, obase, odims, ostr, obox, ones, "conv output")) return e;
+  }
   switch (d->epi) {
     case ATDN_EPI_STORE16:
       ATDN_REQUIRE(!(d->flags & ATDN_F_RESID) || (d->resid16 && d->resid_pitch % 8 == 0 && d->resid_ch_off % 8 == 0 && d->n_valid % 8 == 0), ATDN_ERR_ARG, "atdn_tc_gemm: residual");

@@ -82,9 +82,12 @@ __device__ __forceinline__ void store_row_f16(__half* dst, const float (&y)[32],
 }
 
 // sidx: state_index() of the pixel (float4 units), or < 0 to derive it from pix = (b * img_h + h) * img_w + w
+// st_row (STORE16, GRU_Q, r half of GRU_ZR): shared-memory address of this thread's 64-byte row in a 64B-swizzled staging box (the caller
+// hands the box to a TMA store), or 0 to store to global memory directly; st_swz = (row >> 1) & 3.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, long long pix, int n,
-                                               const uint32_t (&v)[32], long long sidx = -1) {
+                                               const uint32_t (&v)[32], long long sidx = -1, uint32_t st_row = 0,
+                                               uint32_t st_swz = 0) {
   if (n >= p.n_valid) return;
   if constexpr (EPI == ATDN_EPI_STORE16 || EPI == ATDN_EPI_GRU_ZR || EPI == ATDN_EPI_GRU_Q) {
     if (sidx < 0 && valid && (EPI != ATDN_EPI_STORE16 || (p.flags & ATDN_F_TANH_LO))) {
@@ -153,7 +156,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
         for (int j = 0; j < 8; ++j) y[g * 8 + j] = fmaxf(r[j] + y[g * 8 + j], 0.0f);
       }
     }
-    store_row_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y, ng, tail);
+    if (st_row != 0) {
+#pragma unroll
+      for (uint32_t g = 0; g < 4; ++g) {
+        const uint4 u = pack8_f16(&y[g * 8]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ((g ^ st_swz) << 4)), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                     : "memory");
+      }
+    } else {
+      store_row_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y, ng, tail);
+    }
   } else if constexpr (EPI == ATDN_EPI_STORE32) {
     float* dst = reinterpret_cast<float*>(p.out) + pix * p.out_pitch + p.out_ch_off + n;
 #pragma unroll
@@ -185,9 +197,18 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
         y[4 * i + 2] = sigmoid_fast(y[4 * i + 2]) * hv[i].z;
         y[4 * i + 3] = sigmoid_fast(y[4 * i + 3]) * hv[i].w;
       }
-      uint4* dst = reinterpret_cast<uint4*>(p.rh16 + pix * 128 + (n - 128));
+      if (st_row != 0) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) dst[g] = pack8_f16(&y[g * 8]);
+        for (uint32_t g = 0; g < 4; ++g) {
+          const uint4 u = pack8_f16(&y[g * 8]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ((g ^ st_swz) << 4)), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                       : "memory");
+        }
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(p.rh16 + pix * 128 + (n - 128));
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dst[g] = pack8_f16(&y[g * 8]);
+      }
     }
   } else if constexpr (EPI == ATDN_EPI_GRU_Q) {
     float4* h = reinterpret_cast<float4*>(p.h32) + sidx + (n >> 2) * 32;
@@ -204,9 +225,18 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i * 32] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n);
+    if (st_row != 0) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) dst[g] = pack8_f16(&y[g * 8]);
+      for (uint32_t g = 0; g < 4; ++g) {
+        const uint4 u = pack8_f16(&y[g * 8]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ((g ^ st_swz) << 4)), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                     : "memory");
+      }
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) dst[g] = pack8_f16(&y[g * 8]);
+    }
   } else if constexpr (EPI == ATDN_EPI_FLOW) {
     if (n == 0) {
       float2* c1 = reinterpret_cast<float2*>(p.h32) + pix;

@@ -70,7 +70,7 @@ def _fold_bn(w, b, sd, name):
 
 # (mt, bn, CTA pair) of the persistent halo-reuse kernel per output width (stride-1 convs); measured on B200 at
 # 47x154 x 24 pairs / encoder resolutions (profiles/r01b_halo_conv_timings.log)
-_HALO_CFG = {64: (4, 64, False), 96: (2, 96, True), 128: (2, 128, True), 192: (1, 192, True), 256: (1, 256, True),
+_HALO_CFG = {64: (4, 64, True), 96: (2, 96, True), 128: (2, 128, True), 192: (1, 192, True), 256: (1, 256, True),
              576: (1, 192, False)}
 
 

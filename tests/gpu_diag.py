@@ -216,6 +216,23 @@ def time_halo():
     return True
 
 
+def time_resident():
+    """Resident-weights mode of the halo kernel (all (chunk, tap) weight tiles stay in shared memory) against the
+    streamed-weights mode (ATDN_NO_B_RESIDENT=1) on the layers that qualify."""
+    for off in ("1", "0"):
+        os.environ["ATDN_NO_B_RESIDENT"] = off
+        print(f"--- ATDN_NO_B_RESIDENT={off}", flush=True)
+        bench_conv("c1x1 324->256", 324, 256, (1, 1), 256, 1, batch=27)
+        bench_conv("c1x1 324->256", 324, 256, (1, 1), 256, 1, batch=27, pair=True)
+        bench_conv("c1x1 128->256", 128, 256, (1, 1), 256, 1, batch=27)
+        bench_conv("c1x1 128->256", 128, 256, (1, 1), 256, 1, batch=27, pair=True)
+        bench_conv("enc 64->64", 64, 64, (3, 3), 64, 4, batch=14, h=188, w=616)
+        bench_conv("enc 64->64", 64, 64, (3, 3), 64, 4, batch=14, h=188, w=616, pair=True)
+        bench_conv("c3x3 128->64", 128, 64, (3, 3), 64, 2, batch=27, pair=True)
+    os.environ.pop("ATDN_NO_B_RESIDENT", None)
+    return True
+
+
 def check_corr_full(h8=47, w8=154, batch=2, reps=0):
     """streaming corr-pyramid kernel at full size: bit-identical to the one-tile-per-CTA kernel (same MMA shape,
     same K order, same pooling arithmetic), and timing."""
@@ -393,6 +410,7 @@ CHECKS = {
     "hpair_gru_q": lambda: check_gru(2, "q", pair=True),
     "halo_gru_zr_bn256": lambda: check_gru(1, "zr", bn=256),
     "time_halo": time_halo,
+    "time_resident": time_resident,
     "pair_rows_basic": lambda: check_rows(pair=True),
     "pair_rows_bn256": lambda: check_rows(m=700, n=512, k=256, bn=256, pair=True),
     "pair_rows_bn64_batch": lambda: check_rows(m=130, n=70, k=128, bn=64, batch=3, pair=True),

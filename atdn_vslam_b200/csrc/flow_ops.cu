@@ -715,6 +715,35 @@ __global__ void __launch_bounds__(256) flow_head_update_kernel(const __half* __r
   }
 }
 
+// flow_head.conv2 as "1x1 conv + gather": the tensor-core kernel evaluates all nine taps on the UNSHIFTED pixel,
+//   d[q, tap*2 + co] = sum_c w2[co, c, tap] * x[q, c]        (a 256 -> 18 1x1 convolution: x is read once, not 9x),
+// and this kernel sums the shifted contributions  delta[p, co] = bias[co] + sum_tap d[p + off(tap), tap*2 + co]
+// (zero for neighbours outside the image = the conv zero padding) and applies network.py:116.  The 3x3 conv with two
+// real output channels in a 32-wide MMA tile re-read its A tile for every tap and took 4x longer than both together.
+__global__ void __launch_bounds__(256) flow_head_gather_kernel(const float* __restrict__ d, long long pitch,
+                                                               const float* __restrict__ bias, float* __restrict__ coords1,
+                                                               float* __restrict__ flow, int B, int H, int W) {
+  const long long npix = static_cast<long long>(B) * H * W;
+  const long long pix = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (pix >= npix) return;
+  const int xw = static_cast<int>(pix % W);
+  const int yh = static_cast<int>((pix / W) % H);
+  float a0 = __ldg(bias), a1 = __ldg(bias + 1);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int iy = yh + dy, ix = xw + dx;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const float2 v = __ldg(reinterpret_cast<const float2*>(d + (pix + dy * W + dx) * pitch + tap * 2));
+    a0 += v.x;
+    a1 += v.y;
+  }
+  const float2 c = *reinterpret_cast<const float2*>(coords1 + pix * 2);
+  const float cxn = c.x + a0, cyn = c.y + a1;
+  *reinterpret_cast<float2*>(coords1 + pix * 2) = make_float2(cxn, cyn);
+  *reinterpret_cast<float2*>(flow + pix * 2) = make_float2(cxn - static_cast<float>(xw), cyn - static_cast<float>(yh));
+}
+
 // ------------------------------------------------------------------------------------------------
 // Convex upsampling: block = 4 low-res pixels (x) x 8 x 8 sub-pixels
 // ------------------------------------------------------------------------------------------------
@@ -914,6 +943,18 @@ extern "C" int atdn_flow_head_update(const void* x16, int64_t pitch, const float
   const long long npix = static_cast<long long>(batch) * h8 * w8;
   flow_head_update_kernel<<<static_cast<unsigned>((npix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x16), pitch, w, bias, coords1, flow, batch, h8, w8);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int atdn_flow_head_gather(const float* d32, int64_t pitch, const float* bias, float* coords1, float* flow,
+                                     int32_t batch, int32_t h8, int32_t w8, void* stream) {
+  if (int e = require_sm100()) return e;
+  ATDN_REQUIRE(d32 && bias && coords1 && flow, ATDN_ERR_ARG, "atdn_flow_head_gather: null argument");
+  ATDN_REQUIRE(pitch >= 18 && pitch % 2 == 0 && (reinterpret_cast<uintptr_t>(d32) & 7u) == 0, ATDN_ERR_ALIGN, "atdn_flow_head_gather: d32 must be 8-byte aligned with an even pitch >= 18");
+  const long long npix = static_cast<long long>(batch) * h8 * w8;
+  flow_head_gather_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d32, pitch, bias, coords1, flow, batch, h8, w8);
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -162,8 +162,13 @@ class _Packed:
             wq, bq = g("gru.convq" + n)
             self.gru.append((_Conv(torch.cat([wz, wr], 0), torch.cat([bz, br], 0)), _Conv(wq, bq)))
         self.fh1 = _Conv(*g("flow_head.conv1"))
-        w2, b2 = g("flow_head.conv2")                  # 3x3, 256 -> 2: zero-padded to one 32-column MMA tile
-        self.fh2 = _Conv(torch.cat([w2.float(), torch.zeros(30, *w2.shape[1:], device=w2.device)], 0), b2)
+        # flow_head.conv2 (3x3, 256 -> 2) as a 1x1 conv 256 -> 18 (row = tap*2 + co, zero-padded to one 32-column MMA
+        # tile) whose per-tap partial products are summed with their shifts by ops.flow_head_gather
+        w2, b2 = g("flow_head.conv2")
+        w18 = torch.zeros(32, w2.shape[1], 1, 1, dtype=torch.float32, device=w2.device)
+        w18[:18, :, 0, 0] = w2.float().permute(2, 3, 0, 1).reshape(18, w2.shape[1])      # [dy, dx, co, c]
+        self.fh2 = _Conv(w18, None)
+        self.fh2_bias = b2.float().contiguous()
         self.mask0 = _Conv(*g("mask.0"))
         self.mask2 = _Conv(*g("mask.2"))
         self.gamma = sd[u + "aggregator.gamma"].float().contiguous()
@@ -203,6 +208,7 @@ class _Plan:
         self.fpack = f16(b, h8, w8, 16)
         self.f1 = f16(b, h8, w8, 128)
         self.fh = f16(b, h8, w8, 256)
+        self.fh2d = f32(b, h8, w8, 32)      # flow_head.conv2 per-tap partial products [.., tap*2 + co]
         self.mh = f16(b, h8, w8, 256)
         self.mask32 = f32(b * n, 576)
 
@@ -438,9 +444,9 @@ class RAFTGMA(nn.Module):
                      h32=plan.h32, z32=plan.z32)
         c = wts.fh1
         _conv_s1(View(hx, 0, 128), c, View(plan.fh), cout=256, taps=(3, 3), flags=R)
-        c = wts.fh2   # flow_head.conv2 + coords update (network.py:111,116) in the conv epilogue
-        ops.conv_tc(View(plan.fh), c.wp, c.bias, None, cout=2, taps=(3, 3), pad=(1, 1), bn=32, mt=4, epi=L.EPI_FLOW,
-                    h32=plan.coords1, z32=plan.flow)
+        c = wts.fh2   # flow_head.conv2 + coords update (network.py:111,116): per-tap 1x1 products, then the shifted sum
+        ops.conv_tc(View(plan.fh), c.wp, None, View(plan.fh2d), cout=18, taps=(1, 1), pad=(0, 0), bn=32, mt=4, epi=L.EPI_STORE32)
+        ops.flow_head_gather(plan.fh2d, wts.fh2_bias, plan.coords1, plan.flow)
 
 
 class CorrBlock:

@@ -344,6 +344,14 @@ def flow_head_update(x, w, bias, coords1, flow):
 
 
 @_profiled
+def flow_head_gather(d32, bias, coords1, flow):
+    """d32 fp32 [B,H8,W8,pitch] per-tap partial products of flow_head.conv2 -> coords1 += delta, flow = coords1 - grid."""
+    b, h8, w8, pitch = d32.shape
+    L.check(L.load().atdn_flow_head_gather(L.ptr(d32), C.c_int64(pitch), L.ptr(bias), L.ptr(coords1), L.ptr(flow), b, h8, w8,
+                                           L.stream_ptr()), "atdn_flow_head_gather")
+
+
+@_profiled
 def convex_upsample(mask32, flow, flow_up, flow_lo=None):
     b, h8, w8, _ = flow.shape
     L.check(L.load().atdn_convex_upsample(L.ptr(mask32), C.c_int64(mask32.shape[-1]), L.ptr(flow), L.ptr(flow_up),

@@ -199,6 +199,11 @@ int atdn_softmax_rows(const float* s32, int64_t s_pitch, void* p16, int64_t p_pi
  * coords1 += delta; flow = coords1 - coords0 (coords0 = pixel grid).  x16 NHWC [B,H8,W8,256].       */
 int atdn_flow_head_update(const void* x16, int64_t pitch, const float* w, const float* bias,
                           float* coords1, float* flow, int32_t batch, int32_t h8, int32_t w8, void* stream);
+/* The same update from the per-tap partial products of a 256 -> 18 1x1 convolution on atdn_tc_gemm (STORE32):
+ * d32[pix, tap*2 + co] = sum_c w[co, c, tap] x[pix, c], tap = dy*3 + dx;  delta[p, co] = bias[co] + sum over the taps whose
+ * neighbour p + (dy-1, dx-1) lies inside the image of d32[that neighbour, tap*2 + co].  d32: fp32 [B*H8*W8, pitch].        */
+int atdn_flow_head_gather(const float* d32, int64_t pitch, const float* bias, float* coords1, float* flow,
+                          int32_t batch, int32_t h8, int32_t w8, void* stream);
 /* network.py:59-70 convex upsampling: mask fp32 [pix, 576] (already x0.25), flow fp32 [B,H8,W8,2]
  * -> flow_up fp32 NCHW [B,2,8*H8,8*W8]; flow_lo NCHW [B,2,H8,W8] is written when non-NULL.          */
 int atdn_convex_upsample(const float* mask32, int64_t mask_pitch, const float* flow, float* flow_up,

@@ -297,7 +297,7 @@ class RAFTGMA(nn.Module):
         ops.stem_pack(images, sc["xpack"])
         r2 = sc["r2"]
         ops.conv_tc(View(sc["xpack"]), ew.stem.wp, ew.stem.bias, View(r2[0]), cout=64, taps=(4, 1), pad=(2, 0), bn=64, mt=4,
-                    flags=relu, out_hw=(h2, w2))
+                    flags=relu, out_hw=(h2, w2))     # one CTA per tile: measured faster than a CTA pair for this K = 4 x 48
         x = View(r2[0])
         if inst:
             norm_apply(x, x)

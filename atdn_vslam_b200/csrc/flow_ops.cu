@@ -899,6 +899,14 @@ extern "C" int atdn_inorm_stats(const void* x16, int64_t pitch, int32_t batch, i
   return 0;
 }
 
+extern "C" int atdn_inorm_finalize(const float* scratch, int32_t parts, int32_t batch, int32_t c, int32_t hw, float* stats, void* stream) {
+  if (int e = require_sm100()) return e;
+  ATDN_REQUIRE(scratch && stats && parts >= 1 && batch >= 1 && c >= 1 && hw >= 1, ATDN_ERR_ARG, "atdn_inorm_finalize: bad arguments");
+  inorm_finalize_kernel<<<(batch * c + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(scratch, parts, c, hw, batch * c, stats);
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int atdn_inorm_apply(const void* x16, int64_t pitch, const float* stats, const void* resid16, int64_t resid_pitch,
                                 void* y16, int64_t y_pitch, int32_t batch, int32_t hw, int32_t c, int32_t relu, void* stream) {
   if (int e = require_sm100()) return e;

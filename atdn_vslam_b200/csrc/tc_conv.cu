@@ -40,6 +40,7 @@ struct alignas(64) ConvParams {
   int chunks_a, chunks_a2, c_a, c_a2;
   int box_w;                         // halo box width in pixels
   int a_stage_bytes, a_tx_bytes, a_stages, b_stages;
+  int stats_parts;                   // ATDN_F_STATS: partial-sum slots per image (0 = off)
   int out_tma;                       // STORE16: fp16 output boxes staged in shared memory and written by TMA stores
   int b_resident;                    // all (chunk, tap) weight tiles fit shared memory: loaded once per CTA, never recycled
   long long* stamps;                 // optional clock64 stamps of CTA 0 (timing experiments), or null
@@ -269,6 +270,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
       if (stamp && threadIdx.x == 128 && n_tile_iter < 8) p.stamps[16 + n_tile_iter] = clock64();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
       const int h = tc.h0 + rh;
+      constexpr bool kCanStats = EPI == ATDN_EPI_STORE16 && MT == 4 && BN == 64;
+      float st_sum[kCanStats ? 32 : 1], st_sq[kCanStats ? 32 : 1];
+      if constexpr (kCanStats) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { st_sum[i] = 0.0f; st_sq[i] = 0.0f; }
+      }
 #pragma unroll 1
       for (int j = half; j < kChunksPerTile; j += 2) {
         const int s = j / (BN / 32), cc = j % (BN / 32);
@@ -281,6 +288,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
         uint32_t v[32];
         tmem_ld_32x32(trow + s * BN + cc * 32, v);
         tmem_ld_wait();
+        if constexpr (EPI == ATDN_EPI_STORE16 && MT == 4 && BN == 64) {
+          // ATDN_F_STATS: this warp sees channel chunk cc == half in all four sub-tiles: running sums stay in registers
+          if (p.stats_parts > 0 && valid) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.e.bias + tc.n0 + cc * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = __ldg(b4 + i);
+              const float y0 = __uint_as_float(v[4 * i]) + bb.x, y1 = __uint_as_float(v[4 * i + 1]) + bb.y;
+              const float y2 = __uint_as_float(v[4 * i + 2]) + bb.z, y3 = __uint_as_float(v[4 * i + 3]) + bb.w;
+              st_sum[4 * i] += y0; st_sum[4 * i + 1] += y1; st_sum[4 * i + 2] += y2; st_sum[4 * i + 3] += y3;
+              st_sq[4 * i] = fmaf(y0, y0, st_sq[4 * i]); st_sq[4 * i + 1] = fmaf(y1, y1, st_sq[4 * i + 1]);
+              st_sq[4 * i + 2] = fmaf(y2, y2, st_sq[4 * i + 2]); st_sq[4 * i + 3] = fmaf(y3, y3, st_sq[4 * i + 3]);
+            }
+          }
+        }
         if constexpr (EPI == ATDN_EPI_STORE16 || EPI == ATDN_EPI_GRU_Q || EPI == ATDN_EPI_GRU_ZR) {
           // fp16 outputs: out16 (STORE16, GRU_Q: the new hidden state) or r*h (GRU_ZR, accumulator columns 128..255)
           if (p.out_tma && (EPI != ATDN_EPI_GRU_ZR || tc.n0 + cc * 32 >= 128)) {
@@ -305,6 +327,28 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
           }
         }
         epilogue_chunk<EPI>(p.e, valid, pix, tc.n0 + cc * 32, v, sidx);
+      }
+      if constexpr (kCanStats) {
+        if (p.stats_parts > 0) {
+          // transposing butterfly: after the step with stride d, lane bit d selects which half of the channels a lane keeps,
+          // so lane l ends with the sums of channel l over the warp's 32 rows (x 4 sub-tiles)
+#pragma unroll
+          for (int d = 16, n = 16; d >= 1; d >>= 1, n >>= 1) {
+            const bool up = (lane & d) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              const float send0 = up ? st_sum[i] : st_sum[i + n], keep0 = up ? st_sum[i + n] : st_sum[i];
+              const float send1 = up ? st_sq[i] : st_sq[i + n], keep1 = up ? st_sq[i + n] : st_sq[i];
+              st_sum[i] = keep0 + __shfl_xor_sync(0xffffffffu, send0, d);
+              st_sq[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, d);
+            }
+          }
+          const int tile_in_img = (t / p.n_tiles) % (p.tiles_w * p.tiles_h);
+          const int part = (tile_in_img * CL + rank) * 4 + q;
+          float2* dst = reinterpret_cast<float2*>(const_cast<float*>(p.e.aux32)) +
+                        (static_cast<long long>(tc.batch) * p.stats_parts + part) * 64 + half * 32 + lane;
+          *dst = make_float2(st_sum[0], st_sq[0]);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -418,6 +462,12 @@ int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream) {
   p.e.img_w = d->out_w;
   p.e.img_h = d->out_h;
   p.stamps = reinterpret_cast<long long*>(d->lvl[2]);   // timing experiments only (normally null)
+  if (d->flags & ATDN_F_STATS) {
+    ATDN_REQUIRE(d->epi == ATDN_EPI_STORE16 && mt == 4 && bn == 64 && d->n_valid == 64 && d->aux32 && d->bias, ATDN_ERR_ARG,
+                 "atdn_tc_gemm: F_STATS needs STORE16, mt 4, bn 64, 64 output channels, a bias and aux32 (the partial-sum buffer)");
+    ATDN_REQUIRE(!(d->flags & (ATDN_F_RELU | ATDN_F_RESID | ATDN_F_FLOWTAIL | ATDN_F_TANH_LO)), ATDN_ERR_ARG,
+                 "atdn_tc_gemm: F_STATS sums acc + bias (no activation flags)");
+  }
 
   const int box_w = kSubW * mt + d->taps_w - 1, box_h = kSubH + d->taps_h - 1;
   ATDN_REQUIRE(box_w <= 256 && box_h <= 256, ATDN_ERR_UNSUP, "atdn_tc_gemm: halo box %d x %d exceeds the TMA box limit", box_w, box_h);
@@ -453,6 +503,7 @@ int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream) {
   p.tiles_h = ceil_div(d->out_h, kSubH);
   p.n_tiles = ceil_div(d->n_valid, bn);
   p.total_tiles = p.tiles_w * p.tiles_h * p.n_tiles * (int)d->a_dims[3];
+  p.stats_parts = (d->flags & ATDN_F_STATS) ? p.tiles_w * p.tiles_h * cl * 4 : 0;
   p.a_tx_bytes = box_w * box_h * 128;
   p.a_stage_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;
   const int b_bytes = (bn / cl) * 128;

@@ -22,6 +22,7 @@ Data layout in HBM (per batch of B pairs, 1/8-resolution grid H8 x W8, N = H8*W8
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 from torch import nn
@@ -72,6 +73,9 @@ def _fold_bn(w, b, sd, name):
 # 47x154 x 24 pairs / encoder resolutions (profiles/r01b_halo_conv_timings.log)
 _HALO_CFG = {64: (4, 64, True), 96: (2, 96, True), 128: (2, 128, True), 192: (1, 192, True), 256: (1, 256, True),
              576: (1, 192, False)}
+
+
+_NO_FUSED_STATS = os.environ.get("ATDN_NO_FUSED_STATS") == "1"      # A/B switch (bench only)
 
 
 def _halo(cout, taps=(3, 3)):
@@ -229,7 +233,8 @@ class _Plan:
                 "r4": [f16(nimg, h4, w4, 96) for _ in range(4)],
                 "r8": [f16(nimg, h8, w8, 128) for _ in range(4)],
                 "stats": torch.empty(nimg, 128, 2, dtype=torch.float32, device=dev),
-                "scratch": torch.empty(nimg * 296 * 128 * 2, dtype=torch.float32, device=dev),
+                # instance-norm partial sums: stats kernel (<= 296 parts x 128 ch) or conv epilogues (F_STATS, 64 ch)
+                "scratch": torch.empty(nimg * max(296 * 128, ops.stats_parts(h2, w2, True) * 64) * 2, dtype=torch.float32, device=dev),
             }
         return self.enc[nimg]
 
@@ -289,18 +294,24 @@ class RAFTGMA(nn.Module):
         relu = 0 if inst else L.F_RELU
         h2, w2 = plan.h // 2, plan.w // 2
 
-        def norm_apply(x, y, resid=None, act=True):
-            # ~1K pixels per partial sum: 113 / 28 / 8 CTAs per image at 1/2, 1/4, 1/8 resolution (measured optimum)
-            ops.inorm_stats(x, sc["scratch"], max(8, min(296, (x.H * x.W) // 1024)), sc["stats"])
+        def norm_apply(x, y, resid=None, act=True, fused_parts=0):
+            if fused_parts:   # the producing conv left per-tile partial sums in the scratch buffer (F_STATS)
+                ops.inorm_finalize(sc["scratch"], fused_parts, sc["stats"], x.B, x.c, x.H * x.W)
+            else:
+                # ~1K pixels per partial sum: 113 / 28 / 8 CTAs per image at 1/2, 1/4, 1/8 resolution (measured optimum)
+                ops.inorm_stats(x, sc["scratch"], max(8, min(296, (x.H * x.W) // 1024)), sc["stats"])
             ops.inorm_apply(x, sc["stats"], y, resid=resid, relu=act)
 
+        # 64-channel layers at 1/2 resolution (70% of the normalised bytes): statistics come out of the conv epilogue
+        fuse64 = inst and not _NO_FUSED_STATS
+        st64 = {"flags": L.F_STATS, "aux32": sc["scratch"]} if fuse64 else {"flags": 0}
         ops.stem_pack(images, sc["xpack"])
         r2 = sc["r2"]
         ops.conv_tc(View(sc["xpack"]), ew.stem.wp, ew.stem.bias, View(r2[0]), cout=64, taps=(4, 1), pad=(2, 0), bn=64, mt=4,
-                    flags=relu, out_hw=(h2, w2))     # one CTA per tile: measured faster than a CTA pair for this K = 4 x 48
+                    flags=relu | st64["flags"], aux32=st64.get("aux32"), out_hw=(h2, w2))   # single CTAs: measured faster than pairs for K = 4 x 48
         x = View(r2[0])
         if inst:
-            norm_apply(x, x)
+            norm_apply(x, x, fused_parts=ops.stats_parts(h2, w2, False) if fuse64 else 0)
         pools = {64: sc["r2"], 96: sc["r4"], 128: sc["r8"]}
         for blk in ew.blocks:
             planes, st = blk["planes"], blk["stride"]
@@ -309,12 +320,15 @@ class RAFTGMA(nn.Module):
             m_tiles = n * math.ceil(t1.H / 8) * math.ceil(t1.W / 16)
             bn = _pick_bn(planes, m_tiles)
             c1, c2 = blk["conv1"], blk["conv2"]
+            f64 = fuse64 and planes == 64
+            kw64 = {"aux32": sc["scratch"]} if f64 else {}
+            parts64 = ops.stats_parts(t1.H, t1.W, _HALO_CFG[64][2]) if f64 else 0
             if st == 1:
-                _conv_s1(x, c1, t1, cout=planes, taps=(3, 3), flags=relu)
+                _conv_s1(x, c1, t1, cout=planes, taps=(3, 3), flags=relu | (L.F_STATS if f64 else 0), **kw64)
             else:
                 ops.conv_tc(x, c1.wp, c1.bias, t1, cout=planes, taps=(3, 3), pad=(1, 1), stride=st, bn=bn, flags=relu)
             if inst:
-                norm_apply(t1, t1)
+                norm_apply(t1, t1, fused_parts=parts64 if st == 1 else 0)
             if st != 1:
                 dn = blk["down"]
                 ops.conv_tc(x, dn.wp, dn.bias, t3, cout=planes, taps=(1, 1), pad=(0, 0), stride=st, bn=bn)
@@ -324,8 +338,8 @@ class RAFTGMA(nn.Module):
             else:
                 skip = x
             if inst:
-                _conv_s1(t1, c2, t2, cout=planes, taps=(3, 3))
-                norm_apply(t2, t2, resid=skip)
+                _conv_s1(t1, c2, t2, cout=planes, taps=(3, 3), flags=L.F_STATS if f64 else 0, **kw64)
+                norm_apply(t2, t2, resid=skip, fused_parts=parts64)
             else:   # y = relu(bn(conv)); out = relu(skip + y) fused in the epilogue
                 _conv_s1(t1, c2, t2, cout=planes, taps=(3, 3), flags=L.F_RELU | L.F_RESID, resid=skip)
             x = t2

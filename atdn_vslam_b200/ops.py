@@ -307,6 +307,17 @@ def inorm_stats(x, scratch, parts, stats):
                                       L.ptr(stats), L.stream_ptr()), "atdn_inorm_stats", 2)
 
 
+def stats_parts(h, w, pair):
+    """Partial-sum slots per image written by a conv launched with F_STATS (halo kernel, mt 4, bn 64)."""
+    cl = 2 if pair else 1
+    return ((h + 15) // 16) * ((w + 32 * cl - 1) // (32 * cl)) * cl * 4
+
+
+@_profiled
+def inorm_finalize(scratch, parts, stats, batch, c, hw):
+    L.check(L.load().atdn_inorm_finalize(L.ptr(scratch), parts, batch, c, hw, L.ptr(stats), L.stream_ptr()), "atdn_inorm_finalize")
+
+
 @_profiled
 def inorm_apply(x, stats, y, resid=None, relu=True):
     L.check(L.load().atdn_inorm_apply(x.ptr(), C.c_int64(x.pitch), L.ptr(stats),

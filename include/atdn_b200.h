@@ -78,7 +78,12 @@ enum {
   ATDN_F_TANH_LO   = 8,  /* STORE16: n < 128 -> tanh (also written to h32), n >= 128 -> relu (network.py:95-97) */
   ATDN_F_B_BATCHED = 16, /* B operand has a batch dimension (attention GEMMs, corr volume)               */
   ATDN_F_A_SHARED  = 32, /* ROWS A is shared by all batches (weights as the A operand: transposed output); batch = b_dims[3] */
-  ATDN_F_PAIR      = 64  /* CTA-pair kernel (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages bn/2 B rows; bn up to 256 */
+  ATDN_F_PAIR      = 64, /* CTA-pair kernel (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages bn/2 B rows; bn up to 256 */
+  ATDN_F_STATS     = 128 /* STORE16 on the halo kernel with mt = 4, bn = 64 (n_valid = 64): per-channel partial sums of
+                            (acc + bias) and its square over the in-image pixels each epilogue warp sees in one tile go to
+                            aux32 as [batch, parts, 64, 2] fp32, parts = ceil(H/16) * ceil(W/(32*cl)) * cl * 4 (cl = 2 with
+                            ATDN_F_PAIR): the instance-norm statistics pass without re-reading the tensor; reduce them with
+                            atdn_inorm_finalize                                                                         */
 };
 
 typedef struct atdn_tc_desc {
@@ -188,6 +193,9 @@ int atdn_flow_pack(const float* flow, void* x16, int32_t batch, int32_t h8, int3
  * into stats fp32 [B, C, 2]; two-stage, deterministic.  scratch: fp32 [B * parts * C * 2].          */
 int atdn_inorm_stats(const void* x16, int64_t pitch, int32_t batch, int32_t hw, int32_t c,
                      float* scratch, int32_t parts, float* stats, void* stream);
+/* second stage alone: scratch fp32 [batch, parts, c, 2] partial (sum, sum of squares) -> stats [batch, c, 2] = (mean, rstd);
+ * the partials may come from atdn_tc_gemm epilogues (ATDN_F_STATS).  Fixed reduction order: deterministic.          */
+int atdn_inorm_finalize(const float* scratch, int32_t parts, int32_t batch, int32_t c, int32_t hw, float* stats, void* stream);
 /* y = relu((x - mean) * rstd); if resid16: y = relu(resid16 + y) (extractor.py:47-55).  In place ok. */
 int atdn_inorm_apply(const void* x16, int64_t pitch, const float* stats, const void* resid16, int64_t resid_pitch,
                      void* y16, int64_t y_pitch, int32_t batch, int32_t hw, int32_t c, int32_t relu, void* stream);

@@ -8,6 +8,7 @@
 // other's MMA phase.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "tc_ptx.cuh"
@@ -22,8 +23,9 @@ constexpr int kABytes = kTileM * kChunkK * 2;  // 16 KiB
 constexpr int kThreads = 192;
 
 struct alignas(64) TcParams {
-  CUtensorMap tmA, tmA2, tmB;
+  CUtensorMap tmA, tmA2, tmB, tmOut;
   int a_mode, tiles_w, out_h, out_w, m_rows;
+  int out_tma;            // STORE16 (single-CTA kernel): fp16 output boxes staged in shared memory, written by TMA stores
   int taps_w, pad_h, pad_w, stride;
   int chunks_a, chunks_a2, c_a, c_a2, num_k_iters;
   int b_batched, a_shared;
@@ -246,12 +248,37 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     if constexpr (EPI == ATDN_EPI_CORR) {
       epilogue_corr(p, valid, pix, bh0, bw0, trow);
     } else {
+      int n_out = 0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(trow + c * 32, v);
         tmem_ld_wait();
+        if constexpr (EPI == ATDN_EPI_STORE16) {
+          // Same staging as the halo kernel (tc_conv.cu): the warp's [32 rows][32 channels] fp16 chunk is one TMA box
+          // (PATCH: 2 image rows x 16 pixels; ROWS: 32 GEMM rows).  All MMAs of this CTA have completed, so the
+          // operand ring at the start of shared memory is free to hold the 4 x 2 staging slots.
+          if (p.out_tma && n0 + c * 32 < p.e.n_valid) {
+            uint8_t* slot = smem + (warp * 2 + (n_out & 1)) * 2048;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            epilogue_chunk<EPI>(p.e, valid, pix, n0 + c * 32, v, -1, smem_u32(slot) + lane * 64, static_cast<uint32_t>(lane >> 1) & 3u);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.a_mode == ATDN_MODE_PATCH) tma_store_4d(&p.tmOut, slot, n0 + c * 32, w0, h0 + warp * 2, batch);
+              else tma_store_4d(&p.tmOut, slot, n0 + c * 32, m0 + warp * 32, 0, batch);
+              bulk_commit();
+            }
+            ++n_out;
+            continue;
+          }
+        }
         epilogue_chunk<EPI>(p.e, valid, pix, n0 + c * 32, v);
+      }
+      if (n_out > 0) {
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
       }
     }
   }
@@ -593,6 +620,22 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
     if (int e = make_map_f16(&p.tmB, d->b, d->b_dims, d->b_strides, box, ones, "B")) return e;
   }
   grid.y = ceil_div(d->n_valid, d->bn);
+  {
+    const char* off = getenv("ATDN_NO_OUT_TMA");
+    p.out_tma = d->epi == ATDN_EPI_STORE16 && !pair && d->out != nullptr && !(off && off[0] == '1') && aligned16(d->out) &&
+                d->out_pitch % 8 == 0 && d->out_ch_off % 8 == 0;
+    if (p.out_tma) {
+      const bool patch = d->a_mode == ATDN_MODE_PATCH;
+      const int64_t nb = (d->flags & ATDN_F_A_SHARED) ? d->b_dims[3] : d->a_dims[3];
+      const int64_t rows = patch ? 0 : d->a_dims[1];
+      const int64_t odims[4] = {d->n_valid, patch ? d->out_w : rows, patch ? d->out_h : 1, nb};
+      const int64_t ostr[3] = {d->out_pitch, patch ? (int64_t)d->out_w * d->out_pitch : rows * d->out_pitch,
+                               patch ? (int64_t)d->out_h * d->out_w * d->out_pitch : rows * d->out_pitch};
+      const uint32_t obox[4] = {32, patch ? 16u : 32u, patch ? 2u : 1u, 1};
+      const __half* obase = static_cast<const __half*>(d->out) + d->out_ch_off;
+      if (int e = make_map(&p.tmOut, 2, CU_TENSOR_MAP_SWIZZLE_64B, obase, odims, ostr, obox, ones, "GEMM output")) return e;
+    }
+  }
   // vector-store alignment of the epilogue
   ATDN_REQUIRE(d->out_pitch % 8 == 0 && d->out_ch_off % 8 == 0, ATDN_ERR_ALIGN, "atdn_tc_gemm: out_pitch/out_ch_off must be multiples of 8");
   switch (d->epi) {

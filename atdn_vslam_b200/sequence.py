@@ -117,9 +117,12 @@ class OdometryPipeline:
             self._staging = [torch.empty((nb,) + tuple(host_frames.shape[1:]), dtype=host_frames.dtype, device=dev) for _ in range(2)]
             self._staging_key = key
         main = torch.cuda.current_stream(dev)
+        # the first batch cannot overlap its own host->device copy: keep it short (a quarter batch), so that the
+        # start-up bubble is the copy of ~batch_pairs/4 frames instead of a whole batch
         ranges, s = [], 0
+        first = max(1, self.batch_pairs // 4) if t - 1 > self.batch_pairs else self.batch_pairs
         while s < t - 1:
-            e = min(t - 1, s + self.batch_pairs)
+            e = min(t - 1, s + (first if s == 0 else self.batch_pairs))
             ranges.append((s, e))
             s = e
         ready = [torch.cuda.Event() for _ in ranges]

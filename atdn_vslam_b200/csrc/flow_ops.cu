@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_kernel(LookupParams
 //   * output: 324 fp32 results staged in shared memory (aliasing the windows), written as 16-byte fp16 vectors.
 // ------------------------------------------------------------------------------------------------
 struct LookupHalfParams {
-  const __half* lvl[4];
-  int pitch[4];
+  const __half* lvl[4];     // tiled: level l = [query][tile][(8 >> l) x (32 >> l)], tile = (y >> (3-l)) * tiles_w + (x >> (5-l))
+  int tiles, tiles_w;       // ceil(h0 / 8) * tiles_w, ceil(w0 / 32): the same tile grid at every level
   int h0, w0;
 };
 
@@ -251,14 +251,16 @@ __global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_half_kernel(const _
     lk_origin(cxy.x, l, W, ix, fdummy);
     lk_origin(cxy.y, l, H, iy, fdummy);
     const int x = (ix & ~3) + 4 * s, y = iy + r;
-    const int pitch = k < 4 ? p.pitch[k] : p.pitch[l];
     const __half* lv = k < 4 ? p.lvl[k] : p.lvl[l];
     raw[k] = make_uint2(0u, 0u);
     dsto[k] = l * kLkLevelStride + r * 16 + 4 * s;
     xs[k] = x;
     ws[k] = W;
-    if (y >= 0 && y < H && x >= 0 && x < W)          // pitch is a multiple of 4 and >= W: the whole segment is inside the row
-      raw[k] = __ldg(reinterpret_cast<const uint2*>(lv + (q * H + y) * static_cast<long long>(pitch) + x));
+    if (y >= 0 && y < H && x >= 0 && x < W) {        // a 4-texel segment never straddles a tile (tile widths are multiples of 4)
+      const int tile = (y >> (3 - l)) * p.tiles_w + (x >> (5 - l));
+      const int within = ((y & ((8 >> l) - 1)) << (5 - l)) + (x & ((32 >> l) - 1));
+      raw[k] = __ldg(reinterpret_cast<const uint2*>(lv + ((q * p.tiles + tile) << (8 - 2 * l)) + within));
+    }
   }
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_half_kernel(const _
     const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw[k].y));
     float4 t = make_float4(lo.x, lo.y, hi.x, hi.y);
     const int x = xs[k], W = ws[k];
-    if (x + 3 >= W) {                                 // the row pad holds whatever the pyramid kernel's boxes left there
+    if (x + 3 >= W) {                                 // texels past the map edge inside a tile hold whatever the pooling left there
       if (x + 1 >= W) t.y = 0.0f;
       if (x + 2 >= W) t.z = 0.0f;
       t.w = 0.0f;
@@ -834,7 +836,7 @@ extern "C" int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitc
   ATDN_REQUIRE(!out32 || aligned16(out32), ATDN_ERR_ALIGN, "atdn_corr_lookup: out32 must be 16-byte aligned");
   int w = w8;
   for (int l = 0; l < 4; ++l) {
-    ATDN_REQUIRE(lvl[l] != nullptr && lvl_pitch[l] >= w, ATDN_ERR_ARG, "atdn_corr_lookup: level %d", l);
+    ATDN_REQUIRE(lvl[l] != nullptr && (half_levels || lvl_pitch[l] >= w), ATDN_ERR_ARG, "atdn_corr_lookup: level %d", l);
     ATDN_REQUIRE(lvl_pitch[l] % 4 == 0 && aligned16(lvl[l]), ATDN_ERR_ALIGN, "atdn_corr_lookup: level %d must be 16-byte aligned with a pitch that is a multiple of 4", l);
     w /= 2;
   }
@@ -842,9 +844,11 @@ extern "C" int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitc
   if (half_levels) {
     LookupHalfParams p;
     for (int l = 0; l < 4; ++l) {
+      ATDN_REQUIRE(lvl_pitch[l] == (256 >> (2 * l)), ATDN_ERR_ARG, "atdn_corr_lookup: tiled level %d has %d elements per tile, expected %d", l, lvl_pitch[l], 256 >> (2 * l));
       p.lvl[l] = static_cast<const __half*>(lvl[l]);
-      p.pitch[l] = lvl_pitch[l];
     }
+    p.tiles_w = (w8 + 31) / 32;
+    p.tiles = ((h8 + 7) / 8) * p.tiles_w;
     p.h0 = h8;
     p.w0 = w8;
     corr_lookup_half_kernel<<<grid, kLkWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(p, coords, static_cast<__half*>(out16), out_pitch, out32, nq);

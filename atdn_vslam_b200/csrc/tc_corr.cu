@@ -147,12 +147,10 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
 
     // staging slot ring: a slot is reused once the bulk store issued two stores ago has read it
     auto acquire = [&]() -> int {
-      // fp16 boxes are at most 2 KiB: the warp's 8 KiB of staging hold a ring of FOUR slots (three stores may still be
-      // reading shared memory).  Measured: no faster than two slots -- the epilogue is bound by its serial
-      // tcgen05.ld -> scale/convert -> st.shared -> fence -> store chain per row, not by slot reuse.
-      if (lane == 0) bulk_wait_read<HALF ? 3 : 1>();
+      // (a ring of four 2-KiB slots was measured: no faster -- slot reuse is not what the epilogue waits for)
+      if (lane == 0) bulk_wait_read<1>();
       __syncwarp();
-      return HALF ? (nstore & 3) * (kCorrSlotBytes / 2) : (nstore & 1) * kCorrSlotBytes;
+      return (nstore & 1) * kCorrSlotBytes;
     };
     auto commit = [&](const CUtensorMap* m, int off, int c0, int c1) {
       fence_proxy_async_smem();
@@ -169,6 +167,86 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
       mbar_wait(&acc_full[g], pf);
       pf ^= 1u;
       tcgen05_fence_after();
+      if constexpr (HALF) {
+        // fp16 pyramid in the TILED layout [query][tile][(8 >> l) x (32 >> l)]: everything this tile contributes to one
+        // query's maps is contiguous (512 / 128 / 32 / 8 bytes at levels 0..3), so level 0 leaves as four boxes of
+        // 128-byte rows (two tile rows each) and levels 1, 2 as one box each: 6 TMA stores per tile instead of 14, with
+        // runs twice as long (the row-major layout wrote 64-byte pieces 320 bytes apart: 3.1 TB/s of a 7.5 TB/s write peak)
+        float hs1[16], hs2[8], hs3[4];
+        uint32_t prev[16];                 // packed even level-0 row, stored together with the odd row below it
+        uint32_t l1p[4][8], l2p[2][4];     // packed level-1 / level-2 rows of this tile
+        uint2 l3p = make_uint2(0u, 0u);
+#pragma unroll
+        for (int hl = 0; hl < 8; ++hl) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + hl * 32, v);
+          tmem_ld_wait();
+          float c[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) c[j] = p.alpha * __uint_as_float(v[j]);
+          if ((hl & 1) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              prev[j] = pack_half2(c[2 * j], c[2 * j + 1]);
+              hs1[j] = c[2 * j] + c[2 * j + 1];
+            }
+          } else {
+            if (!(p.dbg & 2)) {
+              const int off = acquire();
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4),
+                             make_uint4(prev[4 * ch], prev[4 * ch + 1], prev[4 * ch + 2], prev[4 * ch + 3]));
+                st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(ch + 4) ^ sw) << 4),
+                             make_uint4(pack_half2(c[8 * ch], c[8 * ch + 1]), pack_half2(c[8 * ch + 2], c[8 * ch + 3]),
+                                        pack_half2(c[8 * ch + 4], c[8 * ch + 5]), pack_half2(c[8 * ch + 6], c[8 * ch + 7])));
+              }
+              commit(&p.tmL[0], off, (hl - 1) * 32, t);
+            }
+            float l1[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) l1[j] = (hs1[j] + (c[2 * j] + c[2 * j + 1])) * 0.25f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) l1p[hl >> 1][j] = pack_half2(l1[2 * j], l1[2 * j + 1]);
+            if ((hl & 3) == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) hs2[j] = l1[2 * j] + l1[2 * j + 1];
+            } else {
+              float l2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) l2[j] = (hs2[j] + (l1[2 * j] + l1[2 * j + 1])) * 0.25f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) l2p[hl >> 2][j] = pack_half2(l2[2 * j], l2[2 * j + 1]);
+              if (hl == 3) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hs3[j] = l2[2 * j] + l2[2 * j + 1];
+              } else {
+                l3p = make_uint2(pack_half2((hs3[0] + (l2[0] + l2[1])) * 0.25f, (hs3[1] + (l2[2] + l2[3])) * 0.25f),
+                                 pack_half2((hs3[2] + (l2[4] + l2[5])) * 0.25f, (hs3[3] + (l2[6] + l2[7])) * 0.25f));
+              }
+            }
+          }
+        }
+        if (!(p.dbg & 3)) {
+          int off = acquire();               // level 1: 4 rows x 32 bytes = one 128-byte row per query, 128B swizzle
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+              st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(2 * r + ch) ^ sw) << 4),
+                           make_uint4(l1p[r][4 * ch], l1p[r][4 * ch + 1], l1p[r][4 * ch + 2], l1p[r][4 * ch + 3]));
+          commit(&p.tmL[1], off, 0, t);
+          off = acquire();                   // level 2: 2 rows x 16 bytes = 32 bytes per query, 32B swizzle
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+            st_shared_v4(st_u32 + off + lane * 32 + ((static_cast<uint32_t>(r) ^ (static_cast<uint32_t>(lane >> 2) & 1u)) << 4),
+                         make_uint4(l2p[r][0], l2p[r][1], l2p[r][2], l2p[r][3]));
+          commit(&p.tmL[2], off, 0, t);
+          // level 3: 4 fp16 = 8 bytes per query and tile, below the 16-byte TMA granularity: stored by the thread
+          if (qrow + lane < p.n)
+            *reinterpret_cast<uint2*>(p.l3 + ((static_cast<long long>(batch) * p.n + qrow + lane) * T + t) * 4) = l3p;
+        }
+      } else {
       float hs1[16];   // horizontal pair sums of the previous (even) level-0 row
       float hs2[8];    // ... of the previous (even) level-1 row
       float hs3[4];    // ... of the previous (even) level-2 row
@@ -292,6 +370,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
           }
         }
       }
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[g]);
@@ -353,21 +432,32 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
     const uint32_t box[4] = {64, 32, 8, 1};
     if (int e = make_map_f16(&p.tmB, fmap2, dims, str, box, ones, "fmap2")) return e;
   }
-  int hl = h8, wl = w8;
-  for (int l = 0; l < 4; ++l) {
-    const bool half = l < half_levels;
-    ATDN_REQUIRE(lvl[l] != nullptr && lvl_pitch[l] % (half ? 8 : 4) == 0 && lvl_pitch[l] >= wl, ATDN_ERR_ALIGN, "atdn_corr_pyramid: level %d pitch %d", l, lvl_pitch[l]);
-    const int64_t dims[4] = {wl, hl, n, batch};
-    const int64_t str[3] = {lvl_pitch[l], (int64_t)hl * lvl_pitch[l], (int64_t)n * hl * lvl_pitch[l]};
-    const uint32_t box[4] = {32u >> l, 1, 32, 1};
-    // staging layouts of the epilogue: fp32 level 0 = 128-byte rows (128B swizzle); fp16 level 0 / 1 = 64 / 32-byte rows
-    // (64B / 32B swizzle), fp16 level 2 = 16-byte rows; everything else is stored unswizzled
-    const CUtensorMapSwizzle swz = half ? (l == 0 ? CU_TENSOR_MAP_SWIZZLE_64B : l == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)
-                                        : (l == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
-    if (half && l == 3) break;                     // 8-byte rows: stored without TMA
-    if (int e = make_map(&p.tmL[l], half ? 2 : 4, swz, lvl[l], dims, str, box, ones, "pyramid level")) return e;
-    hl /= 2;
-    wl /= 2;
+  if (half_levels) {
+    // tiled fp16 layout: level l = [batch * n, tiles, (8 >> l) * (32 >> l)], tiles = ceil(h8 / 8) * ceil(w8 / 32)
+    for (int l = 0; l < 4; ++l) {
+      const int el = 256 >> (2 * l);
+      ATDN_REQUIRE(lvl[l] != nullptr && aligned16(lvl[l]) && lvl_pitch[l] == el, ATDN_ERR_ALIGN,
+                   "atdn_corr_pyramid: tiled level %d needs a 16-byte aligned buffer with %d elements per tile (got %d)", l, el, lvl_pitch[l]);
+      if (l == 3) break;                             // 8-byte tiles: stored without TMA
+      const int64_t dims[4] = {el, p.tiles, n, batch};
+      const int64_t str[3] = {el, (int64_t)p.tiles * el, (int64_t)n * p.tiles * el};
+      const uint32_t box[4] = {l == 2 ? 16u : 64u, 1, 32, 1};
+      if (int e = make_map(&p.tmL[l], 2, l == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B, lvl[l], dims, str, box, ones,
+                           "pyramid level")) return e;
+    }
+  } else {
+    int hl = h8, wl = w8;
+    for (int l = 0; l < 4; ++l) {
+      ATDN_REQUIRE(lvl[l] != nullptr && lvl_pitch[l] % 4 == 0 && lvl_pitch[l] >= wl, ATDN_ERR_ALIGN, "atdn_corr_pyramid: level %d pitch %d", l, lvl_pitch[l]);
+      const int64_t dims[4] = {wl, hl, n, batch};
+      const int64_t str[3] = {lvl_pitch[l], (int64_t)hl * lvl_pitch[l], (int64_t)n * hl * lvl_pitch[l]};
+      const uint32_t box[4] = {32u >> l, 1, 32, 1};
+      // fp32 staging of the epilogue: level 0 = 128-byte rows (128B swizzle), the pooled levels are stored unswizzled
+      if (int e = make_map(&p.tmL[l], 4, l == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, lvl[l], dims, str, box, ones,
+                           "pyramid level")) return e;
+      hl /= 2;
+      wl /= 2;
+    }
   }
   static bool configured = false;
   if (!configured) {

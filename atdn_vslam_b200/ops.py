@@ -192,11 +192,27 @@ def pyramid_shapes(h8, w8):
 
 
 def alloc_pyramid(batch, h8, w8, device, half_levels=0):
-    """The four pyramid levels; ``half_levels=4`` stores them as fp16 (the sequence pipeline's layout), 0 keeps the
-    reference's fp32 pyramid (``CorrBlock`` drop-in)."""
+    """The four pyramid levels.  ``half_levels=0``: the reference's fp32 pyramid, row-major [B*N, H_l, pitch_l]
+    (``CorrBlock`` drop-in).  ``half_levels=4`` (the sequence pipeline): fp16 in the TILED layout of
+    ``atdn_corr_pyramid``: level l = [B*N, tiles, (8 >> l) * (32 >> l)], tiles = ceil(h8/8) * ceil(w8/32) -- what one
+    8 x 32 target tile contributes to a query's map is contiguous, so the kernel's stores are long runs."""
     n = h8 * w8
-    return [torch.empty(batch * n, h, p, dtype=torch.float16 if l < half_levels else torch.float32, device=device)
-            for l, (h, w, p) in enumerate(pyramid_shapes(h8, w8))]
+    if half_levels:
+        assert half_levels == 4
+        tiles = ((h8 + 7) // 8) * ((w8 + 31) // 32)
+        return [torch.empty(batch * n, tiles, 256 >> (2 * l), dtype=torch.float16, device=device) for l in range(4)]
+    return [torch.empty(batch * n, h, p, dtype=torch.float32, device=device) for (h, w, p) in pyramid_shapes(h8, w8)]
+
+
+def pyramid_untile(levels, h8, w8):
+    """Tiled fp16 pyramid -> list of row-major fp32 [B*N, H_l, W_l] tensors (tests / inspection)."""
+    th, tw = (h8 + 7) // 8, (w8 + 31) // 32
+    out = []
+    for l, t in enumerate(levels):
+        rh, rw = 8 >> l, 32 >> l
+        x = t.float().view(t.shape[0], th, tw, rh, rw).permute(0, 1, 3, 2, 4).reshape(t.shape[0], th * rh, tw * rw)
+        out.append(x[:, : h8 >> l, : w8 >> l].contiguous())
+    return out
 
 
 def _half_levels(levels):

@@ -142,8 +142,10 @@ int atdn_tc_gemm(const atdn_tc_desc* desc, void* stream);
  * and written with TMA stores (full 128-byte runs per query row); columns [W_l, ceil4(W_l)) of a row may be
  * overwritten with pad values (16-byte store granularity).
  * half_levels = 0: all four levels fp32 (the reference's corr_pyramid, bit-for-bit layout of its values).
- * half_levels = 4: all levels are stored as fp16 (pitch a multiple of 8), each pooled from the un-rounded fp32
- *   values of the level below and rounded once.  The kernel is bound by its HBM stores, so this halves its time
+ * half_levels = 4: all levels are stored as fp16 in a TILED layout, lvl[l] = [batch*n, tiles, (8>>l)*(32>>l)] with
+ *   tiles = ceil(h8/8)*ceil(w8/32) and texel (y, x) of level l at tile (y >> (3-l))*ceil(w8/32) + (x >> (5-l)),
+ *   offset (y & ((8>>l)-1))*(32>>l) + (x & ((32>>l)-1)); lvl_pitch[l] must be the tile size (256, 64, 16, 4).  Each
+ *   level is pooled from the un-rounded fp32 values of the level below and rounded once.  The kernel is bound by its HBM stores, so this halves its time
  *   (and the lookup's read traffic); the end-to-end flow moves by 8e-4 px mean
  *   (tools/fp16_pyramid_sensitivity.py), inside the 1e-2 px bar.
  * ---------------------------------------------------------------------------------------------- */

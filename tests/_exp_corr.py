@@ -1,3 +1,5 @@
+"""Experiment (not a test): where does the streaming corr-pyramid kernel spend its time?  ATDN_CORR_DBG switches:
+1 = no level 1..3 stores, 2 = no stores at all (MMA + operand feed + epilogue arithmetic only)."""
 import os, sys, torch
 sys.path.insert(0, '/root/repo')
 from atdn_vslam_b200 import ops
@@ -15,12 +17,10 @@ ms = timeit(lambda: y.copy_(x)); print(f"copy 8GB: {ms:.3f} ms {2*x.numel()*4/ms
 del x, y
 b, h8, w8 = 27, 47, 154
 v1 = ops.View(torch.randn(b, h8, w8, 256).half().cuda()); v2 = ops.View(torch.randn(b, h8, w8, 256).half().cuda())
-lv = ops.alloc_pyramid(b, h8, w8, "cuda")
-ref = None
-for dbg in (0, 1, 2, 4, 5):
-    os.environ["ATDN_CORR_DBG"] = str(dbg)
-    ms = timeit(lambda: ops.corr_pyramid_build(v1, v2, lv))
-    extra = ""
-    if dbg == 0: ref = lv[0].clone()
-    if dbg == 4: extra = f" L0 equal to TMA path: {torch.equal(ref[:, :, :154], lv[0][:, :, :154])}"
-    print(f"corr dbg={dbg}: {ms:.3f} ms{extra}")
+for half in (4, 0):
+    lv = ops.alloc_pyramid(b, h8, w8, "cuda", half_levels=half)
+    for dbg in (0, 1, 2):
+        os.environ["ATDN_CORR_DBG"] = str(dbg)
+        ms = timeit(lambda: ops.corr_pyramid_build(v1, v2, lv))
+        print(f"corr half_levels={half} dbg={dbg}: {ms:.3f} ms")
+os.environ.pop("ATDN_CORR_DBG")

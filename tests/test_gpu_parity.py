@@ -130,9 +130,9 @@ def test_corrblock_dropin_api():
 
 @pytest.mark.parametrize("h8,w8,batch", [(47, 154, 1), (23, 39, 2), (16, 20, 3)])
 def test_half_level_pyramid_and_lookup(h8, w8, batch):
-    """half_levels=4 (the sequence pipeline's layout): every level is the fp32 pyramid (pooled from un-rounded
-    values) rounded ONCE to fp16; the separable lookup on it equals the oracle lookup on the same rounded pyramid
-    to fp32 round-off, including integer coordinates (iteration 0) and windows hanging over every border."""
+    """half_levels=4 (the sequence pipeline's tiled fp16 layout): every level is the fp32 pyramid (pooled from
+    un-rounded values) rounded ONCE to fp16; the separable lookup on it equals the oracle lookup on the same rounded
+    pyramid to fp32 round-off, including integer coordinates (iteration 0) and windows hanging over every border."""
     from atdn_vslam_b200 import ops
     from oracle import gma_oracle
     g = torch.Generator().manual_seed(h8 * 1000 + w8)
@@ -145,8 +145,8 @@ def test_half_level_pyramid_and_lookup(h8, w8, batch):
     ops.corr_pyramid_build(ops.View(f1.permute(0, 2, 3, 1).contiguous().cuda()), ops.View(f2.permute(0, 2, 3, 1).contiguous().cuda()), lv)
     assert all(t.dtype == torch.float16 for t in lv)
     rounded = []
-    for t, r in zip(lv, pyr):
-        got = t[:, :, : r.shape[-1]].float().cpu().reshape(r.shape)
+    for t, r in zip(ops.pyramid_untile(lv, h8, w8), pyr):
+        got = t.cpu().reshape(r.shape)
         assert not torch.isnan(got).any()
         # one fp16 rounding of a value that matches the fp32 oracle to 1e-5: at most 1 fp16 ulp apart (rounding ties)
         want = r.half().float()

@@ -156,3 +156,43 @@ def test_feature_gather_world2_gloo():
         assert p.exitcode == 0
     for _, vals in res:
         assert vals == [float(i) for i in range(7)]
+
+
+def test_tiled_state_layout_matches_the_header_formula():
+    """ops.state_from_nhwc / state_to_nhwc implement the index formula documented for atdn_tc_desc.h32 / z32."""
+    import torch
+    from atdn_vslam_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    b, h, w = 2, 37, 45
+    x = torch.randn(b, h, w, 128, generator=g)
+    t = ops.state_from_nhwc(x)
+    th_n, tw_n = (h + 15) // 16, (w + 7) // 8
+    assert tuple(t.shape) == (b, th_n, tw_n, 4, 32, 32, 4) and t.numel() == b * th_n * 16 * tw_n * 8 * 128
+    flat = t.flatten()
+    for (bb, hh, ww, c) in [(0, 0, 0, 0), (1, 20, 13, 77), (0, 36, 44, 127), (1, 15, 8, 3), (0, 16, 7, 64)]:
+        r = ((hh & 15) << 3) | (ww & 7)
+        idx = ((((bb * th_n + (hh >> 4)) * tw_n + (ww >> 3)) * 4 + (r >> 5)) * 32 + c // 4) * 128 + (r & 31) * 4 + c % 4
+        assert flat[idx] == x[bb, hh, ww, c]
+    assert torch.equal(ops.state_to_nhwc(t, h, w), x)
+
+
+def test_tiled_pyramid_layout_matches_the_header_formula():
+    """ops.pyramid_untile inverts the tile / offset formula documented for atdn_corr_pyramid (half_levels = 4)."""
+    import torch
+    from atdn_vslam_b200 import ops
+    h8, w8 = 23, 39
+    th, tw = (h8 + 7) // 8, (w8 + 31) // 32
+    levels, refs = [], []
+    for l in range(4):
+        H, W, rh, rw = h8 >> l, w8 >> l, 8 >> l, 32 >> l
+        ref = (torch.arange(2 * H * W) % 2048).float().view(2, H, W)
+        t = torch.full((2, th * tw, rh * rw), -1.0)
+        for y in range(H):
+            for x in range(W):
+                tile = (y >> (3 - l)) * tw + (x >> (5 - l))
+                t[:, tile, (y & (rh - 1)) * rw + (x & (rw - 1))] = ref[:, y, x]
+        levels.append(t.half())
+        refs.append(ref)
+    for got, ref in zip(ops.pyramid_untile(levels, h8, w8), refs):
+        assert torch.equal(got, ref)
+    assert ops.stats_parts(188, 616, True) == 12 * 10 * 2 * 4 and ops.stats_parts(188, 616, False) == 12 * 20 * 4

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libatdn_b200.so")
 
 MODE_ROWS, MODE_PATCH = 0, 1
 EPI_STORE16, EPI_STORE32, EPI_CORR, EPI_GRU_ZR, EPI_GRU_Q, EPI_PV, EPI_FLOW = range(7)
-F_RELU, F_RESID, F_FLOWTAIL, F_TANH_LO, F_B_BATCHED, F_A_SHARED, F_PAIR, F_STATS = 1, 2, 4, 8, 16, 32, 64, 128
+F_RELU, F_RESID, F_FLOWTAIL, F_TANH_LO, F_B_BATCHED, F_A_SHARED, F_PAIR, F_STATS, F_TILED32 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 EXPORTS = (
     "atdn_last_error", "atdn_version", "atdn_check_device", "atdn_tc_gemm", "atdn_corr_lookup",
@@ -110,6 +110,8 @@ def tc_label(d: TcDesc):
         cin = d.a_dims[0] + (d.a2_dims[0] if d.a_split_chunk else 0)
         flops = 2.0 * d.out_h * d.out_w * d.a_dims[3] * d.n_valid * d.taps_h * d.taps_w * cin   # algorithmic (n_valid, not the padded tile)
         name = {EPI_GRU_ZR: "gru_zr", EPI_GRU_Q: "gru_q", EPI_FLOW: "flow_head2"}.get(d.epi, f"conv{d.taps_h}x{d.taps_w}_{cin}to{d.n_valid}_s{d.stride}")
+        if d.flags & F_TILED32:
+            name = "gru_context_pre"
     else:
         batch = d.b_dims[3] if (d.flags & F_A_SHARED) else d.a_dims[3]
         flops = 2.0 * d.a_dims[1] * d.n_valid * d.a_dims[0] * batch

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
         const bool valid = (h < p.out_h) && (w < p.out_w);
         const long long pix = (static_cast<long long>(tc.batch) * p.out_h + h) * p.out_w + w;
         long long sidx = 0;
-        if constexpr (EPI == ATDN_EPI_STORE16 || EPI == ATDN_EPI_GRU_ZR || EPI == ATDN_EPI_GRU_Q)
+        if constexpr (EPI == ATDN_EPI_STORE16 || EPI == ATDN_EPI_STORE32 || EPI == ATDN_EPI_GRU_ZR || EPI == ATDN_EPI_GRU_Q)
           sidx = state_index(tc.batch, h, w, p.out_h, p.out_w);
         uint32_t v[32];
         tmem_ld_32x32(trow + s * BN + cc * 32, v);

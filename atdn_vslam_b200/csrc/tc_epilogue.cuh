@@ -89,8 +89,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
                                                const uint32_t (&v)[32], long long sidx = -1, uint32_t st_row = 0,
                                                uint32_t st_swz = 0) {
   if (n >= p.n_valid) return;
-  if constexpr (EPI == ATDN_EPI_STORE16 || EPI == ATDN_EPI_GRU_ZR || EPI == ATDN_EPI_GRU_Q) {
-    if (sidx < 0 && valid && (EPI != ATDN_EPI_STORE16 || (p.flags & ATDN_F_TANH_LO))) {
+  if constexpr (EPI == ATDN_EPI_STORE16 || EPI == ATDN_EPI_STORE32 || EPI == ATDN_EPI_GRU_ZR || EPI == ATDN_EPI_GRU_Q) {
+    if (sidx < 0 && valid && ((EPI != ATDN_EPI_STORE16 && EPI != ATDN_EPI_STORE32) || (p.flags & (ATDN_F_TANH_LO | ATDN_F_TILED32)))) {
       const int w = static_cast<int>(pix % p.img_w);
       const long long t = pix / p.img_w;
       sidx = state_index(static_cast<int>(t / p.img_h), static_cast<int>(t % p.img_h), w, p.img_h, p.img_w);
@@ -167,6 +167,13 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       store_row_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y, ng, tail);
     }
   } else if constexpr (EPI == ATDN_EPI_STORE32) {
+    if (p.flags & ATDN_F_TILED32) {   // tiled recurrent-state layout, 128 channels per buffer (n_valid is a multiple of 32 here)
+      float4* t = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(n >> 7) * p.out_pitch) + sidx +
+                  ((n & 127) >> 2) * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i * 32] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      return;
+    }
     float* dst = reinterpret_cast<float*>(p.out) + pix * p.out_pitch + p.out_ch_off + n;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -180,6 +187,14 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       }
     }
   } else if constexpr (EPI == ATDN_EPI_GRU_ZR) {
+    if (p.aux32) {   // context part of the convolution, computed once per pair (bias included)
+      const float4* pre = reinterpret_cast<const float4*>(p.aux32 + (n < 128 ? 0 : p.resid_pitch)) + sidx + ((n & 127) >> 2) * 32;
+      float4 pv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pv[i] = __ldg(pre + i * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { y[4 * i] += pv[i].x; y[4 * i + 1] += pv[i].y; y[4 * i + 2] += pv[i].z; y[4 * i + 3] += pv[i].w; }
+    }
     if (n < 128) {
       float4* z = reinterpret_cast<float4*>(p.z32) + sidx + (n >> 2) * 32;
 #pragma unroll
@@ -211,6 +226,14 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       }
     }
   } else if constexpr (EPI == ATDN_EPI_GRU_Q) {
+    if (p.aux32) {
+      const float4* pre = reinterpret_cast<const float4*>(p.aux32) + sidx + (n >> 2) * 32;
+      float4 pv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pv[i] = __ldg(pre + i * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { y[4 * i] += pv[i].x; y[4 * i + 1] += pv[i].y; y[4 * i + 2] += pv[i].z; y[4 * i + 3] += pv[i].w; }
+    }
     float4* h = reinterpret_cast<float4*>(p.h32) + sidx + (n >> 2) * 32;
     const float4* z = reinterpret_cast<const float4*>(p.z32) + sidx + (n >> 2) * 32;
     float4 hv[8], zv[8];

@@ -75,7 +75,8 @@ _HALO_CFG = {64: (4, 64, True), 96: (2, 96, True), 128: (2, 128, True), 192: (1,
              576: (1, 192, False)}
 
 
-_NO_FUSED_STATS = os.environ.get("ATDN_NO_FUSED_STATS") == "1"      # A/B switch (bench only)
+_NO_FUSED_STATS = os.environ.get("ATDN_NO_FUSED_STATS") == "1"      # A/B switches (bench only)
+_NO_GRU_PRE = os.environ.get("ATDN_NO_GRU_PRE") == "1"
 
 
 def _halo(cout, taps=(3, 3)):
@@ -159,12 +160,22 @@ class _Packed:
         self.convf2 = _Conv(*g("encoder.convf2"))
         w, b = g("encoder.conv")                       # 126 outputs + 2 raw flow channels (update.py:84)
         self.conv = _Conv(w, torch.cat([b.float(), torch.zeros(2, device=b.device)]))
-        self.gru = []
+        # SepConvGRU (update.py:48-63) on hx = [h | inp | mf | mfg]: the context features `inp` do not change over the
+        # refinement iterations, so their part of every gate convolution (+ bias) is computed once per pair
+        # (gru_pre: zr / q weights over input channels 128..255) and the per-iteration convolutions contract only
+        # [h | mf | mfg] (384 of 512 channels: 25% fewer MMAs); the epilogues add the stored term.
+        self.gru, self.gru_pre = [], []
+        rest = lambda w: torch.cat([w[:, :128], w[:, 256:]], 1)
         for n in ("1", "2"):
             wz, bz = g("gru.convz" + n)
             wr, br = g("gru.convr" + n)
             wq, bq = g("gru.convq" + n)
-            self.gru.append((_Conv(torch.cat([wz, wr], 0), torch.cat([bz, br], 0)), _Conv(wq, bq)))
+            wzr, bzr = torch.cat([wz, wr], 0), torch.cat([bz, br], 0)
+            if _NO_GRU_PRE:
+                self.gru.append((_Conv(wzr, bzr), _Conv(wq, bq)))
+            else:
+                self.gru.append((_Conv(rest(wzr), None), _Conv(rest(wq), None)))
+                self.gru_pre.append((_Conv(wzr[:, 128:256], bzr), _Conv(wq[:, 128:256], bq)))
         self.fh1 = _Conv(*g("flow_head.conv1"))
         # flow_head.conv2 (3x3, 256 -> 2) as a 1x1 conv 256 -> 18 (row = tap*2 + co, zero-padded to one 32-column MMA
         # tile) whose per-tap partial products are summed with their shifts by ops.flow_head_gather
@@ -198,6 +209,9 @@ class _Plan:
         self.hx = f16(b, h8, w8, 512)
         self.h32 = ops.state_alloc(b, h8, w8, dev)     # tiled fp32 state layout (csrc/tc_epilogue.cuh)
         self.z32 = ops.state_alloc(b, h8, w8, dev)
+        # context part of the GRU gate convolutions per GRU half: [z | r] and q, tiled fp32 like h32
+        self.pre_zr = [torch.empty((2,) + tuple(self.z32.shape), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.pre_q = [ops.state_alloc(b, h8, w8, dev) for _ in range(2)]
         self.rh = f16(b, h8, w8, 128)
         self.pyr = ops.alloc_pyramid(b, h8, w8, dev, half_levels=4)
         self.qk = f16(b, h8, w8, 256)
@@ -391,6 +405,15 @@ class RAFTGMA(nn.Module):
         hx = plan.hx
         self._encoder(plan, wts.cnet, image1, View(hx, 0, 256), final_flags=L.F_TANH_LO, h32=plan.h32)
 
+        if wts.gru_pre:
+            per_buf = plan.z32.numel()
+            for i, (taps, pad) in enumerate((((1, 5), (0, 2)), ((5, 1), (2, 0)))):
+                zr, q = wts.gru_pre[i]
+                _conv_s1(View(hx, 128, 128), zr, View(plan.pre_zr[i].view(-1, 1, 1, 8)), cout=256, taps=taps, epi=L.EPI_STORE32,
+                         flags=L.F_TILED32, out_pitch=per_buf)
+                _conv_s1(View(hx, 128, 128), q, View(plan.pre_q[i].view(-1, 1, 1, 8)), cout=128, taps=taps, epi=L.EPI_STORE32,
+                         flags=L.F_TILED32, out_pitch=per_buf)
+
         # attention (gma.py:54-76): q.k^T * scale -> softmax
         _conv_s1(View(hx, 128, 128), wts.to_qk, View(plan.qk), cout=256, taps=(1, 1))
         ops.attn_probs(plan.qk, plan.p16, plan.inv_sum, 128 ** -0.5)
@@ -452,10 +475,16 @@ class RAFTGMA(nn.Module):
         ops.gemm_rows(L.ptr(plan.p16), n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
                       b_bstride=128 * np_, bn=128, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
                       aux32=plan.inv_sum, gamma=wts.gamma)
-        for (zr, q), taps, pad in ((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0))):
-            _conv_s1(View(hx), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, h32=plan.h32, z32=plan.z32, rh16=plan.rh)
-            _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 128, 384),
-                     h32=plan.h32, z32=plan.z32)
+        for i, ((zr, q), taps, pad) in enumerate(((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0)))):
+            if wts.gru_pre:   # contract [h | mf | mfg] only; the context term comes from plan.pre_*
+                _conv_s1(View(hx, 0, 128), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, a2=View(hx, 256, 256), h32=plan.h32,
+                         z32=plan.z32, rh16=plan.rh, aux32=plan.pre_zr[i], aux_half_offset=plan.z32.numel())
+                _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 256, 256),
+                         h32=plan.h32, z32=plan.z32, aux32=plan.pre_q[i])
+            else:
+                _conv_s1(View(hx), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, h32=plan.h32, z32=plan.z32, rh16=plan.rh)
+                _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 128, 384),
+                         h32=plan.h32, z32=plan.z32)
         c = wts.fh1
         _conv_s1(View(hx, 0, 128), c, View(plan.fh), cout=256, taps=(3, 3), flags=R)
         c = wts.fh2   # flow_head.conv2 + coords update (network.py:111,116): per-tap 1x1 products, then the shifted sum

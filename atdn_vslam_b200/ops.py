@@ -90,7 +90,7 @@ def _fill_out(d, out, n_valid, alpha, bias):
 
 def conv_tc(a, wp, bias, out, *, cout, taps=(1, 1), pad=(0, 0), stride=1, bn=128, epi=L.EPI_STORE16, flags=0,
             alpha=1.0, a2=None, resid=None, h32=None, z32=None, rh16=None, aux32=None, gamma=None, mt=0, stamps=None,
-            out_hw=None):
+            out_hw=None, out_pitch=None, aux_half_offset=None):
     """Convolution as implicit GEMM on tcgen05.  ``a`` (and optional ``a2``, concatenated after it)
     are NHWC fp16 Views of the INPUT image; ``out`` is a View of the output buffer."""
     d = L.TcDesc()
@@ -119,6 +119,10 @@ def conv_tc(a, wp, bias, out, *, cout, taps=(1, 1), pad=(0, 0), stride=1, bn=128
     if resid is not None:
         d.resid16, d.resid_pitch, d.resid_ch_off = resid.ptr(), resid.pitch, 0
     d.h32, d.z32, d.rh16, d.aux32, d.gamma = L.ptr(h32), L.ptr(z32), L.ptr(rh16), L.ptr(aux32), L.ptr(gamma)
+    if out_pitch is not None:       # F_TILED32: floats per 128-channel buffer
+        d.out_pitch = out_pitch
+    if aux_half_offset is not None:  # GRU_ZR with a pre-activation term: offset (floats) of the r half
+        d.resid_pitch = aux_half_offset
     L.tc_gemm(d)
     return oh, ow
 

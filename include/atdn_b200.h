@@ -79,7 +79,11 @@ enum {
   ATDN_F_B_BATCHED = 16, /* B operand has a batch dimension (attention GEMMs, corr volume)               */
   ATDN_F_A_SHARED  = 32, /* ROWS A is shared by all batches (weights as the A operand: transposed output); batch = b_dims[3] */
   ATDN_F_PAIR      = 64, /* CTA-pair kernel (tcgen05 cta_group::2): 256 x bn tiles, each CTA stages bn/2 B rows; bn up to 256 */
-  ATDN_F_STATS     = 128 /* STORE16 on the halo kernel with mt = 4, bn = 64 (n_valid = 64): per-channel partial sums of
+  ATDN_F_TILED32   = 256, /* STORE32: fp32 output in the tiled recurrent-state layout (see h32 below), 128 channels per buffer:
+                            channel n goes to buffer n / 128 at out + (n / 128) * out_pitch floats (out_pitch = floats per buffer).
+                            Used once per pair for the part of the SepConvGRU convolutions that only sees the context
+                            features (constant over the refinement iterations); bias included                          */
+  ATDN_F_STATS     = 128, /* STORE16 on the halo kernel with mt = 4, bn = 64 (n_valid = 64): per-channel partial sums of
                             (acc + bias) and its square over the in-image pixels each epilogue warp sees in one tile go to
                             aux32 as [batch, parts, 64, 2] fp32, parts = ceil(H/16) * ceil(W/(32*cl)) * cl * 4 (cl = 2 with
                             ATDN_F_PAIR): the instance-norm statistics pass without re-reading the tensor; reduce them with
@@ -115,7 +119,9 @@ typedef struct atdn_tc_desc {
   float* h32;             /* GRU_*: hidden state master copy; STORE16|TANH_LO: written (FLOW: coords1)   */
   float* z32;             /* GRU_ZR writes / GRU_Q reads the update gate            (FLOW: flow)         */
   void* rh16;             /* GRU_ZR: fp16 [pix,128] = r*h                                           */
-  const float* aux32;     /* FLOWTAIL: fp32 flow [pix,2]; PV: row_scale [pix]                       */
+  const float* aux32;     /* FLOWTAIL: fp32 flow [pix,2]; PV: row_scale [pix]; STATS: partial sums (written);
+                             GRU_ZR / GRU_Q: optional pre-activation term in the tiled layout (ATDN_F_TILED32 output), added
+                             to acc + bias; GRU_ZR reads the r half at aux32 + resid_pitch floats                 */
   const float* gamma;     /* PV: pointer to the scalar Aggregate.gamma                              */
   /* CORR: pyramid levels 1..3 (fp32) and their row pitches; level l is [batch*rows, H_l, pitch_l]  */
   float* lvl[3];

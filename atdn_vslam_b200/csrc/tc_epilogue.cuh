@@ -84,6 +84,29 @@ __device__ __forceinline__ void store_row_f16(__half* dst, const float (&y)[32],
 // sidx: state_index() of the pixel (float4 units), or < 0 to derive it from pix = (b * img_h + h) * img_w + w
 // st_row (STORE16, GRU_Q, r half of GRU_ZR): shared-memory address of this thread's 64-byte row in a 64B-swizzled staging box (the caller
 // hands the box to a TMA store), or 0 to store to global memory directly; st_swz = (row >> 1) & 3.
+// y[0..31] += the stored pre-activation term of channels c0 .. c0+31 (tiled layout, fp32 or fp16)
+__device__ __forceinline__ void add_pre_term(const EpiParams& p, long long elem_off, long long sidx, int c0, float (&y)[32]) {
+  if (p.flags & ATDN_F_PRE16) {
+    const uint2* pre = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.aux32) + elem_off) + sidx + (c0 >> 2) * 32;
+    uint2 pv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pv[i] = __ldg(pre + i * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&pv[i].x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&pv[i].y));
+      y[4 * i] += a.x; y[4 * i + 1] += a.y; y[4 * i + 2] += b.x; y[4 * i + 3] += b.y;
+    }
+  } else {
+    const float4* pre = reinterpret_cast<const float4*>(p.aux32 + elem_off) + sidx + (c0 >> 2) * 32;
+    float4 pv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pv[i] = __ldg(pre + i * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { y[4 * i] += pv[i].x; y[4 * i + 1] += pv[i].y; y[4 * i + 2] += pv[i].z; y[4 * i + 3] += pv[i].w; }
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, long long pix, int n,
                                                const uint32_t (&v)[32], long long sidx = -1, uint32_t st_row = 0,
@@ -167,6 +190,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       store_row_f16(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + p.out_ch_off + n, y, ng, tail);
     }
   } else if constexpr (EPI == ATDN_EPI_STORE32) {
+    if ((p.flags & ATDN_F_TILED32) && (p.flags & ATDN_F_PRE16)) {   // same tiled index space, fp16 storage
+      uint2* t = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + static_cast<long long>(n >> 7) * p.out_pitch) + sidx +
+                 ((n & 127) >> 2) * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __half2 a = __floats2half2_rn(y[4 * i], y[4 * i + 1]), b = __floats2half2_rn(y[4 * i + 2], y[4 * i + 3]);
+        t[i * 32] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+      }
+      return;
+    }
     if (p.flags & ATDN_F_TILED32) {   // tiled recurrent-state layout, 128 channels per buffer (n_valid is a multiple of 32 here)
       float4* t = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(n >> 7) * p.out_pitch) + sidx +
                   ((n & 127) >> 2) * 32;
@@ -187,14 +220,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       }
     }
   } else if constexpr (EPI == ATDN_EPI_GRU_ZR) {
-    if (p.aux32) {   // context part of the convolution, computed once per pair (bias included)
-      const float4* pre = reinterpret_cast<const float4*>(p.aux32 + (n < 128 ? 0 : p.resid_pitch)) + sidx + ((n & 127) >> 2) * 32;
-      float4 pv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pv[i] = __ldg(pre + i * 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { y[4 * i] += pv[i].x; y[4 * i + 1] += pv[i].y; y[4 * i + 2] += pv[i].z; y[4 * i + 3] += pv[i].w; }
-    }
+    if (p.aux32) add_pre_term(p, n < 128 ? 0 : p.resid_pitch, sidx, n & 127, y);   // context part of the conv, once per pair (bias included)
     if (n < 128) {
       float4* z = reinterpret_cast<float4*>(p.z32) + sidx + (n >> 2) * 32;
 #pragma unroll
@@ -226,14 +252,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       }
     }
   } else if constexpr (EPI == ATDN_EPI_GRU_Q) {
-    if (p.aux32) {
-      const float4* pre = reinterpret_cast<const float4*>(p.aux32) + sidx + (n >> 2) * 32;
-      float4 pv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pv[i] = __ldg(pre + i * 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { y[4 * i] += pv[i].x; y[4 * i + 1] += pv[i].y; y[4 * i + 2] += pv[i].z; y[4 * i + 3] += pv[i].w; }
-    }
+    if (p.aux32) add_pre_term(p, 0, sidx, n, y);
     float4* h = reinterpret_cast<float4*>(p.h32) + sidx + (n >> 2) * 32;
     const float4* z = reinterpret_cast<const float4*>(p.z32) + sidx + (n >> 2) * 32;
     float4 hv[8], zv[8];

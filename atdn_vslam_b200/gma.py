@@ -77,6 +77,8 @@ _HALO_CFG = {64: (4, 64, True), 96: (2, 96, True), 128: (2, 128, True), 192: (1,
 
 _NO_FUSED_STATS = os.environ.get("ATDN_NO_FUSED_STATS") == "1"      # A/B switches (bench only)
 _NO_GRU_PRE = os.environ.get("ATDN_NO_GRU_PRE") == "1"
+_GRU_PRE32 = os.environ.get("ATDN_GRU_PRE32") == "1"
+_PRE16 = 0 if _GRU_PRE32 else L.F_PRE16
 
 
 def _halo(cout, taps=(3, 3)):
@@ -209,9 +211,11 @@ class _Plan:
         self.hx = f16(b, h8, w8, 512)
         self.h32 = ops.state_alloc(b, h8, w8, dev)     # tiled fp32 state layout (csrc/tc_epilogue.cuh)
         self.z32 = ops.state_alloc(b, h8, w8, dev)
-        # context part of the GRU gate convolutions per GRU half: [z | r] and q, tiled fp32 like h32
-        self.pre_zr = [torch.empty((2,) + tuple(self.z32.shape), dtype=torch.float32, device=dev) for _ in range(2)]
-        self.pre_q = [ops.state_alloc(b, h8, w8, dev) for _ in range(2)]
+        # context part of the GRU gate convolutions per GRU half: [z | r] and q, tiled like h32, fp16 (one rounding of a
+        # pre-activation: the same size as the fp16 rounding of the conv operands) unless ATDN_GRU_PRE32=1
+        pdt = torch.float32 if _GRU_PRE32 else torch.float16
+        self.pre_zr = [torch.empty((2,) + tuple(self.z32.shape), dtype=pdt, device=dev) for _ in range(2)]
+        self.pre_q = [torch.empty(tuple(self.z32.shape), dtype=pdt, device=dev) for _ in range(2)]
         self.rh = f16(b, h8, w8, 128)
         self.pyr = ops.alloc_pyramid(b, h8, w8, dev, half_levels=4)
         self.qk = f16(b, h8, w8, 256)
@@ -410,9 +414,9 @@ class RAFTGMA(nn.Module):
             for i, (taps, pad) in enumerate((((1, 5), (0, 2)), ((5, 1), (2, 0)))):
                 zr, q = wts.gru_pre[i]
                 _conv_s1(View(hx, 128, 128), zr, View(plan.pre_zr[i].view(-1, 1, 1, 8)), cout=256, taps=taps, epi=L.EPI_STORE32,
-                         flags=L.F_TILED32, out_pitch=per_buf)
+                         flags=L.F_TILED32 | _PRE16, out_pitch=per_buf)
                 _conv_s1(View(hx, 128, 128), q, View(plan.pre_q[i].view(-1, 1, 1, 8)), cout=128, taps=taps, epi=L.EPI_STORE32,
-                         flags=L.F_TILED32, out_pitch=per_buf)
+                         flags=L.F_TILED32 | _PRE16, out_pitch=per_buf)
 
         # attention (gma.py:54-76): q.k^T * scale -> softmax
         _conv_s1(View(hx, 128, 128), wts.to_qk, View(plan.qk), cout=256, taps=(1, 1))
@@ -478,9 +482,9 @@ class RAFTGMA(nn.Module):
         for i, ((zr, q), taps, pad) in enumerate(((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0)))):
             if wts.gru_pre:   # contract [h | mf | mfg] only; the context term comes from plan.pre_*
                 _conv_s1(View(hx, 0, 128), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, a2=View(hx, 256, 256), h32=plan.h32,
-                         z32=plan.z32, rh16=plan.rh, aux32=plan.pre_zr[i], aux_half_offset=plan.z32.numel())
+                         z32=plan.z32, rh16=plan.rh, aux32=plan.pre_zr[i], aux_half_offset=plan.z32.numel(), flags=_PRE16)
                 _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 256, 256),
-                         h32=plan.h32, z32=plan.z32, aux32=plan.pre_q[i])
+                         h32=plan.h32, z32=plan.z32, aux32=plan.pre_q[i], flags=_PRE16)
             else:
                 _conv_s1(View(hx), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, h32=plan.h32, z32=plan.z32, rh16=plan.rh)
                 _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 128, 384),

@@ -83,6 +83,9 @@ enum {
                             channel n goes to buffer n / 128 at out + (n / 128) * out_pitch floats (out_pitch = floats per buffer).
                             Used once per pair for the part of the SepConvGRU convolutions that only sees the context
                             features (constant over the refinement iterations); bias included                          */
+  ATDN_F_PRE16     = 512, /* the pre-activation term is fp16: with ATDN_F_TILED32 the buffers are written as fp16 (same tiled
+                            index space, out_pitch in elements); with GRU_ZR / GRU_Q aux32 points to fp16 (resid_pitch in
+                            elements).  Halves the per-iteration epilogue traffic of the context term               */
   ATDN_F_STATS     = 128, /* STORE16 on the halo kernel with mt = 4, bn = 64 (n_valid = 64): per-channel partial sums of
                             (acc + bias) and its square over the in-image pixels each epilogue warp sees in one tile go to
                             aux32 as [batch, parts, 64, 2] fp32, parts = ceil(H/16) * ceil(W/(32*cl)) * cl * 4 (cl = 2 with

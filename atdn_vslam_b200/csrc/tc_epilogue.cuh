@@ -222,10 +222,20 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
   } else if constexpr (EPI == ATDN_EPI_GRU_ZR) {
     if (p.aux32) add_pre_term(p, n < 128 ? 0 : p.resid_pitch, sidx, n & 127, y);   // context part of the conv, once per pair (bias included)
     if (n < 128) {
-      float4* z = reinterpret_cast<float4*>(p.z32) + sidx + (n >> 2) * 32;
+      if (p.flags & ATDN_F_Z16) {
+        uint2* z = reinterpret_cast<uint2*>(p.z32) + sidx + (n >> 2) * 32;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        z[i * 32] = make_float4(sigmoid_fast(y[4 * i]), sigmoid_fast(y[4 * i + 1]), sigmoid_fast(y[4 * i + 2]), sigmoid_fast(y[4 * i + 3]));
+        for (int i = 0; i < 8; ++i) {
+          const __half2 a = __floats2half2_rn(sigmoid_fast(y[4 * i]), sigmoid_fast(y[4 * i + 1]));
+          const __half2 b = __floats2half2_rn(sigmoid_fast(y[4 * i + 2]), sigmoid_fast(y[4 * i + 3]));
+          z[i * 32] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+        }
+      } else {
+        float4* z = reinterpret_cast<float4*>(p.z32) + sidx + (n >> 2) * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          z[i * 32] = make_float4(sigmoid_fast(y[4 * i]), sigmoid_fast(y[4 * i + 1]), sigmoid_fast(y[4 * i + 2]), sigmoid_fast(y[4 * i + 3]));
+      }
     } else {
       const float4* h = reinterpret_cast<const float4*>(p.h32) + sidx + ((n - 128) >> 2) * 32;
       float4 hv[8];
@@ -254,10 +264,23 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
   } else if constexpr (EPI == ATDN_EPI_GRU_Q) {
     if (p.aux32) add_pre_term(p, 0, sidx, n, y);
     float4* h = reinterpret_cast<float4*>(p.h32) + sidx + (n >> 2) * 32;
-    const float4* z = reinterpret_cast<const float4*>(p.z32) + sidx + (n >> 2) * 32;
     float4 hv[8], zv[8];
+    if (p.flags & ATDN_F_Z16) {
+      const uint2* z = reinterpret_cast<const uint2*>(p.z32) + sidx + (n >> 2) * 32;
+      uint2 zu[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { hv[i] = h[i * 32]; zv[i] = z[i * 32]; }
+      for (int i = 0; i < 8; ++i) { hv[i] = h[i * 32]; zu[i] = z[i * 32]; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&zu[i].x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&zu[i].y));
+        zv[i] = make_float4(a.x, a.y, b.x, b.y);
+      }
+    } else {
+      const float4* z = reinterpret_cast<const float4*>(p.z32) + sidx + (n >> 2) * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { hv[i] = h[i * 32]; zv[i] = z[i * 32]; }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       y[4 * i + 0] = (1.0f - zv[i].x) * hv[i].x + zv[i].x * tanh_fast(y[4 * i + 0]);

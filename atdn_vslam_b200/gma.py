@@ -79,6 +79,7 @@ _NO_FUSED_STATS = os.environ.get("ATDN_NO_FUSED_STATS") == "1"      # A/B switch
 _NO_GRU_PRE = os.environ.get("ATDN_NO_GRU_PRE") == "1"
 _GRU_PRE32 = os.environ.get("ATDN_GRU_PRE32") == "1"
 _PRE16 = 0 if _GRU_PRE32 else L.F_PRE16
+_Z16 = 0 if os.environ.get("ATDN_GRU_Z32") == "1" else L.F_Z16
 
 
 def _halo(cout, taps=(3, 3)):
@@ -211,6 +212,7 @@ class _Plan:
         self.hx = f16(b, h8, w8, 512)
         self.h32 = ops.state_alloc(b, h8, w8, dev)     # tiled fp32 state layout (csrc/tc_epilogue.cuh)
         self.z32 = ops.state_alloc(b, h8, w8, dev)
+        self.z = self.z32.half() if _Z16 else self.z32     # update gate, fp16 in the same tiled index space (ATDN_F_Z16)
         # context part of the GRU gate convolutions per GRU half: [z | r] and q, tiled like h32, fp16 (one rounding of a
         # pre-activation: the same size as the fp16 rounding of the conv operands) unless ATDN_GRU_PRE32=1
         pdt = torch.float32 if _GRU_PRE32 else torch.float16
@@ -482,9 +484,9 @@ class RAFTGMA(nn.Module):
         for i, ((zr, q), taps, pad) in enumerate(((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0)))):
             if wts.gru_pre:   # contract [h | mf | mfg] only; the context term comes from plan.pre_*
                 _conv_s1(View(hx, 0, 128), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, a2=View(hx, 256, 256), h32=plan.h32,
-                         z32=plan.z32, rh16=plan.rh, aux32=plan.pre_zr[i], aux_half_offset=plan.z32.numel(), flags=_PRE16)
+                         z32=plan.z, rh16=plan.rh, aux32=plan.pre_zr[i], aux_half_offset=plan.z32.numel(), flags=_PRE16 | _Z16)
                 _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 256, 256),
-                         h32=plan.h32, z32=plan.z32, aux32=plan.pre_q[i], flags=_PRE16)
+                         h32=plan.h32, z32=plan.z, aux32=plan.pre_q[i], flags=_PRE16 | _Z16)
             else:
                 _conv_s1(View(hx), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, h32=plan.h32, z32=plan.z32, rh16=plan.rh)
                 _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 128, 384),

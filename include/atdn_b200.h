@@ -86,6 +86,8 @@ enum {
   ATDN_F_PRE16     = 512, /* the pre-activation term is fp16: with ATDN_F_TILED32 the buffers are written as fp16 (same tiled
                             index space, out_pitch in elements); with GRU_ZR / GRU_Q aux32 points to fp16 (resid_pitch in
                             elements).  Halves the per-iteration epilogue traffic of the context term               */
+  ATDN_F_Z16       = 1024, /* GRU_ZR / GRU_Q: z32 points to fp16 (same tiled index space): the update gate lies in (0, 1), its fp16
+                             rounding (2.4e-4 absolute) is below the fp16 rounding of the hidden state it blends        */
   ATDN_F_STATS     = 128, /* STORE16 on the halo kernel with mt = 4, bn = 64 (n_valid = 64): per-channel partial sums of
                             (acc + bias) and its square over the in-image pixels each epilogue warp sees in one tile go to
                             aux32 as [batch, parts, 64, 2] fp32, parts = ceil(H/16) * ceil(W/(32*cl)) * cl * 4 (cl = 2 with

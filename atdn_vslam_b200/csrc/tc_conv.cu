@@ -517,18 +517,20 @@ int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream) {
   const int avail = kMaxDynSmem - 1024 - out_bytes;   // 1 KiB alignment slack
   p.a_stages = (3 * p.a_stage_bytes + 4 * b_bytes <= avail) ? 3 : 2;
   if (d->taps_h * d->taps_w == 1) {
-    // 1x1: one A box per weight tile, both rings drain at the same rate -- and an A box is 128 scattered 128-byte
-    // rows whose TMA latency (not bandwidth) bounds the kernel with 3 boxes in flight: split shared memory evenly
+    // 1x1: one A box per weight tile, both rings drain at the same rate: split shared memory evenly (measured neutral
+    // against 3 A stages -- the 1x1 layers were bound by their epilogue stores, see the TMA-store epilogue below)
     const int n = avail / (p.a_stage_bytes + b_bytes);
     p.a_stages = n > kMaxAStages ? kMaxAStages : (n < 2 ? 2 : n);
   }
   int bs = (avail - p.a_stages * p.a_stage_bytes) / b_bytes;
   p.b_stages = bs > kMaxBStages ? kMaxBStages : bs;
   {
-    // resident weights: every (chunk, tap) tile of the single N tile in shared memory next to >= 2 A stages
+    // resident weights (opt-in, ATDN_B_RESIDENT=1): every (chunk, tap) tile of the single N tile in shared memory next to
+    // >= 2 A stages.  Measured on the 1x1 and 64-channel layers: no gain (the weight stream was not their limiter, and
+    // the 1x1 324 -> 256 layer loses A stages: 77 vs 74 us), so the streamed ring stays the default.
     const int need = chunks * d->taps_h * d->taps_w;
-    const char* off = getenv("ATDN_NO_B_RESIDENT");
-    if (!(off && off[0] == '1') && p.n_tiles == 1 && need <= kMaxBStages && 2 * p.a_stage_bytes + need * b_bytes <= avail) {
+    const char* on = getenv("ATDN_B_RESIDENT");
+    if (on && on[0] == '1' && p.n_tiles == 1 && need <= kMaxBStages && 2 * p.a_stage_bytes + need * b_bytes <= avail) {
       p.b_resident = 1;
       p.b_stages = need;
       const int as = (avail - need * b_bytes) / p.a_stage_bytes;

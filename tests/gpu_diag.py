@@ -218,10 +218,10 @@ def time_halo():
 
 def time_resident():
     """Resident-weights mode of the halo kernel (all (chunk, tap) weight tiles stay in shared memory) against the
-    streamed-weights mode (ATDN_NO_B_RESIDENT=1) on the layers that qualify."""
-    for off in ("1", "0"):
-        os.environ["ATDN_NO_B_RESIDENT"] = off
-        print(f"--- ATDN_NO_B_RESIDENT={off}", flush=True)
+    default streamed-weights ring (resident mode is opt-in: ATDN_B_RESIDENT=1) on the layers that qualify."""
+    for on in ("0", "1"):
+        os.environ["ATDN_B_RESIDENT"] = on
+        print(f"--- ATDN_B_RESIDENT={on}", flush=True)
         bench_conv("c1x1 324->256", 324, 256, (1, 1), 256, 1, batch=27)
         bench_conv("c1x1 324->256", 324, 256, (1, 1), 256, 1, batch=27, pair=True)
         bench_conv("c1x1 128->256", 128, 256, (1, 1), 256, 1, batch=27)
@@ -229,7 +229,7 @@ def time_resident():
         bench_conv("enc 64->64", 64, 64, (3, 3), 64, 4, batch=14, h=188, w=616)
         bench_conv("enc 64->64", 64, 64, (3, 3), 64, 4, batch=14, h=188, w=616, pair=True)
         bench_conv("c3x3 128->64", 128, 64, (3, 3), 64, 2, batch=27, pair=True)
-    os.environ.pop("ATDN_NO_B_RESIDENT", None)
+    os.environ.pop("ATDN_B_RESIDENT", None)
     return True
 
 

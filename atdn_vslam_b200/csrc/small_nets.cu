@@ -686,8 +686,8 @@ extern "C" int atdn_conv32(const atdn_conv32_desc* d, void* stream) {
       const bool k3 = d->k == 3 && d->pad == 1 && d->cin == 16 && !d->in_scale;
       if (k3 && d->stride == 1 && !d->skip) return launch_conv16t<3, 1, 1, 16, 8, false, false>(p, st);
       if (k3 && d->stride == 1 && d->skip) return launch_conv16t<3, 1, 1, 16, 8, false, true>(p, st);
-      if (k3 && d->stride == 2 && !d->skip) return launch_conv16t<3, 2, 1, 16, 4, false, false>(p, st);
-      if (k3 && d->stride == 2 && d->skip) return launch_conv16t<3, 2, 1, 16, 4, false, true>(p, st);
+      if (k3 && d->stride == 2 && !d->skip) return launch_conv16t<3, 2, 1, 16, 2, false, false>(p, st);
+      if (k3 && d->stride == 2 && d->skip) return launch_conv16t<3, 2, 1, 16, 2, false, true>(p, st);
       if (d->k == 7 && d->stride == 2 && d->pad == 3 && d->cin == 2 && d->in_scale && !d->skip)
         return launch_conv16t<7, 2, 3, 2, 2, true, false>(p, st);
     }

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libatdn_b200.so")
 
 MODE_ROWS, MODE_PATCH = 0, 1
 EPI_STORE16, EPI_STORE32, EPI_CORR, EPI_GRU_ZR, EPI_GRU_Q, EPI_PV, EPI_FLOW = range(7)
-F_RELU, F_RESID, F_FLOWTAIL, F_TANH_LO, F_B_BATCHED, F_A_SHARED, F_PAIR, F_STATS, F_TILED32, F_PRE16, F_Z16 = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
+F_RELU, F_RESID, F_FLOWTAIL, F_TANH_LO, F_B_BATCHED, F_A_SHARED, F_PAIR, F_STATS, F_TILED32, F_PRE16, F_Z16, F_H16 = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048
 
 EXPORTS = (
     "atdn_last_error", "atdn_version", "atdn_check_device", "atdn_tc_gemm", "atdn_corr_lookup",

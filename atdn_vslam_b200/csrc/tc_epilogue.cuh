@@ -81,9 +81,40 @@ __device__ __forceinline__ void store_row_f16(__half* dst, const float (&y)[32],
   }
 }
 
-// sidx: state_index() of the pixel (float4 units), or < 0 to derive it from pix = (b * img_h + h) * img_w + w
-// st_row (STORE16, GRU_Q, r half of GRU_ZR): shared-memory address of this thread's 64-byte row in a 64B-swizzled staging box (the caller
-// hands the box to a TMA store), or 0 to store to global memory directly; st_swz = (row >> 1) & 3.
+// 32 channels (c0 .. c0+31) of one pixel of a tiled state buffer, fp32 or fp16 storage
+__device__ __forceinline__ void load_tiled(const void* base, bool half, long long sidx, int c0, float4 (&o)[8]) {
+  if (half) {
+    const uint2* s = reinterpret_cast<const uint2*>(base) + sidx + (c0 >> 2) * 32;
+    uint2 u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = s[i * 32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u[i].x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u[i].y));
+      o[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+  } else {
+    const float4* s = reinterpret_cast<const float4*>(base) + sidx + (c0 >> 2) * 32;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = s[i * 32];
+  }
+}
+__device__ __forceinline__ void store_tiled(void* base, bool half, long long sidx, int c0, const float (&y)[32]) {
+  if (half) {
+    uint2* d = reinterpret_cast<uint2*>(base) + sidx + (c0 >> 2) * 32;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __half2 a = __floats2half2_rn(y[4 * i], y[4 * i + 1]), b = __floats2half2_rn(y[4 * i + 2], y[4 * i + 3]);
+      d[i * 32] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+  } else {
+    float4* d = reinterpret_cast<float4*>(base) + sidx + (c0 >> 2) * 32;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i * 32] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+  }
+}
+
 // y[0..31] += the stored pre-activation term of channels c0 .. c0+31 (tiled layout, fp32 or fp16)
 __device__ __forceinline__ void add_pre_term(const EpiParams& p, long long elem_off, long long sidx, int c0, float (&y)[32]) {
   if (p.flags & ATDN_F_PRE16) {
@@ -107,6 +138,9 @@ __device__ __forceinline__ void add_pre_term(const EpiParams& p, long long elem_
   }
 }
 
+// sidx: state_index() of the pixel (4-channel-group units), or < 0 to derive it from pix = (b * img_h + h) * img_w + w
+// st_row (STORE16, GRU_Q, r half of GRU_ZR): shared-memory address of this thread's 64-byte row in a 64B-swizzled
+// staging box (the caller hands the box to a TMA store), or 0 to store to global memory directly; st_swz = (row >> 1) & 3.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, long long pix, int n,
                                                const uint32_t (&v)[32], long long sidx = -1, uint32_t st_row = 0,
@@ -152,9 +186,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       if (n < 128) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] = tanh_fast(y[j]);
-        float4* h = reinterpret_cast<float4*>(p.h32) + sidx + (n >> 2) * 32;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i * 32] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+        store_tiled(p.h32, (p.flags & ATDN_F_H16) != 0, sidx, n, y);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
@@ -237,10 +269,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
           z[i * 32] = make_float4(sigmoid_fast(y[4 * i]), sigmoid_fast(y[4 * i + 1]), sigmoid_fast(y[4 * i + 2]), sigmoid_fast(y[4 * i + 3]));
       }
     } else {
-      const float4* h = reinterpret_cast<const float4*>(p.h32) + sidx + ((n - 128) >> 2) * 32;
       float4 hv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) hv[i] = h[i * 32];
+      load_tiled(p.h32, (p.flags & ATDN_F_H16) != 0, sidx, n - 128, hv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         y[4 * i + 0] = sigmoid_fast(y[4 * i + 0]) * hv[i].x;
@@ -263,24 +293,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
     }
   } else if constexpr (EPI == ATDN_EPI_GRU_Q) {
     if (p.aux32) add_pre_term(p, 0, sidx, n, y);
-    float4* h = reinterpret_cast<float4*>(p.h32) + sidx + (n >> 2) * 32;
     float4 hv[8], zv[8];
-    if (p.flags & ATDN_F_Z16) {
-      const uint2* z = reinterpret_cast<const uint2*>(p.z32) + sidx + (n >> 2) * 32;
-      uint2 zu[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { hv[i] = h[i * 32]; zu[i] = z[i * 32]; }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&zu[i].x));
-        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&zu[i].y));
-        zv[i] = make_float4(a.x, a.y, b.x, b.y);
-      }
-    } else {
-      const float4* z = reinterpret_cast<const float4*>(p.z32) + sidx + (n >> 2) * 32;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { hv[i] = h[i * 32]; zv[i] = z[i * 32]; }
-    }
+    load_tiled(p.h32, (p.flags & ATDN_F_H16) != 0, sidx, n, hv);
+    load_tiled(p.z32, (p.flags & ATDN_F_Z16) != 0, sidx, n, zv);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       y[4 * i + 0] = (1.0f - zv[i].x) * hv[i].x + zv[i].x * tanh_fast(y[4 * i + 0]);
@@ -288,8 +303,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
       y[4 * i + 2] = (1.0f - zv[i].z) * hv[i].z + zv[i].z * tanh_fast(y[4 * i + 2]);
       y[4 * i + 3] = (1.0f - zv[i].w) * hv[i].w + zv[i].w * tanh_fast(y[4 * i + 3]);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[i * 32] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    store_tiled(p.h32, (p.flags & ATDN_F_H16) != 0, sidx, n, y);
     if (st_row != 0) {
 #pragma unroll
       for (uint32_t g = 0; g < 4; ++g) {

@@ -10,8 +10,8 @@ Data layout in HBM (per batch of B pairs, 1/8-resolution grid H8 x W8, N = H8*W8
   HX  [B,H8,W8,512] fp16 : [0:128] GRU hidden state h | [128:256] context inp | [256:384] motion
                           features | [384:512] globally aggregated motion features  (the reference's
                           torch.cat([net, inp, mf, mfg]) materialised once, never copied)
-  h32, z32         fp32 master copy of the hidden state (recurrent precision) and the update gate, in the tiled
-                   layout of csrc/tc_epilogue.cuh (one warp access = 512 contiguous bytes; ops.state_alloc)
+  h32, z32         hidden state and update gate in the tiled layout of csrc/tc_epilogue.cuh (one warp access =
+                   contiguous bytes; ops.state_alloc); fp16 by default (ATDN_F_H16 / ATDN_F_Z16), fp32 optional
   corr pyramid     fp16 [B*N, H_l, pitch_l] for l = 0..3 (pitch = W_l rounded up to 32/16/8/8 elements: sector-aligned
                    store boxes), pooled in fp32 and rounded once on store; CorrBlock keeps the reference's fp32 pyramid
   P   [B,N,Np]     fp16 un-normalised attention probabilities exp(s - max), Np = N rounded up to 64
@@ -80,6 +80,9 @@ _NO_GRU_PRE = os.environ.get("ATDN_NO_GRU_PRE") == "1"
 _GRU_PRE32 = os.environ.get("ATDN_GRU_PRE32") == "1"
 _PRE16 = 0 if _GRU_PRE32 else L.F_PRE16
 _Z16 = 0 if os.environ.get("ATDN_GRU_Z32") == "1" else L.F_Z16
+# fp16-only hidden state (no fp32 master copy), like the reference's own fp16-autocast path: measured flow EPE
+# 7.105e-3 vs 7.107e-3 px with the fp32 master (ATDN_GRU_H32=1 restores it), 1.5 KB/pixel/iteration less GRU traffic
+_H16 = 0 if os.environ.get("ATDN_GRU_H32") == "1" else L.F_H16
 
 
 def _halo(cout, taps=(3, 3)):
@@ -211,6 +214,8 @@ class _Plan:
         h8, w8 = self.h8, self.w8
         self.hx = f16(b, h8, w8, 512)
         self.h32 = ops.state_alloc(b, h8, w8, dev)     # tiled fp32 state layout (csrc/tc_epilogue.cuh)
+        if _H16:
+            self.h32 = self.h32.half()
         self.z32 = ops.state_alloc(b, h8, w8, dev)
         self.z = self.z32.half() if _Z16 else self.z32     # update gate, fp16 in the same tiled index space (ATDN_F_Z16)
         # context part of the GRU gate convolutions per GRU half: [z | r] and q, tiled like h32, fp16 (one rounding of a
@@ -409,7 +414,7 @@ class RAFTGMA(nn.Module):
 
         # context network: net = tanh(.) -> HX[0:128] + h32, inp = relu(.) -> HX[128:256]
         hx = plan.hx
-        self._encoder(plan, wts.cnet, image1, View(hx, 0, 256), final_flags=L.F_TANH_LO, h32=plan.h32)
+        self._encoder(plan, wts.cnet, image1, View(hx, 0, 256), final_flags=L.F_TANH_LO | _H16, h32=plan.h32)
 
         if wts.gru_pre:
             per_buf = plan.z32.numel()
@@ -484,9 +489,9 @@ class RAFTGMA(nn.Module):
         for i, ((zr, q), taps, pad) in enumerate(((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0)))):
             if wts.gru_pre:   # contract [h | mf | mfg] only; the context term comes from plan.pre_*
                 _conv_s1(View(hx, 0, 128), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, a2=View(hx, 256, 256), h32=plan.h32,
-                         z32=plan.z, rh16=plan.rh, aux32=plan.pre_zr[i], aux_half_offset=plan.z32.numel(), flags=_PRE16 | _Z16)
+                         z32=plan.z, rh16=plan.rh, aux32=plan.pre_zr[i], aux_half_offset=plan.z32.numel(), flags=_PRE16 | _Z16 | _H16)
                 _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 256, 256),
-                         h32=plan.h32, z32=plan.z, aux32=plan.pre_q[i], flags=_PRE16 | _Z16)
+                         h32=plan.h32, z32=plan.z, aux32=plan.pre_q[i], flags=_PRE16 | _Z16 | _H16)
             else:
                 _conv_s1(View(hx), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, h32=plan.h32, z32=plan.z32, rh16=plan.rh)
                 _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 128, 384),

@@ -176,7 +176,7 @@ def state_from_nhwc(x):
 def state_to_nhwc(t, h, w):
     """Tiled state buffer -> [B, h, w, 128] fp32."""
     b, th, tw = t.shape[:3]
-    x = t.view(b, th, tw, 4, 32, 4, 8, 4).permute(0, 1, 3, 5, 2, 6, 4, 7).reshape(b, th * 16, tw * 8, 128)
+    x = t.float().view(b, th, tw, 4, 32, 4, 8, 4).permute(0, 1, 3, 5, 2, 6, 4, 7).reshape(b, th * 16, tw * 8, 128)
     return x[:, :h, :w].contiguous()
 
 

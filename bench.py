@@ -180,6 +180,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")      # its banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L.check(L.load().atdn_check_device(local), "atdn_check_device")
 

@@ -88,6 +88,8 @@ enum {
                             elements).  Halves the per-iteration epilogue traffic of the context term               */
   ATDN_F_Z16       = 1024, /* GRU_ZR / GRU_Q: z32 points to fp16 (same tiled index space): the update gate lies in (0, 1), its fp16
                              rounding (2.4e-4 absolute) is below the fp16 rounding of the hidden state it blends        */
+  ATDN_F_H16       = 2048, /* h32 points to fp16 (same tiled index space): the hidden state has no fp32 master copy, as in the
+                             reference's own fp16-autocast path (GRU_ZR / GRU_Q / STORE16|TANH_LO)                      */
   ATDN_F_STATS     = 128, /* STORE16 on the halo kernel with mt = 4, bn = 64 (n_valid = 64): per-channel partial sums of
                             (acc + bias) and its square over the in-image pixels each epilogue warp sees in one tile go to
                             aux32 as [batch, parts, 64, 2] fp32, parts = ceil(H/16) * ceil(W/(32*cl)) * cl * 4 (cl = 2 with

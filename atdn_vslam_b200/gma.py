@@ -213,16 +213,17 @@ class _Plan:
         self.enc = {}          # encoder scratch keyed by number of images
         h8, w8 = self.h8, self.w8
         self.hx = f16(b, h8, w8, 512)
-        self.h32 = ops.state_alloc(b, h8, w8, dev)     # tiled fp32 state layout (csrc/tc_epilogue.cuh)
-        if _H16:
-            self.h32 = self.h32.half()
-        self.z32 = ops.state_alloc(b, h8, w8, dev)
-        self.z = self.z32.half() if _Z16 else self.z32     # update gate, fp16 in the same tiled index space (ATDN_F_Z16)
+        # recurrent state in the tiled layout of csrc/tc_epilogue.cuh: hidden state h, update gate z (fp16 by default)
+        st = ops.state_alloc(b, h8, w8, dev)
+        self.state_numel = st.numel()
+        self.h32 = st.half() if _H16 else st
+        self.z = torch.empty_like(st, dtype=torch.float16) if _Z16 else torch.empty_like(st)
+        self.z32 = self.z                       # (name kept for the fp32 variant and the tests)
         # context part of the GRU gate convolutions per GRU half: [z | r] and q, tiled like h32, fp16 (one rounding of a
         # pre-activation: the same size as the fp16 rounding of the conv operands) unless ATDN_GRU_PRE32=1
         pdt = torch.float32 if _GRU_PRE32 else torch.float16
-        self.pre_zr = [torch.empty((2,) + tuple(self.z32.shape), dtype=pdt, device=dev) for _ in range(2)]
-        self.pre_q = [torch.empty(tuple(self.z32.shape), dtype=pdt, device=dev) for _ in range(2)]
+        self.pre_zr = [torch.empty((2,) + tuple(st.shape), dtype=pdt, device=dev) for _ in range(2)]
+        self.pre_q = [torch.empty(tuple(st.shape), dtype=pdt, device=dev) for _ in range(2)]
         self.rh = f16(b, h8, w8, 128)
         self.pyr = ops.alloc_pyramid(b, h8, w8, dev, half_levels=4)
         self.qk = f16(b, h8, w8, 256)
@@ -417,7 +418,7 @@ class RAFTGMA(nn.Module):
         self._encoder(plan, wts.cnet, image1, View(hx, 0, 256), final_flags=L.F_TANH_LO | _H16, h32=plan.h32)
 
         if wts.gru_pre:
-            per_buf = plan.z32.numel()
+            per_buf = plan.state_numel
             for i, (taps, pad) in enumerate((((1, 5), (0, 2)), ((5, 1), (2, 0)))):
                 zr, q = wts.gru_pre[i]
                 _conv_s1(View(hx, 128, 128), zr, View(plan.pre_zr[i].view(-1, 1, 1, 8)), cout=256, taps=taps, epi=L.EPI_STORE32,
@@ -489,13 +490,14 @@ class RAFTGMA(nn.Module):
         for i, ((zr, q), taps, pad) in enumerate(((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0)))):
             if wts.gru_pre:   # contract [h | mf | mfg] only; the context term comes from plan.pre_*
                 _conv_s1(View(hx, 0, 128), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, a2=View(hx, 256, 256), h32=plan.h32,
-                         z32=plan.z, rh16=plan.rh, aux32=plan.pre_zr[i], aux_half_offset=plan.z32.numel(), flags=_PRE16 | _Z16 | _H16)
+                         z32=plan.z, rh16=plan.rh, aux32=plan.pre_zr[i], aux_half_offset=plan.state_numel, flags=_PRE16 | _Z16 | _H16)
                 _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 256, 256),
                          h32=plan.h32, z32=plan.z, aux32=plan.pre_q[i], flags=_PRE16 | _Z16 | _H16)
             else:
-                _conv_s1(View(hx), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, h32=plan.h32, z32=plan.z32, rh16=plan.rh)
+                _conv_s1(View(hx), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, h32=plan.h32, z32=plan.z, rh16=plan.rh,
+                         flags=_Z16 | _H16)
                 _conv_s1(View(plan.rh), q, View(hx, 0, 128), cout=128, taps=taps, epi=L.EPI_GRU_Q, a2=View(hx, 128, 384),
-                         h32=plan.h32, z32=plan.z32)
+                         h32=plan.h32, z32=plan.z, flags=_Z16 | _H16)
         c = wts.fh1
         _conv_s1(View(hx, 0, 128), c, View(plan.fh), cout=256, taps=(3, 3), flags=R)
         c = wts.fh2   # flow_head.conv2 + coords update (network.py:111,116): per-tap 1x1 products, then the shifted sum

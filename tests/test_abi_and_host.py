@@ -196,3 +196,19 @@ def test_tiled_pyramid_layout_matches_the_header_formula():
     for got, ref in zip(ops.pyramid_untile(levels, h8, w8), refs):
         assert torch.equal(got, ref)
     assert ops.stats_parts(188, 616, True) == 12 * 10 * 2 * 4 and ops.stats_parts(188, 616, False) == 12 * 20 * 4
+
+
+def test_flag_and_epilogue_constants_match_header(tmp_path):
+    """_lib.py mirrors the enums of include/atdn_b200.h by value (ctypes has no access to C enums)."""
+    names = ["ATDN_EPI_STORE16", "ATDN_EPI_STORE32", "ATDN_EPI_CORR", "ATDN_EPI_GRU_ZR", "ATDN_EPI_GRU_Q", "ATDN_EPI_PV", "ATDN_EPI_FLOW",
+             "ATDN_F_RELU", "ATDN_F_RESID", "ATDN_F_FLOWTAIL", "ATDN_F_TANH_LO", "ATDN_F_B_BATCHED", "ATDN_F_A_SHARED", "ATDN_F_PAIR",
+             "ATDN_F_STATS", "ATDN_F_TILED32", "ATDN_F_PRE16", "ATDN_F_Z16", "ATDN_F_H16", "ATDN_MODE_ROWS", "ATDN_MODE_PATCH"]
+    src = tmp_path / "en.c"
+    src.write_text('#include <stdio.h>\n#include "atdn_b200.h"\nint main(){printf("' + " ".join(["%d"] * len(names)) + '\\n", ' +
+                   ", ".join(f"(int){n}" for n in names) + ");return 0;}\n")
+    exe = tmp_path / "en"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    vals = dict(zip(names, map(int, subprocess.check_output([str(exe)]).split())))
+    for n, v in vals.items():
+        py = n.replace("ATDN_", "")
+        assert getattr(L, py) == v, (n, v, getattr(L, py))

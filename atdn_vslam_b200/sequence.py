@@ -28,6 +28,19 @@ def shard_ranges(num_pairs, world):
     return out
 
 
+def batch_ranges(num_pairs, batch_pairs, short_first=False):
+    """Pair ranges [start, end) of the batches of one rank.  ``short_first``: the first batch of a streamed (host
+    frames) run cannot overlap its own host->device copy, so it is a quarter batch -- the start-up bubble is the copy of
+    ~batch_pairs/4 frames instead of a whole batch."""
+    first = max(1, batch_pairs // 4) if (short_first and num_pairs > batch_pairs) else batch_pairs
+    out, s = [], 0
+    while s < num_pairs:
+        e = min(num_pairs, s + (first if s == 0 else batch_pairs))
+        out.append((s, e))
+        s = e
+    return out
+
+
 def gather_features(local, num_pairs, group=None):
     """All-gather variable-length [p_r, D] shards (contiguous ranges of ``shard_ranges``) into [P, D]."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -96,12 +109,7 @@ class OdometryPipeline:
             return self._pair_features_streamed(frames)
         frames = preprocess(frames)
         t = frames.shape[0]
-        feats = []
-        s = 0
-        while s < t - 1:
-            e = min(t - 1, s + self.batch_pairs)
-            feats.append(self._batch(frames[s:e + 1]))
-            s = e
+        feats = [self._batch(frames[s:e + 1]) for s, e in batch_ranges(t - 1, self.batch_pairs)]
         return torch.cat(feats, 0) if feats else torch.empty(0, 512, device=frames.device)
 
     def _pair_features_streamed(self, host_frames):
@@ -117,14 +125,7 @@ class OdometryPipeline:
             self._staging = [torch.empty((nb,) + tuple(host_frames.shape[1:]), dtype=host_frames.dtype, device=dev) for _ in range(2)]
             self._staging_key = key
         main = torch.cuda.current_stream(dev)
-        # the first batch cannot overlap its own host->device copy: keep it short (a quarter batch), so that the
-        # start-up bubble is the copy of ~batch_pairs/4 frames instead of a whole batch
-        ranges, s = [], 0
-        first = max(1, self.batch_pairs // 4) if t - 1 > self.batch_pairs else self.batch_pairs
-        while s < t - 1:
-            e = min(t - 1, s + (first if s == 0 else self.batch_pairs))
-            ranges.append((s, e))
-            s = e
+        ranges = batch_ranges(t - 1, self.batch_pairs, short_first=True)
         ready = [torch.cuda.Event() for _ in ranges]
         consumed = [torch.cuda.Event() for _ in ranges]
 

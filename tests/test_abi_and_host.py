@@ -212,3 +212,15 @@ def test_flag_and_epilogue_constants_match_header(tmp_path):
     for n, v in vals.items():
         py = n.replace("ATDN_", "")
         assert getattr(L, py) == v, (n, v, getattr(L, py))
+
+
+def test_batch_ranges_cover_every_pair_once():
+    from atdn_vslam_b200.sequence import batch_ranges
+    assert batch_ranges(270, 54) == [(0, 54), (54, 108), (108, 162), (162, 216), (216, 270)]
+    assert batch_ranges(270, 54, short_first=True) == [(0, 13), (13, 67), (67, 121), (121, 175), (175, 229), (229, 270)]
+    assert batch_ranges(5, 54, short_first=True) == [(0, 5)]            # a single batch is never split
+    assert batch_ranges(0, 8) == [] and batch_ranges(3, 2, short_first=True) == [(0, 1), (1, 3)]
+    for n, b, sf in [(4540, 54, True), (271, 27, False), (7, 3, True), (1, 1, True)]:
+        r = batch_ranges(n, b, sf)
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == c[0] for a, c in zip(r, r[1:]))
+        assert all(0 < e - s <= b for s, e in r)

@@ -224,3 +224,42 @@ def test_batch_ranges_cover_every_pair_once():
         r = batch_ranges(n, b, sf)
         assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == c[0] for a, c in zip(r, r[1:]))
         assert all(0 < e - s <= b for s, e in r)
+
+
+def test_flow_head_tap_decomposition_identity():
+    """flow_head.conv2 as '1x1 conv to 18 per-tap products + shifted sum' (gma._Packed.fh2, atdn_flow_head_gather) is the
+    3x3 convolution with zero padding: checked in plain PyTorch on the weight layout the product packs."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    b, c, h, w = 2, 256, 9, 11
+    x = torch.randn(b, c, h, w, generator=g, dtype=torch.float64)
+    w2 = torch.randn(2, c, 3, 3, generator=g, dtype=torch.float64)
+    bias = torch.randn(2, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w2, bias, padding=1)
+    w18 = w2.permute(2, 3, 0, 1).reshape(18, c)                       # row = (dy*3 + dx)*2 + co, as in gma._Packed
+    d = torch.einsum("rc,bchw->bhwr", w18, x)                          # the 1x1 tensor-core conv: d[b, y, x, tap*2 + co]
+    out = bias.view(1, 2, 1, 1).repeat(b, 1, h, w).clone()
+    for tap in range(9):
+        dy, dx = tap // 3 - 1, tap % 3 - 1
+        for co in range(2):
+            src = d[..., tap * 2 + co]
+            ys, xs = slice(max(0, -dy), h - max(0, dy)), slice(max(0, -dx), w - max(0, dx))       # destination pixels p
+            yq, xq = slice(max(0, dy), h + min(0, dy)), slice(max(0, dx), w + min(0, dx))         # neighbours p + off(tap)
+            out[:, co, ys, xs] += src[:, yq, xq]
+    assert (out - ref).abs().max() < 1e-10
+
+
+def test_gru_context_precompute_identity():
+    """conv(W, [h | inp | mf | mfg]) = conv(W[:, rest], [h | mf | mfg]) + conv(W[:, 128:256], inp): the split the product
+    uses to take the context features out of the per-iteration SepConvGRU convolutions (gma._Packed.gru / gru_pre)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(4)
+    hx = torch.randn(1, 512, 6, 12, generator=g, dtype=torch.float64)
+    for cout, k, pad in ((256, (1, 5), (0, 2)), (128, (5, 1), (2, 0))):
+        wt = torch.randn(cout, 512, *k, generator=g, dtype=torch.float64)
+        bias = torch.randn(cout, generator=g, dtype=torch.float64)
+        full = F.conv2d(hx, wt, bias, padding=pad)
+        rest_w = torch.cat([wt[:, :128], wt[:, 256:]], 1)
+        rest_x = torch.cat([hx[:, :128], hx[:, 256:]], 1)
+        pre = F.conv2d(hx[:, 128:256], wt[:, 128:256], bias, padding=pad)
+        assert (F.conv2d(rest_x, rest_w, None, padding=pad) + pre - full).abs().max() < 1e-9

@@ -408,9 +408,10 @@ def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shif
 
     def pitch(t):
         """Row pitch of an NCHW map that is dense except for padded rows (a [..., :w] view of a wider buffer)."""
-        bb, cc, hh, _ = t.shape
-        pt = t.stride(2)
-        assert t.stride(3) == 1 and t.stride(1) == hh * pt and t.stride(0) == cc * hh * pt, "unsupported strides"
+        bb, cc, hh, ww = t.shape
+        pt = t.stride(2) if hh > 1 else ww          # strides of size-1 dimensions carry no information
+        assert (ww == 1 or t.stride(3) == 1) and (cc == 1 or t.stride(1) == hh * pt) and (bb == 1 or t.stride(0) == cc * hh * pt), \
+            "unsupported strides"
         return pt
     d.x, d.y, d.w, d.bias = L.ptr(x), L.ptr(y), L.ptr(w), L.ptr(bias)
     d.in_scale, d.in_shift, d.skip = L.ptr(in_scale), L.ptr(in_shift), L.ptr(skip)

@@ -399,6 +399,16 @@ def coords_init(coords1, flow, flow_init=None):
 # ----------------------------------------------------------------------------------------------
 # fp32 small nets
 # ----------------------------------------------------------------------------------------------
+def nchw_pitch(t):
+    """Row pitch of an NCHW map that is dense except for padded rows (a [..., :w] view of a wider buffer)."""
+    bb, cc, hh, ww = t.shape
+    # strides of size-1 dimensions carry no information: take the pitch from the first dimension that has one
+    pt = t.stride(2) if hh > 1 else t.stride(1) if cc > 1 else t.stride(0) if bb > 1 else ww
+    assert pt >= ww and (ww == 1 or t.stride(3) == 1) and (cc == 1 or t.stride(1) == hh * pt) and \
+        (bb == 1 or t.stride(0) == cc * hh * pt), "unsupported strides"
+    return pt
+
+
 @_profiled
 def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shift=None, skip=None, bn_scale=None,
            bn_shift=None, bn2_scale=None, bn2_shift=None):
@@ -406,13 +416,7 @@ def conv32(x, w, bias, y, *, stride=1, pad=0, mish=False, in_scale=None, in_shif
     b, cin, h, wd = x.shape
     cout, _, k, _ = w.shape
 
-    def pitch(t):
-        """Row pitch of an NCHW map that is dense except for padded rows (a [..., :w] view of a wider buffer)."""
-        bb, cc, hh, ww = t.shape
-        pt = t.stride(2) if hh > 1 else ww          # strides of size-1 dimensions carry no information
-        assert (ww == 1 or t.stride(3) == 1) and (cc == 1 or t.stride(1) == hh * pt) and (bb == 1 or t.stride(0) == cc * hh * pt), \
-            "unsupported strides"
-        return pt
+    pitch = nchw_pitch
     d.x, d.y, d.w, d.bias = L.ptr(x), L.ptr(y), L.ptr(w), L.ptr(bias)
     d.in_scale, d.in_shift, d.skip = L.ptr(in_scale), L.ptr(in_shift), L.ptr(skip)
     d.bn_scale, d.bn_shift = L.ptr(bn_scale), L.ptr(bn_shift)

@@ -263,3 +263,21 @@ def test_gru_context_precompute_identity():
         rest_x = torch.cat([hx[:, :128], hx[:, 256:]], 1)
         pre = F.conv2d(hx[:, 128:256], wt[:, 128:256], bias, padding=pad)
         assert (F.conv2d(rest_x, rest_w, None, padding=pad) + pre - full).abs().max() < 1e-9
+
+
+def test_nchw_pitch_of_padded_and_degenerate_maps():
+    """ops.nchw_pitch: the row pitch of CLVO maps that live in row-padded buffers (154 -> 156 floats); size-1
+    dimensions have arbitrary strides in torch and must not decide (or fail) the check."""
+    from atdn_vslam_b200 import ops
+    buf = torch.zeros(2, 3, 5, 156)
+    assert ops.nchw_pitch(buf) == 156
+    assert ops.nchw_pitch(buf[..., :154]) == 156
+    assert ops.nchw_pitch(torch.zeros(2, 3, 1, 156)[..., :154]) == 156          # H == 1: pitch from the channel stride
+    assert ops.nchw_pitch(torch.zeros(2, 1, 1, 156)[..., :154]) == 156          # H == C == 1: from the batch stride
+    assert ops.nchw_pitch(torch.zeros(1, 1, 1, 156)[..., :154]) == 154          # nothing to contradict a dense row
+    assert ops.nchw_pitch(torch.zeros(1, 16, 5, 8).as_strided((1, 16, 5, 8), (12345, 40, 8, 1))) == 8   # B == 1
+    assert ops.nchw_pitch(torch.zeros(4, 512, 1, 1)) == 1
+    with pytest.raises(AssertionError):
+        ops.nchw_pitch(torch.zeros(2, 3, 5, 8).permute(0, 1, 3, 2))            # transposed rows
+    with pytest.raises(AssertionError):
+        ops.nchw_pitch(torch.zeros(2, 6, 5, 8)[:, ::2])                        # channel gaps

@@ -120,19 +120,31 @@ class KeyframeIndex:
     def search_sharded(self, code, group=None):
         """Every rank holds a row shard; returns the GLOBAL arg-min (lowest global index on ties).
         Global index = sum of lower ranks' sizes + local index (contiguous row sharding)."""
-        import torch.distributed as dist
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        sizes = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([self._n], dtype=torch.int64, device=self.device), group=group)
-        offset = int(sum(int(s.item()) for s in sizes[:rank]))
         if self._n > 0:
             idx, d = self.search_device(code)
-            best = torch.stack([d[idx.long()].reshape(()).double(), (idx.long() + offset).reshape(()).double()])
+            local = (d[idx.long()].reshape(()), idx.long().reshape(()))
         else:
-            best = torch.tensor([float("inf"), -1.0], dtype=torch.float64, device=self.device)
-        allb = [torch.zeros(2, dtype=torch.float64, device=self.device) for _ in range(world)]
-        dist.all_gather(allb, best, group=group)
-        return merge_shard_minima([(float(t[0]), int(t[1])) for t in allb])
+            local = None
+        return global_first_minimum(local, self._n, self.device, group)
+
+
+def global_first_minimum(local, n_local, device, group=None):
+    """Exchange step of the sharded keyframe search: ``local`` = (distance, local index) 0-d tensors of
+    this rank's first minimum (None for an empty shard), ``n_local`` = rows in this rank's shard.  Two small all-gathers
+    (shard sizes, then one (distance, global index) pair per rank); every rank returns the same
+    (global index, distance) with the lowest global index on ties, like the reference's serial loop."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([n_local], dtype=torch.int64, device=device), group=group)
+    offset = int(sum(int(s.item()) for s in sizes[:rank]))
+    if local is not None and n_local > 0:
+        best = torch.stack([local[0].double(), (local[1] + offset).double()]).to(device)
+    else:
+        best = torch.tensor([float("inf"), -1.0], dtype=torch.float64, device=device)
+    allb = [torch.zeros(2, dtype=torch.float64, device=device) for _ in range(world)]
+    dist.all_gather(allb, best, group=group)
+    return merge_shard_minima([(float(t[0]), int(t[1])) for t in allb])
 
 
 class Relocalizer:

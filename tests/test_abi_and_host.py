@@ -142,6 +142,55 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_search_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from atdn_vslam_b200.localization import global_first_minimum
+    from oracle import clvo_oracle
+    g = torch.Generator().manual_seed(7)
+    db = torch.randn(11, 32, generator=g)
+    db[9] = db[2]                                   # planted duplicate: rows 2 (rank 0) and 9 (rank 1) tie
+    code = db[2] + 0.0
+    bounds = [(0, 6), (6, 11)]
+    out = []
+    for case in range(3):
+        if case == 1:                               # the minimum lives on the last rank only
+            code = db[10] + 0.0
+        if case == 2:                               # rank 0 holds nothing
+            bounds = [(0, 0), (0, 11)]
+        s, e = bounds[rank]
+        if e > s:
+            k, d = clvo_oracle.keyframe_search(db[s:e], code)      # stand-in for the local CUDA search
+            local = (d[k].reshape(()), torch.tensor(k))
+        else:
+            local = None
+        gi, gd = global_first_minimum(local, e - s, torch.device("cpu"))
+        ok, od = clvo_oracle.keyframe_search(db, code)
+        out.append((gi, ok, abs(gd - float(od[ok])) < 1e-6))
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_sharded_keyframe_minimum_world2_gloo():
+    """Exchange step of the sharded search (localization.global_first_minimum) == the serial first minimum."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_search_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, out in res:
+        assert [o[0] for o in out] == [2, 10, 10]
+        assert all(o[0] == o[1] and o[2] for o in out)
+
+
 def test_feature_gather_world2_gloo():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")

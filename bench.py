@@ -9,6 +9,8 @@ BASELINE.json configs[1]); ranks process independent sequence shards (weak scali
 the [270,512] CLVO features (NCCL all-gather) before the serial LSTM scan.  `value` times the step
 with frames resident in HBM; `e2e` times the public API with frames in pinned HOST memory (H2D of
 the frames and D2H of the relative poses inside the timed region, plus the host pose chain).
+`online_b1` (extra key, rank 0) is the wall-clock latency of the reference's per-frame loop shape
+(one pair per call through the drop-in forward()s, host read after every frame, neural_slam.py:202-204).
 
 `--impl reference`: /root/reference does not exist on the GPU box and the reference is pure Python,
 so this arm times the oracle port of the reference's device=cpu path (oracle/) on the host cores.
@@ -167,6 +169,29 @@ class KernelProfile:
         return agg
 
 
+def online_latency(flow, vo, dev_frames, reps=10, warm=2):
+    """Wall-clock time per frame of the reference's online loop shape: flow_net(im1, im2, iters=12, test_mode=True) ->
+    odometry_net(flow) -> host read of (rot, tr), batch 1, frames already on the device at the SLAM size."""
+    reps = max(1, min(reps, dev_frames.shape[0] - 1 - warm))
+    vo.reset_lstm()
+
+    def frame(t):
+        _, up = flow(dev_frames[t:t + 1], dev_frames[t + 1:t + 2], iters=12, test_mode=True)
+        rot, tr = vo(up)
+        return rot.cpu(), tr.cpu()
+
+    for t in range(warm):
+        frame(t)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(warm, warm + reps):
+        frame(t)
+    dt = (time.perf_counter() - t0) / reps
+    vo.reset_lstm()
+    return {"ms_per_pair": 1e3 * dt, "pairs_per_s": 1.0 / dt, "pairs": reps,
+            "note": "batch 1, eager launches, host sync per frame (wall clock); the metric above batches 54 pairs"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from atdn_vslam_b200 import _lib as L, synth
@@ -322,6 +347,12 @@ def run_ours(args):
                                 "algorithmic_bytes_per_launch": a["bytes"] / a["launches"], "launches": a["launches"]}
         if traffic_note:
             line["roofline"]["traffic_note"] = traffic_note
+        # ---- online call pattern of NeuralSLAM.__call__ (neural_slam.py:202-204): ONE pair per call through the drop-in
+        # forward()s, eager launches, relative pose read back on the host after every frame.  Latency, not the metric.
+        try:
+            line["online_b1"] = online_latency(flow, vo, dev_frames)
+        except Exception as exc:   # an extra: never lose the bench line over it
+            line["online_b1"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         # ---- CPU baseline (oracle port of the reference device=cpu path) on a bounded sample
         if world == 1 and not args.no_cpu_baseline:
             v, dt = cpu_pairs_per_s(args.cpu_pairs, warm=1)

@@ -103,7 +103,7 @@ def cpu_pairs_per_s(num_pairs, warm=1):
     state = clvo_oracle.zero_state()
 
     def pair(t):
-        _, up = gma_oracle.raftgma_forward(gsd, frames[t:t + 1], frames[t + 1:t + 2], iters=12)
+        _, up = gma_oracle.raftgma_forward(gsd, frames[t:t + 1], frames[t + 1:t + 2], iters=12, aten_ops=True)
         return clvo_oracle.atdnvo_forward(vsd, up, state)
 
     for t in range(warm):

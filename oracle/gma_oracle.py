@@ -138,6 +138,41 @@ def corr_lookup(pyramid, coords, radius=4):
     return out.permute(0, 3, 1, 2).contiguous().float()
 
 
+def corr_pyramid_aten(fmap1, fmap2, num_levels=4):
+    """corr.py:16-30 with the SAME ATen ops the reference calls (``avg_pool2d`` on the [B*N,1,H,W] volume) -- the form
+    the CPU baseline is timed on, so that the port is not slower than the reference; equal to :func:`corr_pyramid`
+    (checked in tests/test_oracle_golden.py).  Levels are returned as [B, N, Hl, Wl] views."""
+    lvl = corr_volume(fmap1, fmap2)
+    b, n, h, w = lvl.shape
+    flat = lvl.reshape(b * n, 1, h, w)
+    pyr = [lvl]
+    for _ in range(num_levels - 1):
+        flat = F.avg_pool2d(flat, 2, stride=2)
+        pyr.append(flat.reshape(b, n, flat.shape[-2], flat.shape[-1]))
+    return pyr
+
+
+def corr_lookup_aten(pyramid, coords, radius=4):
+    """corr.py:32-53 + utils.py:59-73 through ``F.grid_sample`` (bilinear, zeros padding, align_corners=True), the op
+    the reference itself calls; same result as the explicit gather of :func:`corr_lookup` up to fp32 rounding of the
+    normalise / de-normalise round trip.  Used for the timed CPU baseline."""
+    bsz, _, h1, w1 = coords.shape
+    n = h1 * w1
+    k = 2 * radius + 1
+    d = torch.arange(-radius, radius + 1, dtype=coords.dtype)
+    centre = coords.permute(0, 2, 3, 1).reshape(bsz * n, 1, 1, 2)
+    # window offset [a, b] -> (x + d[a], y + d[b]): the slow window index offsets x (see corr_lookup)
+    offs = torch.stack([d.view(k, 1).expand(k, k), d.view(1, k).expand(k, k)], dim=-1).view(1, k, k, 2)
+    out = []
+    for lvl, corr in enumerate(pyramid):
+        hl, wl = corr.shape[-2:]
+        pos = centre / (2 ** lvl) + offs
+        grid = torch.stack([2 * pos[..., 0] / (wl - 1) - 1, 2 * pos[..., 1] / (hl - 1) - 1], dim=-1)
+        smp = F.grid_sample(corr.reshape(bsz * n, 1, hl, wl), grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+        out.append(smp.reshape(bsz, h1, w1, k * k))
+    return torch.cat(out, dim=-1).permute(0, 3, 1, 2).contiguous().float()
+
+
 def coords_grid(batch, ht, wd):
     """utils.py:76-79: channel 0 = x (column index), channel 1 = y (row index)."""
     ys, xs = torch.meshgrid(torch.arange(ht), torch.arange(wd), indexing="ij")
@@ -219,9 +254,11 @@ def upsample_flow(flow, mask):
 # ----------------------------------------------------------------------------------------------
 # whole network -- network.py:72-129
 # ----------------------------------------------------------------------------------------------
-def raftgma_forward(sd, image1, image2, iters=12, flow_init=None, test_mode=True, return_intermediates=False):
+def raftgma_forward(sd, image1, image2, iters=12, flow_init=None, test_mode=True, return_intermediates=False, aten_ops=False):
     """Reference ``RAFTGMA.forward`` on the fp32 CPU path.  ``test_mode`` returns
-    (coords1 - coords0, flow_up); otherwise the list of per-iteration ``flow_up``."""
+    (coords1 - coords0, flow_up); otherwise the list of per-iteration ``flow_up``.
+    ``aten_ops``: pyramid and lookup through ``avg_pool2d`` / ``grid_sample`` like the reference (the timed CPU
+    baseline) instead of the explicit restatements (the checker)."""
     sd = _strip(sd)
     with torch.no_grad():
         im1 = (2 * (image1.float() / 255.0) - 1.0).contiguous()
@@ -229,7 +266,8 @@ def raftgma_forward(sd, image1, image2, iters=12, flow_init=None, test_mode=True
         b = im1.shape[0]
         fm = basic_encoder(torch.cat([im1, im2], 0), sd, "fnet.", "instance")
         fmap1, fmap2 = fm[:b].float(), fm[b:].float()
-        pyr = corr_pyramid(fmap1, fmap2)
+        pyr = (corr_pyramid_aten if aten_ops else corr_pyramid)(fmap1, fmap2)
+        lookup = corr_lookup_aten if aten_ops else corr_lookup
         cnet = basic_encoder(im1, sd, "cnet.", "batch")
         net, inp = torch.split(cnet, [128, 128], dim=1)
         net = torch.tanh(net)
@@ -243,7 +281,7 @@ def raftgma_forward(sd, image1, image2, iters=12, flow_init=None, test_mode=True
         preds = []
         inter = {"fmap1": fmap1, "fmap2": fmap2, "net0": net, "inp": inp, "corr": [], "delta": []}
         for _ in range(iters):
-            corr = corr_lookup(pyr, coords1)
+            corr = lookup(pyr, coords1)
             flow = coords1 - coords0
             net, mask, delta = update_block(net, inp, corr, flow, attn, sd)
             coords1 = coords1 + delta

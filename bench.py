@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--batch-pairs", type=int, default=54)
-    ap.add_argument("--cpu-pairs", type=int, default=6)
+    ap.add_argument("--cpu-pairs", type=int, default=12)
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -1,10 +1,12 @@
 // Gather / element-wise kernels of the GMA flow path (HBM- or latency-bound, CUDA cores).
 // See include/atdn_b200.h for the reference call sites each entry point replaces.
 #include <math.h>
+#include <stdlib.h>
 
 #include <cuda_fp16.h>
 
 #include "common.h"
+#include "corr_lookup_v2.cuh"
 
 namespace atdn {
 
@@ -851,7 +853,29 @@ extern "C" int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitc
     p.tiles = ((h8 + 7) / 8) * p.tiles_w;
     p.h0 = h8;
     p.w0 = w8;
-    corr_lookup_half_kernel<<<grid, kLkWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(p, coords, static_cast<__half*>(out16), out_pitch, out32, nq);
+    static const bool use_v2 = [] { const char* e = getenv("ATDN_LOOKUP_V2"); return e && e[0] == '1'; }();
+    if (use_v2 && out16 && !out32) {
+      // experimental CTA-of-32-queries layout (corr_lookup_v2.cuh): same fp16 results, ~2.3x fewer instructions; opt-in
+      // until it has been timed on a GPU
+      lk2::Params v;
+      for (int l = 0; l < 4; ++l) v.lvl[l] = p.lvl[l];
+      v.tiles = p.tiles;
+      v.tiles_w = p.tiles_w;
+      v.h0 = h8;
+      v.w0 = w8;
+      v.coords = coords;
+      v.out16 = static_cast<__half*>(out16);
+      v.out_pitch = out_pitch;
+      v.nq = nq;
+      static bool configured = false;
+      if (!configured) {
+        ATDN_CUDA(cudaFuncSetAttribute(lk2::corr_lookup_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lk2::kSmemBytes));
+        configured = true;
+      }
+      lk2::corr_lookup_v2_kernel<<<static_cast<unsigned>((nq + lk2::kQ - 1) / lk2::kQ), lk2::kThreads, lk2::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(v);
+    } else {
+      corr_lookup_half_kernel<<<grid, kLkWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(p, coords, static_cast<__half*>(out16), out_pitch, out32, nq);
+    }
   } else {
     LookupParams p;
     int h = h8;

@@ -330,3 +330,19 @@ def test_nchw_pitch_of_padded_and_degenerate_maps():
         ops.nchw_pitch(torch.zeros(2, 3, 5, 8).permute(0, 1, 3, 2))            # transposed rows
     with pytest.raises(AssertionError):
         ops.nchw_pitch(torch.zeros(2, 6, 5, 8)[:, ::2])                        # channel gaps
+
+
+def test_lookup_v2_kernel_logic_on_the_host(tmp_path):
+    """The opt-in lookup kernel (csrc/corr_lookup_v2.cuh, ATDN_LOOKUP_V2=1) is written as host/device phase functions;
+    tools/lookup_v2_emulate.cu runs them thread by thread on the CPU and compares the fp16 output bit for bit with
+    the formulas of the shipped kernel and, within fp16 rounding, with a 4-tap bilinear sample."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "lookup_v2_emulate")
+    subprocess.check_call([nvcc, "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                           os.path.join(ROOT, "tools", "lookup_v2_emulate.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "all cases match" in out.stdout, out.stdout + out.stderr

@@ -1,0 +1,132 @@
+"""CPU experiment (test infrastructure): could the attention probabilities of the P.V aggregation be stored in fp8?
+
+P.V re-reads the fp16 probabilities 12 times per pair and runs at 93% of the HBM copy bandwidth (DESIGN.md section 6
+item 1); only fewer bytes can make it faster.  tcgen05 kind::f8f6f4 needs BOTH operands in an 8-bit format, so the
+variants quantise P = exp(s - rowmax) (values in (0, 1]) and V = to_v(motion features) inside the fp32 oracle:
+
+    p16/v16      what the CUDA path stores today (P fp16, V fp16)
+    p8/v8        P e4m3, V e4m3
+    p8/v8x2      P e4m3, V = hi + lo with both halves e4m3 (two MMAs per tile, V is 2% of the bytes)
+    p8s/v8x2     the same with P scaled by 448 before rounding (uses e4m3's full exponent range: small probabilities
+                 keep 3 mantissa bits down to 2^-15 instead of going subnormal below 2^-6)
+
+    mixed        per 128 x 64 tile of P: fp16 where any entry exceeds 1/16 of its row maximum ("hot" tiles, MMA kind::f16
+                 with the fp16 V), scaled e4m3 elsewhere (kind::f8f6f4 with V = hi + lo); both accumulate into the same fp32
+                 tile.  Quantisation error scales with the value, so the cold tiles contribute little; the hot fraction
+                 (printed) says how many bytes are saved: bytes = (1 + hot) / 2 of today's.
+    mixed-e      the same with an energy criterion: a tile is hot when sqrt(sum_tile p^2) / sum_row p > 2e-3 for one of its
+                 rows (flat attention -> everything cold, peaked attention -> only the tiles that carry the mass are hot)
+
+The row sum that normalises the output is taken over the ROUNDED probabilities, so the rounding bias cancels.
+The synthetic weights give nearly flat attention; trained GMA attention is peaked, so the logits are sharpened by a
+temperature (q.k scaled) and the effective support n_eff = 1 / sum_j p_ij^2 is reported next to the flow error.
+Reference for every temperature: the fp32 oracle with the same sharpened weights.
+
+    python tools/fp8_attention_sensitivity.py [H W]        (default 376 1232; ~3 s per forward on 8 threads)
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch                                   # noqa: E402
+import torch.nn.functional as F                # noqa: E402
+
+from atdn_vslam_b200 import synth              # noqa: E402
+from oracle import gma_oracle as G             # noqa: E402
+
+torch.set_num_threads(os.cpu_count() or 8)
+torch.set_grad_enabled(False)
+h, w = (376, 1232) if len(sys.argv) < 3 else (int(sys.argv[1]), int(sys.argv[2]))
+fr = synth.frame_sequence(2, h, w, seed=11)
+E4 = torch.float8_e4m3fn
+
+
+def q8(x, scale=1.0):
+    return (x * scale).to(E4).float() / scale
+
+
+def mixed_aggregate(attn, fmap, sd, heads=1, theta=1.0 / 16, tm=128, tn=64, energy=None):
+    b, c, hh, ww = fmap.shape
+    n = hh * ww
+    v = F.conv2d(fmap, sd["update_block.aggregator.to_v.weight"]).reshape(b, 1, c, n).transpose(2, 3)
+    p = attn / attn.amax(dim=-1, keepdim=True)
+    pad_m, pad_n = (-n) % tm, (-n) % tn
+    pp = F.pad(p, (0, pad_n, 0, pad_m))
+    tiles = pp.reshape(b, 1, (n + pad_m) // tm, tm, (n + pad_n) // tn, tn)
+    if energy is None:
+        hot = (tiles.amax(dim=(3, 5), keepdim=True) > theta)
+    else:   # a tile is hot when it holds more than `energy` of some row's probability mass in the L2 sense:
+        # sqrt(sum_{j in tile} p_ij^2) / sum_j p_ij  (the e4m3 rounding error of the tile relative to the row's output)
+        frac = tiles.pow(2).sum(dim=5, keepdim=True).sqrt() / F.pad(p.sum(-1), (0, pad_m), value=1.0).reshape(b, 1, -1, tm, 1, 1)
+        hot = frac.amax(dim=3, keepdim=True) > energy
+    stats["hot"] = float(hot.float().mean())
+    hot_full = hot.expand_as(tiles).reshape(b, 1, n + pad_m, n + pad_n)[:, :, :n, :n]
+    p_hot = torch.where(hot_full, p.half().float(), torch.zeros_like(p))
+    p_cold = torch.where(hot_full, torch.zeros_like(p), q8(p, 448.0))
+    hi = q8(v)
+    out = torch.matmul(p_hot, v.half().float()) + torch.matmul(p_cold, hi) + torch.matmul(p_cold, q8(v - hi))
+    out = out / (p_hot + p_cold).sum(dim=-1, keepdim=True)
+    out = out.transpose(2, 3).reshape(b, c, hh, ww)
+    return fmap + sd["update_block.aggregator.gamma"] * out
+
+
+def make_aggregate(pq, vq):
+    if pq is None:
+        return mixed_aggregate if vq is None else (lambda a, f, sd, heads=1: mixed_aggregate(a, f, sd, heads, energy=vq))
+
+    def aggregate(attn, fmap, sd, heads=1):
+        b, c, hh, ww = fmap.shape
+        v = F.conv2d(fmap, sd["update_block.aggregator.to_v.weight"]).reshape(b, 1, c, hh * ww).transpose(2, 3)
+        p = attn / attn.amax(dim=-1, keepdim=True)                 # exp(s - rowmax), what the kernel stores
+        p = pq(p)
+        out = torch.zeros_like(v)
+        for term in vq(v):
+            out = out + torch.matmul(p, term)
+        out = out / p.sum(dim=-1, keepdim=True)
+        out = out.transpose(2, 3).reshape(b, c, hh, ww)
+        return fmap + sd["update_block.aggregator.gamma"] * out
+    return aggregate
+
+
+def split8(v):
+    hi = q8(v)
+    return [hi, q8(v - hi)]
+
+
+VARIANTS = {
+    "p16/v16": (lambda p: p.half().float(), lambda v: [v.half().float()]),
+    "p8/v8": (q8, lambda v: [q8(v)]),
+    "p8/v8x2": (q8, split8),
+    "p8s/v8x2": (lambda p: q8(p, 448.0), split8),
+    "mixed": (None, None),
+    "mixed-e": (None, 2e-3),
+}
+
+orig_aggregate, orig_attention = G.aggregate, G.attention
+stats = {}
+
+
+def attention_probe(inp, sd, heads=1):
+    a = orig_attention(inp, sd, heads)
+    stats["n_eff"] = float((1.0 / a.pow(2).sum(-1)).mean())
+    stats["p_max"] = float(a.amax(-1).mean())
+    return a
+
+
+G.attention = attention_probe
+print(f"{h}x{w}, N = {(h // 8) * (w // 8)} positions, iters=12, gamma = {float(synth.gma_state_dict()['update_block.aggregator.gamma']):.2f}")
+for temp in (1.0, 3.0, 8.0, 32.0, 128.0):
+    sd = dict(synth.gma_state_dict())
+    sd["att.to_qk.weight"] = sd["att.to_qk.weight"] * (temp ** 0.5)     # q and k both scaled: logits x temp
+    G.aggregate = orig_aggregate
+    t0 = time.time()
+    _, base = G.raftgma_forward(sd, fr[0:1], fr[1:2], iters=12, aten_ops=True)
+    print(f"logit scale {temp:5.0f}: n_eff {stats['n_eff']:8.1f}  mean max-probability {stats['p_max']:.3f}  |flow| {base.abs().mean():.2f} px  ({time.time() - t0:.1f} s)", flush=True)
+    for name, (pq, vq) in VARIANTS.items():
+        G.aggregate = make_aggregate(pq, vq)
+        _, up = G.raftgma_forward(sd, fr[0:1], fr[1:2], iters=12, aten_ops=True)
+        epe = (up - base).pow(2).sum(1).sqrt()
+        extra = f"  hot tiles {100 * stats['hot']:.1f}%" if name.startswith("mixed") else ""
+        print(f"    {name:9s} EPE mean {epe.mean():.3e}  p99 {epe.flatten().quantile(0.99):.3e}  max {epe.max():.3e}{extra}", flush=True)
+G.aggregate, G.attention = orig_aggregate, orig_attention

@@ -192,6 +192,43 @@ def online_latency(flow, vo, dev_frames, reps=10, warm=2):
             "note": "batch 1, eager launches, host sync per frame (wall clock); the metric above batches 54 pairs"}
 
 
+def localization_extras(dev, frame, pk, keyframes=8192, reps=10):
+    """Rows A16/A17 of SURVEY.md section 8 (not part of the odometry step): keyframe embedding latency of one
+    376x1232 frame and the similarity search over a synthetic database that does not fit the L2 (K x 15360 fp32),
+    as achieved HBM GB/s.  CUDA events on the launching stream."""
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.localization import KeyframeIndex, MappingEncoder
+    enc = MappingEncoder()
+    enc.load_state_dict(synth.vae_state_dict())
+    enc = enc.to(dev).eval()
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+
+    mu = enc.embed(frame)
+    embed_ms = timed(lambda: enc.embed(frame))
+    dim = mu[0].numel()
+    index = KeyframeIndex(dim=dim, capacity=keyframes + 1, device=dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    index.add(torch.randn(keyframes, dim, device=dev, generator=g))
+    index.add(mu)                                     # the query's own embedding: the search must return the last row
+    search_ms = timed(lambda: index.search_device(mu))
+    found = int(index.search_device(mu)[0].item())
+    nbytes = float(len(index) * dim * 4)
+    gbs = nbytes / (search_ms * 1e-3) / 1e9
+    return {"embed_ms_per_frame": embed_ms, "embedding_dim": dim,
+            "search": {"keyframes": len(index), "ms": search_ms, "gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"],
+                       "found_planted_row": found == len(index) - 1}}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from atdn_vslam_b200 import _lib as L, synth
@@ -353,6 +390,10 @@ def run_ours(args):
             line["online_b1"] = online_latency(flow, vo, dev_frames)
         except Exception as exc:   # an extra: never lose the bench line over it
             line["online_b1"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        try:
+            line["localization"] = localization_extras(dev, dev_frames[0:1], pk)
+        except Exception as exc:
+            line["localization"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         # ---- CPU baseline (oracle port of the reference device=cpu path) on a bounded sample
         if world == 1 and not args.no_cpu_baseline:
             v, dt = cpu_pairs_per_s(args.cpu_pairs, warm=1)

@@ -356,6 +356,12 @@ def run_ours(args):
                 ent["frac_of_hbm_peak"] = round(ent["gbs"] / pk["hbm_gbs"], 4)
             kernels[label] = ent
         line["kernels"] = kernels
+        # the two kernels BASELINE.json's metric names, against its 60% targets (corr GEMM vs tensor peak, lookup vs HBM)
+        line["north_star_kernels"] = {
+            "corr_pyramid_frac_of_tensor_peak": kernels.get("corr_pyramid", {}).get("frac_of_tensor_peak"),
+            "corr_pyramid_frac_of_hbm_peak": kernels.get("corr_pyramid", {}).get("frac_of_hbm_peak"),
+            "corr_lookup_frac_of_hbm_peak": kernels.get("corr_lookup", {}).get("frac_of_hbm_peak"),
+            "target": 0.6}
         # roofline of the dominant kernel: the binding roofline is the one with the larger time floor for the
         # kernel's algorithmic work (flops / tensor peak vs bytes / HBM peak); kernels inside the long step are
         # compared with the SUSTAINED bf16 peak, HBM with the measured copy bandwidth

@@ -164,6 +164,33 @@ def test_half_level_pyramid_and_lookup(h8, w8, batch):
         assert (got - ref).abs().max() <= 2e-5 * ref.abs().max()
 
 
+@pytest.mark.skipif(__import__("os").environ.get("ATDN_LOOKUP_V2") != "1",
+                    reason="opt-in lookup kernel: run the GPU suite with ATDN_LOOKUP_V2=1 to exercise it")
+@pytest.mark.parametrize("h8,w8,batch", [(47, 154, 2), (47, 156, 1), (16, 20, 3)])
+def test_lookup_v2_is_bit_identical_to_the_shipped_kernel(h8, w8, batch):
+    """With ATDN_LOOKUP_V2=1 an fp16-only lookup runs the CTA-of-32-queries kernel (csrc/corr_lookup_v2.cuh) while a
+    lookup that asks for fp32 outputs still runs the shipped kernel: same fp32 formulas, so fp16(v1) == v2 bit for bit,
+    and the pad channels of the output rows stay untouched."""
+    from atdn_vslam_b200 import ops
+    g = torch.Generator().manual_seed(7 + h8 * w8)
+    f1 = torch.randn(batch, h8, w8, 256, generator=g).half().cuda()
+    f2 = torch.randn(batch, h8, w8, 256, generator=g).half().cuda()
+    lv = ops.alloc_pyramid(batch, h8, w8, "cuda", half_levels=4)
+    ops.corr_pyramid_build(ops.View(f1), ops.View(f2), lv)
+    ys, xs = torch.meshgrid(torch.arange(h8), torch.arange(w8), indexing="ij")
+    base = torch.stack([xs, ys], -1).float()[None].repeat(batch, 1, 1, 1)
+    for coords in (base + 6.0 * torch.randn(batch, h8, w8, 2, generator=g), base.clone(),
+                   base + 40.0 * torch.randn(batch, h8, w8, 2, generator=g)):
+        c = coords.contiguous().cuda()
+        out32 = torch.empty(batch * h8 * w8, 324, dtype=torch.float32, device="cuda")
+        ops.corr_lookup(lv, c, out32=out32)                                    # shipped kernel
+        out16 = torch.full((batch, h8, w8, 328), 77.0, dtype=torch.float16, device="cuda")
+        ops.corr_lookup(lv, c, out16=ops.View(out16))                          # v2
+        torch.cuda.synchronize()
+        assert torch.equal(out16[..., :324].reshape(-1, 324), out32.half())
+        assert (out16[..., 324:] == 77.0).all()
+
+
 def test_padded_direct_call_376x1248():
     """A raw 376x1241 frame padded by InputPadder to 376x1248 (N = 47x156 = 7332) must work too."""
     from atdn_vslam_b200 import synth

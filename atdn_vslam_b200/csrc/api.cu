@@ -4,6 +4,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace atdn {
@@ -18,22 +20,56 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
-int require_sm100() {
-  static int cached_dev = -1;
-  static int cached_res = 0;
+thread_local int DeviceOnce::dev_ = 0;
+
+namespace {
+struct DevInfo {
+  std::atomic<int> state{0};   // 0 = unknown, 1 = sm_100, 2 = other
+  int major = 0, minor = 0, sms = 0;
+};
+DevInfo g_dev[128];
+
+DevInfo* dev_info(int* dev_out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return set_error((int)e, "cudaGetDevice: %s", cudaGetErrorString(e));
-  if (dev == cached_dev) return cached_res;
-  int major = 0, minor = 0;
-  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
-  cached_dev = dev;
-  cached_res = (major == 10 && minor == 0)
-                   ? 0
-                   : set_error(ATDN_ERR_ARCH, "device %d is sm_%d%d; libatdn_b200 contains sm_100a code only (no fallback)",
-                               dev, major, minor);
-  return cached_res;
+  if (e != cudaSuccess || dev < 0 || dev >= 128) return nullptr;
+  if (dev_out) *dev_out = dev;
+  DevInfo* d = &g_dev[dev];
+  if (d->state.load(std::memory_order_acquire) == 0) {
+    cudaDeviceGetAttribute(&d->major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&d->minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev);
+    d->state.store((d->major == 10 && d->minor == 0) ? 1 : 2, std::memory_order_release);
+  }
+  return d;
+}
+}  // namespace
+
+int require_sm100() {
+  int dev = 0;
+  DevInfo* d = dev_info(&dev);
+  if (!d) return set_error(ATDN_ERR_ARCH, "cudaGetDevice failed or device index out of range");
+  if (d->state.load(std::memory_order_acquire) == 1) return 0;
+  return set_error(ATDN_ERR_ARCH, "device %d is sm_%d%d; libatdn_b200 contains sm_100a code only (no fallback)", dev, d->major, d->minor);
+}
+
+int num_sms() {
+  DevInfo* d = dev_info(nullptr);
+  return d ? d->sms : 0;
+}
+
+const EnvSwitches& env_switches() {
+  static const EnvSwitches s = [] {
+    auto on = [](const char* name) { const char* e = getenv(name); return e && e[0] == '1'; };
+    EnvSwitches v;
+    v.no_out_tma = on("ATDN_NO_OUT_TMA");
+    v.b_resident = on("ATDN_B_RESIDENT");
+    v.lookup_v2 = on("ATDN_LOOKUP_V2");
+    const char* dbg = getenv("ATDN_CORR_DBG");
+    v.corr_dbg = dbg ? atoi(dbg) : 0;
+    return v;
+  }();
+  return s;
 }
 
 }  // namespace atdn

@@ -195,10 +195,10 @@ extern "C" int atdn_clvo_lstm_scan(const float* p1, const float* w_hh1, const fl
   p.h1_0 = const_cast<float*>(h1_0); p.c1 = c1; p.h2_0 = const_cast<float*>(h2_0); p.c2 = c2;
   p.h1_all = h1_all; p.h2_all = h2_all; p.x2 = x2_scratch; p.counter = counter; p.T = steps; p.B = batch;
   const int smem = kScanSmemFloats * (int)sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     ATDN_CUDA(cudaFuncSetAttribute(clvo_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.done();
   }
   ATDN_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint32_t), stream));
   void* args[] = {&p};

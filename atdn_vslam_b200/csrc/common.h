@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/atdn_b200.h"
 
 namespace atdn {
@@ -27,5 +29,35 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // returns 0 when the current device is sm_100 (cached per device), ATDN_ERR_ARCH otherwise
 int require_sm100();
+
+// One-time PER-DEVICE configuration of a launch site: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a property of
+// the function on ONE device, so a process that drives several GPUs must repeat it on each of them.
+//   static DeviceOnce once;  if (once.pending()) { ATDN_CUDA(cudaFuncSetAttribute(...)); once.done(); }
+// Lock-free; two threads racing on the same device both configure (idempotent).
+class DeviceOnce {
+ public:
+  bool pending() {
+    dev_ = 0;
+    cudaGetDevice(&dev_);
+    return dev_ < 0 || dev_ >= 128 || !(mask_[dev_ >> 6].load(std::memory_order_acquire) >> (dev_ & 63) & 1u);
+  }
+  void done() {
+    if (dev_ >= 0 && dev_ < 128) mask_[dev_ >> 6].fetch_or(uint64_t(1) << (dev_ & 63), std::memory_order_release);
+  }
+
+ private:
+  static thread_local int dev_;
+  std::atomic<uint64_t> mask_[2] = {};
+};
+
+// multiprocessor count of the current device (cached per device)
+int num_sms();
+
+// environment switches (A/B experiments), read ONCE per process
+struct EnvSwitches {
+  bool no_out_tma, b_resident, lookup_v2;
+  int corr_dbg;
+};
+const EnvSwitches& env_switches();
 
 }  // namespace atdn

@@ -853,7 +853,7 @@ extern "C" int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitc
     p.tiles = ((h8 + 7) / 8) * p.tiles_w;
     p.h0 = h8;
     p.w0 = w8;
-    static const bool use_v2 = [] { const char* e = getenv("ATDN_LOOKUP_V2"); return e && e[0] == '1'; }();
+    const bool use_v2 = env_switches().lookup_v2;
     if (use_v2 && out16 && !out32) {
       // experimental CTA-of-32-queries layout (corr_lookup_v2.cuh): same fp16 results, ~2.3x fewer instructions; opt-in
       // until it has been timed on a GPU
@@ -867,10 +867,10 @@ extern "C" int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitc
       v.out16 = static_cast<__half*>(out16);
       v.out_pitch = out_pitch;
       v.nq = nq;
-      static bool configured = false;
-      if (!configured) {
+      static DeviceOnce configured;
+      if (configured.pending()) {
         ATDN_CUDA(cudaFuncSetAttribute(lk2::corr_lookup_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lk2::kSmemBytes));
-        configured = true;
+        configured.done();
       }
       lk2::corr_lookup_v2_kernel<<<static_cast<unsigned>((nq + lk2::kQ - 1) / lk2::kQ), lk2::kThreads, lk2::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(v);
     } else {

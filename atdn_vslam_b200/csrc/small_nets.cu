@@ -280,10 +280,10 @@ template <int K, int S, int CIT>
 static int launch_conv16(Conv32Params p, cudaStream_t stream) {
   using G = C16Geom<K, S>;
   constexpr int smem = (CIT * G::IH * G::PITCH + CIT * K * K * 16) * (int)sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     if (smem > 48 * 1024) ATDN_CUDA(cudaFuncSetAttribute(conv16_kernel<K, S, CIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.done();
   }
   p.tiles_x = ceil_div(p.OW, kC16TW);
   dim3 grid(p.tiles_x * ceil_div(p.OH, kC16TH), 1, p.B);
@@ -469,11 +469,11 @@ static int launch_conv16t(Conv32Params p, cudaStream_t stream) {
   constexpr int NSTAGE = CIN / CIT > 1 ? 2 : 1;
   constexpr int STAGE_FLOATS = (CIT * G::IH * G::ROW + 31) / 32 * 32;
   constexpr int smem = (NSTAGE * STAGE_FLOATS + CIN * K * K * 16) * (int)sizeof(float) + 128;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     if (smem > 48 * 1024)
       ATDN_CUDA(cudaFuncSetAttribute(conv16t_kernel<K, S, PAD, CIN, CIT, AFFINE, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.done();
   }
   CUtensorMap tmx;
   {

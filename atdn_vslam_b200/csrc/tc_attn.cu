@@ -259,10 +259,10 @@ extern "C" int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, in
   const int64_t pdims[4] = {n, n, 1, batch};
   const int64_t pstr[3] = {p_pitch, (int64_t)n * p_pitch, (int64_t)n * p_pitch};
   if (int e = make_map_f16(&p.tmP, p16, pdims, pstr, pbox, ones, "P")) return e;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     ATDN_CUDA(cudaFuncSetAttribute(attn_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    configured = true;
+    configured.done();
   }
   attn_probs_kernel<<<dim3(ceil_div(n, 128), batch), kAttnThreads, kAttnSmem, stream>>>(p);
   ATDN_CUDA(cudaGetLastError());

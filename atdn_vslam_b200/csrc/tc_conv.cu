@@ -380,22 +380,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
-
 template <int MT, int BN, int EPI, bool PAIR>
 static int launch_conv(const ConvParams& p, int smem, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     ATDN_CUDA(cudaFuncSetAttribute(tc_conv_kernel<MT, BN, EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-    configured = true;
+    configured.done();
   }
   const int cl = PAIR ? 2 : 1;
   const int max_clusters = num_sms() / cl;
@@ -508,10 +498,10 @@ int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream) {
   p.a_stage_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;
   const int b_bytes = (bn / cl) * 128;
   {
-    const char* off = getenv("ATDN_NO_OUT_TMA");
+    const bool off = env_switches().no_out_tma;
     const void* o16 = d->epi == ATDN_EPI_GRU_ZR ? d->rh16 : d->out;
     p.out_tma = (d->epi == ATDN_EPI_STORE16 || d->epi == ATDN_EPI_GRU_Q || d->epi == ATDN_EPI_GRU_ZR) && o16 != nullptr &&
-                !(off && off[0] == '1') && aligned16(o16);
+                !off && aligned16(o16);
   }
   const int out_bytes = p.out_tma ? 8 * 2 * 2048 + 1024 : 0;   // staging slots (+ alignment of the slot base to 1 KiB)
   const int avail = kMaxDynSmem - 1024 - out_bytes;   // 1 KiB alignment slack
@@ -529,8 +519,7 @@ int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream) {
     // >= 2 A stages.  Measured on the 1x1 and 64-channel layers: no gain (the weight stream was not their limiter, and
     // the 1x1 324 -> 256 layer loses A stages: 77 vs 74 us), so the streamed ring stays the default.
     const int need = chunks * d->taps_h * d->taps_w;
-    const char* on = getenv("ATDN_B_RESIDENT");
-    if (on && on[0] == '1' && p.n_tiles == 1 && need <= kMaxBStages && 2 * p.a_stage_bytes + need * b_bytes <= avail) {
+    if (env_switches().b_resident && p.n_tiles == 1 && need <= kMaxBStages && 2 * p.a_stage_bytes + need * b_bytes <= avail) {
       p.b_resident = 1;
       p.b_stages = need;
       const int as = (avail - need * b_bytes) / p.a_stage_bytes;

@@ -410,10 +410,7 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
   p.tiles_w = ceil_div(w8, 32);
   p.tiles = p.tiles_w * ceil_div(h8, 8);
   p.alpha = alpha;
-  {
-    const char* dbg = getenv("ATDN_CORR_DBG");
-    p.dbg = dbg ? atoi(dbg) : 0;
-  }
+  p.dbg = env_switches().corr_dbg;
   p.l0 = static_cast<float*>(lvl[0]);
   p.l3 = static_cast<__half*>(lvl[3]);
   p.pitch3 = lvl_pitch[3];
@@ -459,11 +456,11 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
       wl /= 2;
     }
   }
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
     ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
-    configured = true;
+    configured.done();
   }
   if (half_levels)
     corr_pyramid_kernel<true><<<dim3(ceil_div(n, 128), batch), kCorrThreads, kCorrSmem, stream>>>(p);

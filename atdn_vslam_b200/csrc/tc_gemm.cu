@@ -462,10 +462,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
 template <int BN, int STAGES, int EPI>
 static int launch(const TcParams& p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + BN * kChunkK * 2) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     ATDN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.done();
   }
   tc_gemm_kernel<BN, STAGES, EPI><<<grid, kThreads, smem, stream>>>(p);
   ATDN_CUDA(cudaGetLastError());
@@ -475,10 +475,10 @@ static int launch(const TcParams& p, dim3 grid, cudaStream_t stream) {
 template <int BN, int STAGES, int EPI>
 static int launch2(const TcParams& p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + (BN / 2) * kChunkK * 2) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.pending()) {
     ATDN_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.done();
   }
   tc_gemm2_kernel<BN, STAGES, EPI><<<grid, kThreads, smem, stream>>>(p);
   ATDN_CUDA(cudaGetLastError());
@@ -621,8 +621,7 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
   }
   grid.y = ceil_div(d->n_valid, d->bn);
   {
-    const char* off = getenv("ATDN_NO_OUT_TMA");
-    p.out_tma = d->epi == ATDN_EPI_STORE16 && !pair && d->out != nullptr && !(off && off[0] == '1') && aligned16(d->out) &&
+    p.out_tma = d->epi == ATDN_EPI_STORE16 && !pair && d->out != nullptr && !env_switches().no_out_tma && aligned16(d->out) &&
                 d->out_pitch % 8 == 0 && d->out_ch_off % 8 == 0;
     if (p.out_tma) {
       const bool patch = d->a_mode == ATDN_MODE_PATCH;

@@ -283,27 +283,37 @@ class RAFTGMA(nn.Module):
             raise NotImplementedError("only the configuration the SLAM uses is built: num_heads=1, content-only "
                                       "attention (atdn_vslam/utils/gma_parameters.py:8-10)")
         _build_module_tree(self, schema.gma_schema())
-        self._packed = None
+        self._packed = {}          # kernel-layout weights per device
         self._plans = {}
+        self._graphs = {}          # captured forward() graphs per (batch, H, W, iters, device)
+        self.generation = 0        # bumped whenever packed weights / plans are dropped: captured CUDA graphs hold raw pointers
+        self.capture_forward = os.environ.get("ATDN_NO_FORWARD_GRAPH") != "1"
 
     # -- weight handling --------------------------------------------------------------------------
+    def _invalidate(self, plans=False):
+        self._packed = {}
+        self._graphs = {}
+        if plans:
+            self._plans = {}
+        self.generation += 1
+
     def load_state_dict(self, state_dict, strict=True, **kw):
-        self._packed = None
+        self._invalidate()
         return super().load_state_dict(schema.strip_module_prefix(state_dict), strict=strict, **kw)
 
     def _apply(self, fn, *a, **kw):
-        self._packed = None
-        self._plans = {}
+        self._invalidate(plans=True)
         return super()._apply(fn, *a, **kw)
 
     def freeze_bn(self):   # network.py:45-48: eval-mode BN is the only mode implemented
         return self
 
     def _weights(self, dev):
-        if self._packed is None:
+        key = str(dev)
+        if key not in self._packed:
             sd = {k: v.detach().to(dev) for k, v in self.state_dict().items()}
-            self._packed = _Packed(sd)
-        return self._packed
+            self._packed[key] = _Packed(sd)
+        return self._packed[key]
 
     def _plan(self, b, h, w, dev):
         key = (b, h, w, str(dev))
@@ -426,9 +436,7 @@ class RAFTGMA(nn.Module):
                 _conv_s1(View(hx, 128, 128), q, View(plan.pre_q[i].view(-1, 1, 1, 8)), cout=128, taps=taps, epi=L.EPI_STORE32,
                          flags=L.F_TILED32 | _PRE16, out_pitch=per_buf)
 
-        # attention (gma.py:54-76): q.k^T * scale -> softmax
-        _conv_s1(View(hx, 128, 128), wts.to_qk, View(plan.qk), cout=256, taps=(1, 1))
-        ops.attn_probs(plan.qk, plan.p16, plan.inv_sum, 128 ** -0.5)
+        self._attention(plan, wts)
 
         if flow_init is not None:
             flow_init = flow_init.float().contiguous()
@@ -453,6 +461,31 @@ class RAFTGMA(nn.Module):
             return flow_lo, flow_up
         return preds
 
+    def _attention(self, plan, wts):
+        """Attention.forward (gma.py:54-76) on the context features HX[128:256]: q.k^T * scale -> un-normalised softmax
+        numerators P (fp16) + 1 / row sums."""
+        _conv_s1(View(plan.hx, 128, 128), wts.to_qk, View(plan.qk), cout=256, taps=(1, 1))
+        ops.attn_probs(plan.qk, plan.p16, plan.inv_sum, 128 ** -0.5)
+
+    def _aggregate(self, plan, wts):
+        """Aggregate.forward (gma.py:102-115) on the motion features HX[256:384] -> HX[384:512]:
+        v^T = W_v . mf^T (stored [B,128,Np]); mfg = mf + gamma * (P . v) / rowsum."""
+        b, n, np_, hx = plan.b, plan.n, plan.np_, plan.hx
+        d = L.TcDesc()
+        d.bn, d.epi, d.flags, d.a_mode, d.b_mode = 128, L.EPI_STORE16, L.F_B_BATCHED | L.F_A_SHARED, L.MODE_ROWS, L.MODE_ROWS
+        d.a = L.ptr(wts.to_v)
+        L._set(d.a_dims, (128, 128, 1, 1))
+        L._set(d.a_strides, (128, 128 * 128, 128 * 128))
+        d.b = L.ptr(hx, 256)
+        L._set(d.b_dims, (128, n, 1, b))
+        L._set(d.b_strides, (512, n * 512, n * 512))
+        d.n_valid, d.alpha = n, 1.0
+        d.out, d.out_pitch = L.ptr(plan.vt), np_
+        L.tc_gemm(d)
+        ops.gemm_rows(L.ptr(plan.p16), n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
+                      b_bstride=128 * np_, bn=128, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
+                      aux32=plan.inv_sum, gamma=wts.gamma)
+
     def _update(self, plan, wts, m_tiles):
         """One refinement iteration: lookup + GMAUpdateBlock (update.py:127-139) + coords update."""
         b, h8, w8, n, np_ = plan.b, plan.h8, plan.w8, plan.n, plan.np_
@@ -472,21 +505,7 @@ class RAFTGMA(nn.Module):
                     flags=R | L.F_PAIR)
         c = wts.conv
         _conv_s1(View(plan.corflo), c, View(hx, 256, 128), cout=128, taps=(3, 3), flags=R | L.F_FLOWTAIL, aux32=plan.flow)
-        # aggregation: v^T = W_v . mf^T (stored [B,128,Np]); mfg = mf + gamma * (P . v) / rowsum
-        d = L.TcDesc()
-        d.bn, d.epi, d.flags, d.a_mode, d.b_mode = 128, L.EPI_STORE16, L.F_B_BATCHED | L.F_A_SHARED, L.MODE_ROWS, L.MODE_ROWS
-        d.a = L.ptr(wts.to_v)
-        L._set(d.a_dims, (128, 128, 1, 1))
-        L._set(d.a_strides, (128, 128 * 128, 128 * 128))
-        d.b = L.ptr(hx, 256)
-        L._set(d.b_dims, (128, n, 1, b))
-        L._set(d.b_strides, (512, n * 512, n * 512))
-        d.n_valid, d.alpha = n, 1.0
-        d.out, d.out_pitch = L.ptr(plan.vt), np_
-        L.tc_gemm(d)
-        ops.gemm_rows(L.ptr(plan.p16), n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
-                      b_bstride=128 * np_, bn=128, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
-                      aux32=plan.inv_sum, gamma=wts.gamma)
+        self._aggregate(plan, wts)
         for i, ((zr, q), taps, pad) in enumerate(((wts.gru[0], (1, 5), (0, 2)), (wts.gru[1], (5, 1), (2, 0)))):
             if wts.gru_pre:   # contract [h | mf | mfg] only; the context term comes from plan.pre_*
                 _conv_s1(View(hx, 0, 128), zr, None, cout=256, taps=taps, epi=L.EPI_GRU_ZR, a2=View(hx, 256, 256), h32=plan.h32,

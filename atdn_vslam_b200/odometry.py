@@ -112,7 +112,8 @@ class ATDNVO(nn.Module):
         self.suffix = "_c" + ("d" if use_dropout else "")     # network.py:52-60; dropout is inactive in eval
         self.lstm_out_size = 512
         _build_module_tree(self, schema.atdnvo_schema())
-        self._packed = None
+        self._packed = {}          # kernel-layout weights per device
+        self.generation = 0        # bumped whenever the packed weights are dropped (captured CUDA graphs hold raw pointers)
         self.reset_lstm()
 
     # -- state ------------------------------------------------------------------------------------------
@@ -125,18 +126,27 @@ class ATDNVO(nn.Module):
         """network.py:156-162: moves the parameters, resets the LSTM state, returns self."""
         super().to(device)
         self.device = device
-        self._packed = None
+        self._invalidate()
         self.reset_lstm()
         return self
 
+    def _invalidate(self):
+        self._packed = {}
+        self.generation += 1
+
+    def _apply(self, fn, *a, **kw):
+        self._invalidate()
+        return super()._apply(fn, *a, **kw)
+
     def load_state_dict(self, state_dict, strict=True, **kw):
-        self._packed = None
+        self._invalidate()
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def _weights(self, dev):
-        if self._packed is None:
-            self._packed = _Packed(self.state_dict(), dev)
-        return self._packed
+        key = str(dev)
+        if key not in self._packed:
+            self._packed[key] = _Packed(self.state_dict(), dev)
+        return self._packed[key]
 
     # -- compute ----------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -74,7 +74,7 @@ class OdometryPipeline:
     def __init__(self, flow_net, odometry_net, batch_pairs=6, iters=12, use_graphs=True):
         self.flow_net, self.odometry_net = flow_net, odometry_net
         self.batch_pairs, self.iters, self.use_graphs = batch_pairs, iters, use_graphs
-        self._graphs = {}
+        self._graphs, self._graph_gen = {}, None
         self._copy_stream, self._staging, self._staging_key = None, None, None
 
     def _batch_eager(self, frames):
@@ -85,7 +85,12 @@ class OdometryPipeline:
         """frames [b+1,3,H,W] -> CLVO features [b,512]"""
         if not self.use_graphs:
             return self._batch_eager(frames)
-        key = tuple(frames.shape)
+        # captured graphs hold raw pointers to the packed weights and plan buffers: the nets' generation counters change
+        # whenever those are dropped (load_state_dict, .to(), ...), which retires every graph captured before
+        gen = (getattr(self.flow_net, "generation", 0), getattr(self.odometry_net, "generation", 0))
+        if gen != self._graph_gen:
+            self._graphs, self._graph_gen = {}, gen
+        key = tuple(frames.shape) + (str(frames.device), self.iters)
         g = self._graphs.get(key)
         if g is None:
             static_in = frames.clone()

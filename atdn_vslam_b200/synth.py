@@ -61,8 +61,18 @@ def gma_state_dict(seed=GMA_SEED, module_prefix=False):
     return make_state_dict(schema.gma_schema(), seed, gain=1.2, module_prefix=module_prefix)
 
 
-def atdnvo_state_dict(seed=ATDNVO_SEED):
-    return make_state_dict(schema.atdnvo_schema(), seed, gain=1.0)
+SEQUENCE_POSE_GAIN = (1.0, 40.0)   # (rotation, translation) head gains of the golden SEQUENCE fixture
+
+
+def atdnvo_state_dict(seed=ATDNVO_SEED, pose_gain=None):
+    """``pose_gain`` = (rotation gain, translation gain) scales the last (bias-free) layer of the two regressor heads:
+    the random-weight network then moves far enough per frame for the keyframe rule (neural_slam.py:288-302: 10 degrees or
+    15 units since the last keyframe) to fire every few frames (tests/golden/make_golden_sequence.py)."""
+    sd = make_state_dict(schema.atdnvo_schema(), seed, gain=1.0)
+    if pose_gain is not None:
+        sd["rotation_regressor.2.weight"] = sd["rotation_regressor.2.weight"] * pose_gain[0]
+        sd["translation_regressor.2.weight"] = sd["translation_regressor.2.weight"] * pose_gain[1]
+    return sd
 
 
 def vae_state_dict(seed=VAE_SEED):

@@ -43,7 +43,7 @@ def linear_block(x, sd, p):
 
 def atdnvo_encode(sd, flows):
     """odometry/network.py:131-134, 63-73: flow / std -> CNN -> [B, 512]."""
-    std = torch.tensor(FLOW_STD, dtype=flows.dtype).view(1, 2, 1, 1)
+    std = torch.tensor(FLOW_STD, dtype=flows.dtype, device=flows.device).view(1, 2, 1, 1)
     x = flows / std
     x = F.conv2d(x, sd["encoder_CNN.0.weight"], sd["encoder_CNN.0.bias"], groups=2)
     x = conv_block(x, sd, "encoder_CNN.1.", 2, 3)
@@ -63,8 +63,8 @@ def lstm_cell(x, h, c, sd, p):
     return h, c
 
 
-def zero_state(batch=1):
-    z = lambda: torch.zeros(batch, 512)
+def zero_state(batch=1, device=None):
+    z = lambda: torch.zeros(batch, 512, device=device)
     return [z(), z(), z(), z()]          # h1, c1, h2, c2 (odometry/network.py:95-104)
 
 

@@ -103,7 +103,7 @@ def corr_lookup(pyramid, coords, radius=4):
     k = 2 * radius + 1
     cx = coords[:, 0].reshape(bsz, n, 1, 1)
     cy = coords[:, 1].reshape(bsz, n, 1, 1)
-    d = torch.arange(-radius, radius + 1, dtype=coords.dtype)
+    d = torch.arange(-radius, radius + 1, dtype=coords.dtype, device=coords.device)
     out = []
     for lvl, corr in enumerate(pyramid):
         hl, wl = corr.shape[-2:]
@@ -124,7 +124,7 @@ def corr_lookup(pyramid, coords, radius=4):
         x0 = x0.long()
         y0 = y0.long()
         flat = corr.reshape(bsz, n, hl * wl)
-        acc = torch.zeros(bsz, n, k, k, dtype=corr.dtype)
+        acc = torch.zeros(bsz, n, k, k, dtype=corr.dtype, device=corr.device)
         for dy_, dx_, wgt in ((0, 0, (1 - fx) * (1 - fy)), (0, 1, fx * (1 - fy)),
                               (1, 0, (1 - fx) * fy), (1, 1, fx * fy)):
             xi = x0 + dx_
@@ -159,7 +159,7 @@ def corr_lookup_aten(pyramid, coords, radius=4):
     bsz, _, h1, w1 = coords.shape
     n = h1 * w1
     k = 2 * radius + 1
-    d = torch.arange(-radius, radius + 1, dtype=coords.dtype)
+    d = torch.arange(-radius, radius + 1, dtype=coords.dtype, device=coords.device)
     centre = coords.permute(0, 2, 3, 1).reshape(bsz * n, 1, 1, 2)
     # window offset [a, b] -> (x + d[a], y + d[b]): the slow window index offsets x (see corr_lookup)
     offs = torch.stack([d.view(k, 1).expand(k, k), d.view(1, k).expand(k, k)], dim=-1).view(1, k, k, 2)
@@ -173,9 +173,9 @@ def corr_lookup_aten(pyramid, coords, radius=4):
     return torch.cat(out, dim=-1).permute(0, 3, 1, 2).contiguous().float()
 
 
-def coords_grid(batch, ht, wd):
+def coords_grid(batch, ht, wd, device=None):
     """utils.py:76-79: channel 0 = x (column index), channel 1 = y (row index)."""
-    ys, xs = torch.meshgrid(torch.arange(ht), torch.arange(wd), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(ht, device=device), torch.arange(wd, device=device), indexing="ij")
     return torch.stack([xs, ys], dim=0).float()[None].repeat(batch, 1, 1, 1)
 
 
@@ -254,28 +254,40 @@ def upsample_flow(flow, mask):
 # ----------------------------------------------------------------------------------------------
 # whole network -- network.py:72-129
 # ----------------------------------------------------------------------------------------------
-def raftgma_forward(sd, image1, image2, iters=12, flow_init=None, test_mode=True, return_intermediates=False, aten_ops=False):
-    """Reference ``RAFTGMA.forward`` on the fp32 CPU path.  ``test_mode`` returns
-    (coords1 - coords0, flow_up); otherwise the list of per-iteration ``flow_up``.
+def raftgma_forward(sd, image1, image2, iters=12, flow_init=None, test_mode=True, return_intermediates=False, aten_ops=False,
+                    mixed_precision=False):
+    """Reference ``RAFTGMA.forward``.  Default: the fp32 path the reference takes with ``device="cpu"`` (O-cpu, the parity
+    oracle).  ``test_mode`` returns (coords1 - coords0, flow_up); otherwise the list of per-iteration ``flow_up``.
     ``aten_ops``: pyramid and lookup through ``avg_pool2d`` / ``grid_sample`` like the reference (the timed CPU
-    baseline) instead of the explicit restatements (the checker)."""
+    baseline) instead of the explicit restatements (the checker).
+    ``mixed_precision``: the reference's CUDA path (O-cuda): the same three
+    ``autocast(enabled=args.mixed_precision)`` regions as network.py:85,93,112 (fp16), the fmaps cast back to fp32 before
+    the correlation (network.py:88-89), lookup / coords / convex upsampling outside autocast.  Runs on whatever device
+    the inputs and ``sd`` live on; used to MEASURE the reference's own fp16-vs-fp32 gap, never as the parity target."""
     sd = _strip(sd)
+    dev = image1.device
+
+    def region():
+        return torch.autocast(device_type=dev.type, dtype=torch.float16, enabled=mixed_precision)
+
     with torch.no_grad():
         im1 = (2 * (image1.float() / 255.0) - 1.0).contiguous()
         im2 = (2 * (image2.float() / 255.0) - 1.0).contiguous()
         b = im1.shape[0]
-        fm = basic_encoder(torch.cat([im1, im2], 0), sd, "fnet.", "instance")
+        with region():
+            fm = basic_encoder(torch.cat([im1, im2], 0), sd, "fnet.", "instance")
         fmap1, fmap2 = fm[:b].float(), fm[b:].float()
         pyr = (corr_pyramid_aten if aten_ops else corr_pyramid)(fmap1, fmap2)
         lookup = corr_lookup_aten if aten_ops else corr_lookup
-        cnet = basic_encoder(im1, sd, "cnet.", "batch")
-        net, inp = torch.split(cnet, [128, 128], dim=1)
-        net = torch.tanh(net)
-        inp = torch.relu(inp)
-        attn = attention(inp, sd)
+        with region():
+            cnet = basic_encoder(im1, sd, "cnet.", "batch")
+            net, inp = torch.split(cnet, [128, 128], dim=1)
+            net = torch.tanh(net)
+            inp = torch.relu(inp)
+            attn = attention(inp, sd)
         h8, w8 = im1.shape[2] // 8, im1.shape[3] // 8
-        coords0 = coords_grid(b, h8, w8)
-        coords1 = coords_grid(b, h8, w8)
+        coords0 = coords_grid(b, h8, w8, dev)
+        coords1 = coords_grid(b, h8, w8, dev)
         if flow_init is not None:
             coords1 = coords1 + flow_init
         preds = []
@@ -283,7 +295,8 @@ def raftgma_forward(sd, image1, image2, iters=12, flow_init=None, test_mode=True
         for _ in range(iters):
             corr = lookup(pyr, coords1)
             flow = coords1 - coords0
-            net, mask, delta = update_block(net, inp, corr, flow, attn, sd)
+            with region():
+                net, mask, delta = update_block(net, inp, corr, flow, attn, sd)
             coords1 = coords1 + delta
             flow_up = upsample_flow(coords1 - coords0, mask)
             preds.append(flow_up)

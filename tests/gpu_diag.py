@@ -372,7 +372,49 @@ def check_attn(n=1000, batch=2, reps=0):
     return ok
 
 
+def check_aggregate(h8=47, w8=154, batch=2, sharp=1.0, same_qk=False):
+    """Attention + Aggregate in isolation (gma.py:54-76, 102-115): the product's to_qk -> attn_probs -> to_v -> P.V with the
+    EPI_PV epilogue (mf + gamma * acc / rowsum) against oracle.attention / oracle.aggregate on the same fp16 inputs.
+    ``sharp`` scales the context features: > 1 gives peaked (trained-like) attention rows (effective support ~5100 / 140 /
+    6 of 7238 positions at 1 / 2 / 3).  ``same_qk``: the reference soft-max is taken over the product's own fp16 q / k
+    (isolates softmax + P.V from the fp16 rounding of q and k, whose effect on the logits grows with their magnitude)."""
+    import torch
+    import gpu_e2e
+    from atdn_vslam_b200 import synth
+    from oracle import gma_oracle
+    m, sd = gpu_e2e._gma()
+    sd = {k[7:]: v for k, v in sd.items()}
+    dev = torch.device("cuda")
+    wts = m._weights(dev)
+    plan = m._plan(batch, h8 * 8, w8 * 8, dev)
+    g = torch.Generator().manual_seed(31)
+    inp = (torch.relu(torch.randn(batch, 128, h8, w8, generator=g)) * sharp).half()
+    mf = torch.relu(torch.randn(batch, 128, h8, w8, generator=g)).half()
+    plan.hx.zero_()
+    plan.hx[..., 128:256] = inp.permute(0, 2, 3, 1).cuda()
+    plan.hx[..., 256:384] = mf.permute(0, 2, 3, 1).cuda()
+    m._attention(plan, wts)
+    m._aggregate(plan, wts)
+    torch.cuda.synchronize()
+    if same_qk:
+        q, k = plan.qk.float().cpu().reshape(batch, h8 * w8, 256).split(128, dim=2)
+        attn = torch.softmax(torch.matmul(q * 128 ** -0.5, k.transpose(1, 2)), dim=-1).unsqueeze(1)
+    else:
+        attn = gma_oracle.attention(inp.float(), sd)
+    ref = gma_oracle.aggregate(attn, mf.float(), sd)
+    got = plan.hx[..., 384:512].float().permute(0, 3, 1, 2)
+    neff = float((1.0 / attn.pow(2).sum(-1)).mean())
+    ok = _cmp(f"aggregate {h8}x{w8} batch={batch} (effective attention support {neff:.0f} of {h8 * w8})", got, ref, 2e-3)
+    # the attention term alone (gamma * attn.v), so that a wrong P.V cannot hide behind the residual
+    ok &= _cmp("aggregate minus residual", got - mf.float().cuda(), ref - mf.float(), 4e-3)
+    return ok
+
+
 CHECKS = {
+    "aggregate_full": lambda: check_aggregate(),
+    "aggregate_peaked": lambda: check_aggregate(batch=1, sharp=2.0),
+    "aggregate_very_peaked_same_qk": lambda: check_aggregate(batch=1, sharp=3.0, same_qk=True),
+    "aggregate_small_odd": lambda: check_aggregate(h8=23, w8=39, batch=3),
     "corr_full_vs_legacy": lambda: check_corr_full(),
     "time_corr": lambda: check_corr_full(batch=27, reps=5),
     "corr_legacy_small": lambda: check_corr(legacy=True),

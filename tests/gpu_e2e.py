@@ -233,8 +233,174 @@ def check_localization():
     return ok
 
 
+def _epe_stats(got, ref):
+    """got/ref [P,2,h,w] -> per-pair (mean, p99, max) end-point error lists"""
+    epe = (got.float().cpu() - ref.float().cpu()).pow(2).sum(1).sqrt().flatten(1)
+    return epe.mean(1).tolist(), epe.quantile(0.99, dim=1).tolist(), epe.amax(1).tolist()
+
+
+def _rel(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    return ((got - ref).norm(dim=-1) / ref.norm(dim=-1)).tolist()
+
+
+def reference_loop(flow_net, odometry_net, host_frames, device):
+    """The reference's per-frame odometry loop (neural_slam.py:192-227, 288-302) restated around ANY flow / odometry
+    modules with the reference signatures: ``TF.resize`` -> flow_net(im1, im2, iters=12, test_mode=True) ->
+    odometry_net(flow) -> transform(...).to("cpu") -> pose chain and keyframe rule on the host."""
+    import math
+    import torch
+    import torchvision.transforms.functional as TF
+    from atdn_vslam_b200.poses import matrix2euler, transform
+    pose, prop = torch.eye(4), torch.eye(4)
+    poses, keys, rots, trs, buf = [], [], [], [], None
+    for t in range(host_frames.shape[0]):
+        im = TF.resize(host_frames[t].to(device), (376, 1232))
+        if buf is None:
+            keys.append(t)
+        else:
+            _, flow = flow_net(buf.unsqueeze(0), im.unsqueeze(0), iters=12, test_mode=True)
+            rot, tr = odometry_net(flow)
+            m = transform(rot.squeeze(), tr.squeeze()).to("cpu")
+            pose = pose @ m
+            prop = prop @ m
+            if torch.norm(matrix2euler(prop[:3, :3])) > 10 / 180 * math.pi or torch.norm(prop[:3, -1]) > 15:
+                keys.append(t)
+                prop = torch.eye(4)
+            rots.append(rot.squeeze(0).cpu())
+            trs.append(tr.squeeze(0).cpu())
+        buf = im
+        poses.append(pose.clone())
+    return torch.stack(rots), torch.stack(trs), torch.stack(poses), keys
+
+
+def check_sequence(batch_pairs=8, out_json=None):
+    """Sequence-level parity of the BENCHMARKED path against the unmodified reference (tests/golden/sequence.npz, produced
+    by driving the reference NeuralSLAM frame by frame on CPU fp32 = O-cpu):
+      A. OdometryPipeline (CUDA graphs, production flags, batch 8, host frames streamed) -> rot/tr/poses/keyframes,
+         flows of the same batches through forward_frames;
+      B. the reference's own call pattern around the drop-ins: DataParallel(RAFTGMA, device_ids=[0]) + module.-prefixed
+         state dict + TF.resize + one pair per call + .to("cpu") per frame (neural_slam.py:51-53, 197-217);
+      C. O-cuda = the oracle under the reference's fp16 autocast regions on this GPU (cuDNN/cuBLAS): the reference's OWN
+         fp16-vs-fp32 gap, the yardstick for the end-to-end pose error (north star: 1e-4 relative)."""
+    import json
+    import numpy as np
+    import torch
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.odometry import ATDNVO
+    from atdn_vslam_b200.sequence import OdometryPipeline, preprocess
+    from oracle import clvo_oracle, gma_oracle
+    g = np.load(os.path.join(GOLD, "sequence.npz"))
+    T = int(g["frames"])
+    m, gsd = _gma()
+    vsd = synth.atdnvo_state_dict(pose_gain=tuple(float(x) for x in g["pose_gain"]))
+    assert str(g["gma_digest"]) == synth.state_dict_digest(gsd) and str(g["vo_digest"]) == synth.state_dict_digest(vsd), "weight RNG drift"
+    vo = ATDNVO()
+    vo.load_state_dict(vsd)
+    vo = vo.to("cuda").eval()
+    host = synth.frame_sequence(T, 376, 1241, seed=int(g["frame_seed"])).pin_memory()
+    ref_lo, ref_up = torch.from_numpy(g["flow_lo"]), torch.from_numpy(g["flow_up_s"])
+    ref_rot, ref_tr, ref_poses = torch.from_numpy(g["rot"]), torch.from_numpy(g["tr"]), torch.from_numpy(g["poses"])
+    ref_keys = g["keyframes"].tolist()
+    rep = {"pairs": T - 1, "batch_pairs": batch_pairs, "tolerances": {"flow_mean_epe_px": 1e-2, "pose_rel": 1e-4}}
+    ok = True
+
+    # ---- A: the pipeline the bench times
+    pipe = OdometryPipeline(m, vo, batch_pairs=batch_pairs, iters=12, use_graphs=True)
+    rot, tr, poses, keys = pipe.run(host)
+    dev_frames = preprocess(host.cuda())
+    los, ups = [], []
+    for s in range(0, T - 1, batch_pairs):
+        e = min(T - 1, s + batch_pairs)
+        lo, up = m.forward_frames(dev_frames[s:e + 1], iters=12, test_mode=True)
+        los.append(lo.clone())
+        ups.append(up[:, :, 3::8, 5::8].clone())
+    lo, up = torch.cat(los), torch.cat(ups)
+    a = {}
+    a["flow_lo_epe_mean"], a["flow_lo_epe_p99"], a["flow_lo_epe_max"] = _epe_stats(lo, ref_lo)
+    a["flow_up_epe_mean"], a["flow_up_epe_p99"], a["flow_up_epe_max"] = _epe_stats(up, ref_up)
+    a["rot_rel"], a["tr_rel"] = _rel(rot, ref_rot), _rel(tr, ref_tr)
+    a["pose_t_rel_final"] = float((poses[-1, :3, 3] - ref_poses[-1, :3, 3]).norm() / ref_poses[-1, :3, 3].norm())
+    a["keyframes"], a["keyframes_equal"] = list(keys), list(keys) == ref_keys
+    rep["pipeline_vs_reference_fp32"] = a
+    okA = max(a["flow_up_epe_mean"]) <= 1e-2 and a["keyframes_equal"]
+    print(f"{'PASS' if okA else 'FAIL'} pipeline (graphs, batch {batch_pairs}) vs reference: flow_up EPE mean max-over-pairs {max(a['flow_up_epe_mean']):.3e} "
+          f"p99 {max(a['flow_up_epe_p99']):.3e} max {max(a['flow_up_epe_max']):.3e}; rot rel max {max(a['rot_rel']):.2e} tr rel max {max(a['tr_rel']):.2e}; "
+          f"keyframes {keys} (reference {ref_keys})", flush=True)
+    ok &= okA
+
+    # ---- B: the reference's call pattern around the drop-ins
+    from atdn_vslam_b200.gma import RAFTGMA
+
+    class Args:
+        mixed_precision, num_heads, position_only, position_and_content = True, 1, False, False
+
+        def __contains__(self, k):
+            return hasattr(self, k)
+
+    dp = torch.nn.DataParallel(RAFTGMA(Args()), device_ids=[0])
+    dp.load_state_dict(synth.gma_state_dict(module_prefix=True))        # neural_slam.py:51-52
+    dp.eval()
+    dp = dp.to("cuda")
+    vo2 = ATDNVO().to("cuda")                                            # neural_slam.py:57-59
+    vo2.load_state_dict(vsd)
+    vo2.eval()
+    rot_b, tr_b, poses_b, keys_b = reference_loop(dp, vo2, host, "cuda")
+    b = {"rot_rel": _rel(rot_b, ref_rot), "tr_rel": _rel(tr_b, ref_tr), "keyframes": keys_b, "keyframes_equal": keys_b == ref_keys,
+         "rot_rel_vs_pipeline": _rel(rot_b, rot), "tr_rel_vs_pipeline": _rel(tr_b, tr)}
+    rep["reference_call_pattern_vs_reference_fp32"] = b
+    okB = b["keyframes_equal"] and max(b["rot_rel_vs_pipeline"]) < 2e-3 and max(b["tr_rel_vs_pipeline"]) < 2e-3
+    print(f"{'PASS' if okB else 'FAIL'} DataParallel + per-frame loop: rot rel max {max(b['rot_rel']):.2e} tr rel max {max(b['tr_rel']):.2e}, "
+          f"vs pipeline rot {max(b['rot_rel_vs_pipeline']):.2e} tr {max(b['tr_rel_vs_pipeline']):.2e}; keyframes {keys_b}", flush=True)
+    ok &= okB
+
+    # ---- C: the reference's own fp16-autocast CUDA path (oracle port, same cast regions) on this GPU
+    gsd_d = {k: v.cuda() for k, v in gsd.items()}
+    vsd_d = {k: v.cuda() for k, v in vsd.items()}
+    for tf32 in (True, False):      # torch default: cuDNN convolutions may use TF32 (what the reference gets on CUDA)
+        torch.backends.cudnn.allow_tf32 = tf32
+        for mp in (True, False):
+            st = clvo_oracle.zero_state(device="cuda")
+            lo_c, up_c, rot_c, tr_c = [], [], [], []
+            for t in range(T - 1):
+                l, u = gma_oracle.raftgma_forward(gsd_d, dev_frames[t:t + 1], dev_frames[t + 1:t + 2], iters=12, aten_ops=True, mixed_precision=mp)
+                r, x = clvo_oracle.atdnvo_forward(vsd_d, u.float(), st)
+                lo_c.append(l.float())
+                up_c.append(u.float()[:, :, 3::8, 5::8])
+                rot_c.append(r[0])
+                tr_c.append(x[0])
+            c = {}
+            c["flow_up_epe_mean"], c["flow_up_epe_p99"], c["flow_up_epe_max"] = _epe_stats(torch.cat(up_c), ref_up)
+            c["rot_rel"], c["tr_rel"] = _rel(torch.stack(rot_c), ref_rot), _rel(torch.stack(tr_c), ref_tr)
+            o_poses, o_keys = clvo_oracle.chain_and_keyframes(torch.stack(rot_c).cpu(), torch.stack(tr_c).cpu())
+            c["keyframes_equal"] = o_keys == ref_keys
+            name = f"torch_eager_cuda_{'fp16_autocast' if mp else 'fp32'}_{'tf32conv' if tf32 else 'ieee'}_vs_reference_fp32"
+            rep[name] = c
+            print(f"INFO {name}: flow_up EPE mean max-over-pairs {max(c['flow_up_epe_mean']):.3e} max {max(c['flow_up_epe_max']):.3e}; "
+                  f"rot rel max {max(c['rot_rel']):.2e} tr rel max {max(c['tr_rel']):.2e}", flush=True)
+    torch.backends.cudnn.allow_tf32 = True
+    gap = rep["torch_eager_cuda_fp16_autocast_tf32conv_vs_reference_fp32"]
+    rep["summary"] = {
+        "ours_flow_up_epe_mean_max": max(a["flow_up_epe_mean"]), "ref_autocast_flow_up_epe_mean_max": max(gap["flow_up_epe_mean"]),
+        "ours_rot_rel_max": max(a["rot_rel"]), "ours_tr_rel_max": max(a["tr_rel"]),
+        "ref_autocast_rot_rel_max": max(gap["rot_rel"]), "ref_autocast_tr_rel_max": max(gap["tr_rel"])}
+    # end-to-end pose: the 1e-4 north-star bound, or -- a fp16 trunk cannot be closer to the fp32 path than fp16 itself --
+    # no worse than the reference's own fp16-autocast path on the same frames
+    s = rep["summary"]
+    okP = (s["ours_rot_rel_max"] <= max(1e-4, s["ref_autocast_rot_rel_max"])) and (s["ours_tr_rel_max"] <= max(1e-4, s["ref_autocast_tr_rel_max"]))
+    print(f"{'PASS' if okP else 'FAIL'} end-to-end pose vs reference fp32: ours rot {s['ours_rot_rel_max']:.2e} tr {s['ours_tr_rel_max']:.2e}; "
+          f"reference fp16-autocast path rot {s['ref_autocast_rot_rel_max']:.2e} tr {s['ref_autocast_tr_rel_max']:.2e}", flush=True)
+    ok &= okP
+    rep["ok"] = bool(ok)
+    out_json = out_json or (os.path.join(ROOT, "gpurun_out", "parity_sequence.json") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None)
+    if out_json:
+        with open(out_json, "w") as f:
+            json.dump(rep, f, indent=1)
+    return ok
+
+
 CHECKS = {"gma_stages": check_gma_stages, "gma_small": check_gma_small, "gma_full": check_gma_full,
-          "atdnvo": check_atdnvo, "localization": check_localization}
+          "atdnvo": check_atdnvo, "localization": check_localization, "sequence": check_sequence}
 
 
 def main():

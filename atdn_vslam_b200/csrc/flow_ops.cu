@@ -214,7 +214,20 @@ struct LookupHalfParams {
   const __half* lvl[4];     // tiled: level l = [query][tile][(8 >> l) x (32 >> l)], tile = (y >> (3-l)) * tiles_w + (x >> (5-l))
   int tiles, tiles_w;       // ceil(h0 / 8) * tiles_w, ceil(w0 / 32): the same tile grid at every level
   int h0, w0;
+  int ldmode;               // experiment (ATDN_LOOKUP_LD): 0 = ld.global.nc, 1 = ld.global.cg, 2 = ld.global.nc.L1::no_allocate
 };
+
+__device__ __forceinline__ uint2 lk_load(const uint2* ptr, int mode) {
+  uint2 v;
+  if (mode == 1) {
+    v = __ldcg(ptr);
+  } else if (mode == 2) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ptr));
+  } else {
+    v = __ldg(ptr);
+  }
+  return v;
+}
 
 constexpr int kLkLevelStride = 176;   // floats per staged level: 10 rows x 16 texels + 16 (bank offset between the levels of a round)
 
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_half_kernel(const _
     if (y >= 0 && y < H && x >= 0 && x < W) {        // a 4-texel segment never straddles a tile (tile widths are multiples of 4)
       const int tile = (y >> (3 - l)) * p.tiles_w + (x >> (5 - l));
       const int within = ((y & ((8 >> l) - 1)) << (5 - l)) + (x & ((32 >> l) - 1));
-      raw[k] = __ldg(reinterpret_cast<const uint2*>(lv + ((q * p.tiles + tile) << (8 - 2 * l)) + within));
+      raw[k] = lk_load(reinterpret_cast<const uint2*>(lv + ((q * p.tiles + tile) << (8 - 2 * l)) + within), p.ldmode);
     }
   }
 #pragma unroll
@@ -853,6 +866,7 @@ extern "C" int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitc
     p.tiles = ((h8 + 7) / 8) * p.tiles_w;
     p.h0 = h8;
     p.w0 = w8;
+    p.ldmode = env_switches().lookup_ld;
     const bool use_v2 = env_switches().lookup_v2;
     if (use_v2 && out16 && !out32) {
       // experimental CTA-of-32-queries layout (corr_lookup_v2.cuh): same fp16 results, ~2.3x fewer instructions; opt-in

@@ -621,6 +621,14 @@ __global__ void __launch_bounds__(256) kf_dist_kernel(const float* __restrict__ 
   }
 }
 
+// torch.argmin semantics (neural_slam.py:383): the FIRST minimum; a NaN distance counts as the minimum (ATen propagates NaN),
+// so a corrupt embedding yields a valid index (the NaN's) instead of the sentinel.
+__device__ __forceinline__ bool kf_better(float v, long long i, float bv, long long bi) {
+  const bool vn = v != v, bn = bv != bv;
+  if (vn || bn) return vn && (!bn || i < bi);
+  return v < bv || (v == bv && i < bi);
+}
+
 __global__ void __launch_bounds__(1024) kf_argmin_kernel(const float* __restrict__ dist, long long n,
                                                          int* __restrict__ index) {
   __shared__ float sv[1024];
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(1024) kf_argmin_kernel(const float* __restrict
   long long bi = 0x7fffffffffffffffLL;
   for (long long i = threadIdx.x; i < n; i += 1024) {
     const float v = dist[i];
-    if (v < best) { best = v; bi = i; }   // strict <: keeps the lowest index of equal values
+    if (kf_better(v, i, best, bi)) { best = v; bi = i; }
   }
   sv[threadIdx.x] = best;
   si[threadIdx.x] = bi;
@@ -638,14 +646,14 @@ __global__ void __launch_bounds__(1024) kf_argmin_kernel(const float* __restrict
     if (threadIdx.x < s) {
       const float v = sv[threadIdx.x + s];
       const long long j = si[threadIdx.x + s];
-      if (v < sv[threadIdx.x] || (v == sv[threadIdx.x] && j < si[threadIdx.x])) {
+      if (kf_better(v, j, sv[threadIdx.x], si[threadIdx.x])) {
         sv[threadIdx.x] = v;
         si[threadIdx.x] = j;
       }
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *index = static_cast<int>(si[0]);
+  if (threadIdx.x == 0) *index = n > 0 ? static_cast<int>(si[0]) : -1;
 }
 
 }  // namespace atdn

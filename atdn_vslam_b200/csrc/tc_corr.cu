@@ -32,11 +32,11 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 
 constexpr int kCorrThreads = 384;
-constexpr int kCorrBStages = 3;                    // ring of 256 x 64 fp16 chunks of the target tile (32 KiB each)
+constexpr int kCorrBRingBytes = 3 * 256 * 128;     // ring of 64-channel chunks of the target tile: 3 x 32 KiB, or 6 x 16 KiB per CTA of a pair
 constexpr int kCorrABytes = 4 * 128 * 128;         // 128 queries x 256 channels
-constexpr int kCorrBStageBytes = 256 * 128;
 constexpr int kCorrSlotBytes = 32 * 128;           // one staging slot: 32 queries x 32 fp32
-constexpr int kCorrSmem = kCorrABytes + kCorrBStages * kCorrBStageBytes + 8 * 2 * kCorrSlotBytes + 1024;
+constexpr int kCorrSmem = kCorrABytes + kCorrBRingBytes + 8 * 2 * kCorrSlotBytes + 1024;
+constexpr int kCorrMaxBStages = 6;
 
 struct alignas(64) CorrParams {
   CUtensorMap tmA, tmB, tmL[4];
@@ -49,10 +49,19 @@ struct alignas(64) CorrParams {
   int pitch3;
 };
 
-template <bool HALF>
+// PAIR: a cluster of two CTAs (the two SMs of a TPC) owns 256 queries and executes cta_group::2 MMAs of M = 256: each CTA
+// keeps its own 128 query rows resident and stages only HALF of every target tile (4 of its 8 rows), so the L2 -> SM
+// operand stream per SM halves and the same ring bytes look ahead twice as far.  ncu on the single-CTA kernel (27 pairs,
+// profiles/r02a_ncu_corr_pyramid_lookup_*): the MMA warp spent 60% of its time waiting for target chunks and the producer
+// 74% waiting for free stages -- a latency-bound 3-stage ring (96 KiB in flight per SM against ~160 KiB needed once the
+// pyramid stores load the L2), tensor pipe 37% busy, with the epilogue warps idle 64% of the time.
+template <bool HALF, bool PAIR>
 __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __grid_constant__ CorrParams p) {
+  constexpr int CL = PAIR ? 2 : 1;
+  constexpr int kCorrBStageBytes = (256 / CL) * 128;
+  constexpr int kCorrBStages = kCorrBRingBytes / kCorrBStageBytes;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t a_full, b_full[kCorrBStages], b_empty[kCorrBStages], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t a_full, b_full[kCorrMaxBStages], b_empty[kCorrMaxBStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,14 +71,15 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128;
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int m0 = blockIdx.x * 128;                   // cluster c = CTAs 2c, 2c + 1: rank r owns queries (2c + r) * 128 ..
   const int batch = blockIdx.y;
   const int T = p.tiles;
 
   if (threadIdx.x == 0) {
     mbar_init(&a_full, 1);
     for (int s = 0; s < kCorrBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * CL); }
     fence_barrier_init();
   }
   if (warp == 2 && lane == 0) {
@@ -77,36 +87,44 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
     tma_prefetch_desc(&p.tmB);
     for (int l = 0; l < (HALF ? 3 : 4); ++l) tma_prefetch_desc(&p.tmL[l]);
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(&tmem_base_smem, 512);
+    else tmem_alloc(&tmem_base_smem, 512);
+  }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();            // the peer's barriers exist before any remote arrive / complete_tx
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===== producer =====
+    // ===== producer (both CTAs of a pair: own query rows, own half of every target tile; bytes land on the leader's barriers) =====
     if (elect_one_sync()) {
-      mbar_arrive_expect_tx(&a_full, kCorrABytes);
-      for (int c = 0; c < 4; ++c) tma_load_4d(smem_a + c * 128 * 128, &p.tmA, &a_full, c * 64, m0, 0, batch);
+      if (rank == 0) mbar_arrive_expect_tx(&a_full, CL * kCorrABytes);
+      for (int c = 0; c < 4; ++c) {
+        if constexpr (PAIR) tma_load_4d_pair(smem_a + c * 128 * 128, &p.tmA, &a_full, c * 64, m0, 0, batch);
+        else tma_load_4d(smem_a + c * 128 * 128, &p.tmA, &a_full, c * 64, m0, 0, batch);
+      }
     }
     __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < T; ++t) {
-      const int bh0 = (t / p.tiles_w) * 8, bw0 = (t % p.tiles_w) * 32;
+      const int bh0 = (t / p.tiles_w) * 8 + rank * 4, bw0 = (t % p.tiles_w) * 32;
       for (int c = 0; c < 4; ++c) {
         mbar_wait(&b_empty[stage], phase ^ 1u);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&b_full[stage], kCorrBStageBytes);
-          tma_load_4d(smem_b + stage * kCorrBStageBytes, &p.tmB, &b_full[stage], c * 64, bw0, bh0, batch);
+          if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], CL * kCorrBStageBytes);
+          if constexpr (PAIR) tma_load_4d_pair(smem_b + stage * kCorrBStageBytes, &p.tmB, &b_full[stage], c * 64, bw0, bh0, batch);
+          else tma_load_4d(smem_b + stage * kCorrBStageBytes, &p.tmB, &b_full[stage], c * 64, bw0, bh0, batch);
         }
         __syncwarp();
         if (++stage == kCorrBStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    constexpr uint32_t kIdesc = make_idesc_f16(128, 256);
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader CTA of a pair) =====
+    constexpr uint32_t kIdesc = make_idesc_f16(128 * CL, 256);
     const uint32_t a_u32 = smem_u32(smem_a), b_u32 = smem_u32(smem_b);
     int stage = 0;
     uint32_t phase = 0, pe0 = 0, pe1 = 0;
@@ -124,10 +142,17 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
         const uint64_t a_desc = make_smem_desc_sw128(a_u32 + c * 128 * 128);
         const uint64_t b_desc = make_smem_desc_sw128(b_u32 + stage * kCorrBStageBytes);
         if (elect_one_sync()) {
+          if constexpr (PAIR) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (c | k) ? 1u : 0u);
-          umma_commit(&b_empty[stage]);
-          if (c == 3) umma_commit(&acc_full[buf]);
+            for (int k = 0; k < 4; ++k) umma_f16_pair(d, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (c | k) ? 1u : 0u);
+            umma_commit_pair(&b_empty[stage]);
+            if (c == 3) umma_commit_pair(&acc_full[buf]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (c | k) ? 1u : 0u);
+            umma_commit(&b_empty[stage]);
+            if (c == 3) umma_commit(&acc_full[buf]);
+          }
         }
         __syncwarp();
         if (++stage == kCorrBStages) { stage = 0; phase ^= 1u; }
@@ -373,7 +398,10 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[g]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(&acc_empty[g], 0);   // the leader's MMA warp owns the accumulators of both CTAs
+        else mbar_arrive(&acc_empty[g]);
+      }
     }
     if (lane == 0) bulk_wait_read<0>();             // shared memory stays valid until the last store has read it
     __syncwarp();
@@ -381,10 +409,12 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
 
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();            // neither CTA frees TMEM / exits while the pair's MMAs or arrives are in flight
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -405,6 +435,7 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
   CorrParams p;
   memset(&p, 0, sizeof(p));
   const int n = h8 * w8;
+  const bool pair = !env_switches().corr_no_pair;
   p.h = h8;
   p.w = w8;
   p.tiles_w = ceil_div(w8, 32);
@@ -426,7 +457,7 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
   {
     const int64_t dims[4] = {channels, w8, h8, batch};
     const int64_t str[3] = {fmap_pitch, (int64_t)w8 * fmap_pitch, (int64_t)n * fmap_pitch};
-    const uint32_t box[4] = {64, 32, 8, 1};
+    const uint32_t box[4] = {64, 32, pair ? 4u : 8u, 1};          // a CTA of a pair stages 4 of the 8 tile rows
     if (int e = make_map_f16(&p.tmB, fmap2, dims, str, box, ones, "fmap2")) return e;
   }
   if (half_levels) {
@@ -458,14 +489,31 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
   }
   static DeviceOnce configured;
   if (configured.pending()) {
-    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
-    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
+    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
+    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
+    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
+    ATDN_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmem));
     configured.done();
   }
-  if (half_levels)
-    corr_pyramid_kernel<true><<<dim3(ceil_div(n, 128), batch), kCorrThreads, kCorrSmem, stream>>>(p);
-  else
-    corr_pyramid_kernel<false><<<dim3(ceil_div(n, 128), batch), kCorrThreads, kCorrSmem, stream>>>(p);
-  ATDN_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = pair ? dim3(2 * ceil_div(n, 256), batch) : dim3(ceil_div(n, 128), batch);
+  cfg.blockDim = dim3(kCorrThreads);
+  cfg.dynamicSmemBytes = kCorrSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (half_levels) {
+    if (pair) ATDN_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<true, true>, p));
+    else ATDN_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<true, false>, p));
+  } else {
+    if (pair) ATDN_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<false, true>, p));
+    else ATDN_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<false, false>, p));
+  }
   return 0;
 }

@@ -384,11 +384,22 @@ class RAFTGMA(nn.Module):
     # -- forward ------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
-        """Estimate optical flow between a pair (or batch of pairs) of frames -- network.py:72-129."""
+        """Estimate optical flow between a pair (or batch of pairs) of frames -- network.py:72-129.
+
+        The reference's caller invokes this once per frame at batch 1 (neural_slam.py:202); the ~330 kernel launches of
+        one call would then be bound by launch overhead, so ``test_mode`` calls are captured into a CUDA graph per
+        (shape, iters) the second time a shape is seen and replayed afterwards (``capture_forward = False`` or
+        ATDN_NO_FORWARD_GRAPH=1 keeps every call eager).  Outputs are fresh tensors on every call."""
         L.require_cuda(image1, image2)
         dev = image1.device
         L.check(L.load().atdn_check_device(dev.index if dev.index is not None else torch.cuda.current_device()),
                 "atdn_check_device")
+        if test_mode and self.capture_forward and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graphed(image1, image2, iters, flow_init)
+        return self._forward_eager(image1, image2, iters, flow_init, test_mode)
+
+    def _forward_eager(self, image1, image2, iters, flow_init, test_mode):
+        dev = image1.device
         b, _, h, w = image1.shape
         image1 = image1.float().contiguous()
         image2 = image2.float().contiguous()
@@ -398,6 +409,28 @@ class RAFTGMA(nn.Module):
         fmap = plan.buffer("fmap", (2 * b, plan.h8, plan.w8, 256), torch.float16)
         self._encoder(plan, wts.fnet, torch.cat([image1, image2], 0), View(fmap))
         return self._flow(plan, wts, image1, View(fmap[:b]), View(fmap[b:]), iters, flow_init, test_mode)
+
+    def _forward_graphed(self, image1, image2, iters, flow_init):
+        key = (tuple(image1.shape), image1.dtype, iters, str(image1.device), None if flow_init is None else tuple(flow_init.shape))
+        g = self._graphs.get(key)
+        if g is None:                       # first sighting of this shape: eager (packs weights, sizes the plan)
+            self._graphs[key] = "seen"
+            return self._forward_eager(image1, image2, iters, flow_init, True)
+        if g == "seen":                     # second sighting: capture
+            s1, s2 = image1.clone(), image2.clone()
+            sf = None if flow_init is None else flow_init.clone()
+            torch.cuda.synchronize(image1.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_eager(s1, s2, iters, sf, True)
+            g = self._graphs[key] = (graph, s1, s2, sf, out)
+        graph, s1, s2, sf, out = g
+        s1.copy_(image1)
+        s2.copy_(image2)
+        if sf is not None:
+            sf.copy_(flow_init)
+        graph.replay()
+        return out[0].clone(), out[1].clone()
 
     @torch.no_grad()
     def forward_frames(self, frames, iters=12, test_mode=True):
@@ -539,6 +572,14 @@ class CorrBlock:
         self.levels = ops.alloc_pyramid(b, h, w, fmap1.device)
         ops.corr_pyramid_build(View(f1), View(f2), self.levels)
         self.shape = (b, h, w)
+
+    @staticmethod
+    def corr(fmap1, fmap2):
+        """corr.py:55-63: the all-pairs volume alone, [B, H, W, 1, H, W] fp32 = <fmap1, fmap2> / sqrt(C) (level 0 of the
+        pyramid the tensor-core kernel builds)."""
+        b, c, h, w = fmap1.shape
+        blk = CorrBlock(fmap1, fmap2)
+        return blk.corr_pyramid[0].reshape(b, h, w, 1, h, w)
 
     @property
     def corr_pyramid(self):

@@ -42,9 +42,16 @@ def rgb_file_name(base_path, index):
 class KeyframeStore:
     """Keyframes of one run: ``frames`` (list of :class:`Frame`), files in the reference layout under ``path``."""
 
-    def __init__(self, path, keep_images=True):
+    def __init__(self, path, keep_images=True, fresh=False):
+        """``fresh``: cold start like ``neural_slam.py:108-123`` -- stale ``rgb/*`` files and ``poses.pth`` of an earlier
+        run under ``path`` are removed, so a run with fewer keyframes cannot pair old images with new poses."""
         self.path = path
         os.makedirs(os.path.join(path, "rgb"), exist_ok=True)
+        if fresh:
+            for f in glob.glob(os.path.join(path, "rgb", "*")):
+                os.remove(f)
+            if os.path.exists(os.path.join(path, "poses.pth")):
+                os.remove(os.path.join(path, "poses.pth"))
         self.frames = []
         self.keep_images = keep_images
         self._images = []                      # uint8 host copies (None when keep_images is off)
@@ -161,14 +168,16 @@ def write_flows(flow_net, frames, out_dir, batch_pairs=27, iters=12, start_index
     writer = threading.Thread(target=drain, daemon=True)
     writer.start()
     t, s, n = frames.shape[0], 0, 0
-    while s < t - 1:
-        e = min(t - 1, s + batch_pairs)
-        _, up = flow_net.forward_frames(frames[s:e + 1], iters=iters, test_mode=True)
-        q.put((start_index + s, up.half().cpu()))
-        n += e - s
-        s = e
-    q.put(None)
-    writer.join()
+    try:
+        while s < t - 1:
+            e = min(t - 1, s + batch_pairs)
+            _, up = flow_net.forward_frames(frames[s:e + 1], iters=iters, test_mode=True)
+            q.put((start_index + s, up.half().cpu()))
+            n += e - s
+            s = e
+    finally:                      # a failing flow net must not leave the writer blocked on the queue
+        q.put(None)
+        writer.join()
     if err:
         raise RuntimeError(f"flow writer failed: {err[0]}") from err[0]
     return n

@@ -31,31 +31,41 @@ class MappingEncoder(nn.Module):
         if variational:
             raise NotImplementedError("the SLAM uses the non-variational MappingVAE (localization/network.py:12)")
         _build_module_tree(self, schema.vae_encoder_schema())
-        self._packed = None
+        self._packed = {}          # kernel-layout weights per device
+        super().train(False)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
-        self._packed = None
+        self._packed = {}
         own = set(self.state_dict().keys())
         sd = {k: v for k, v in state_dict.items() if k in own or not k.startswith("decoder.")}
         return super().load_state_dict(sd, strict=strict, **kw)
 
     def _apply(self, fn, *a, **kw):
-        self._packed = None
+        self._packed = {}
         return super()._apply(fn, *a, **kw)
 
+    def train(self, mode=True):
+        """Inference only: the map training of ``NeuralSLAM.__create_map`` (neural_slam.py:305-352) needs the decoder and
+        autograd of the reference ``MappingVAE``; train that, then ``load_state_dict`` its weights here."""
+        if mode:
+            raise NotImplementedError("MappingEncoder is the inference-only keyframe embedder (no decoder, no autograd): keep "
+                                      "the reference MappingVAE for __create_map and load its state dict into this class")
+        return super().train(False)
+
     def _weights(self, dev):
-        if self._packed is None:
+        key = str(dev)
+        if key not in self._packed:
             sd = {k: v.detach().to(dev) for k, v in self.state_dict().items()}
             mean = torch.tensor(RGB_MEAN, dtype=torch.float32, device=dev)
             std = torch.tensor(RGB_STD, dtype=torch.float32, device=dev)
-            self._packed = {
+            self._packed[key] = {
                 # Normalize(0,255) then Normalize(mean,std): x * 1/(255 std) - mean/std
                 "in_scale": (1.0 / (255.0 * std)).contiguous(), "in_shift": (-mean / std).contiguous(),
                 "stem": _ConvBlock(sd, "encoder.0."),
                 "res": [_ResidualBlock(sd, f"encoder.{i}.") for i in range(1, 7)],
                 "mean_w": sd["mean_lin.weight"].float().contiguous(), "mean_b": sd["mean_lin.bias"].float().contiguous(),
             }
-        return self._packed
+        return self._packed[key]
 
     @torch.no_grad()
     def embed(self, image):
@@ -115,7 +125,10 @@ class KeyframeIndex:
     def search(self, code):
         """-> (index of the closest keyframe (first minimum), distances [K]) like neural_slam.py:373-384."""
         idx, dist = self.search_device(code)
-        return int(idx.item()), dist.clone()
+        i = int(idx.item())
+        if not 0 <= i < self._n:
+            raise RuntimeError(f"keyframe search returned index {i} for {self._n} keyframes")
+        return i, dist.clone()
 
     def search_sharded(self, code, group=None):
         """Every rank holds a row shard; returns the GLOBAL arg-min (lowest global index on ties).

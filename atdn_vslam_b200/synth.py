@@ -107,30 +107,43 @@ def texture_canvas(height, width, seed=FRAME_SEED, margin=64):
     return (canvas[0] * 255.0).contiguous()
 
 
-def frame_sequence(num_frames, height=376, width=1232, seed=FRAME_SEED, max_shift=6.0, integer=True):
+def frame_sequence(num_frames, height=376, width=1232, seed=FRAME_SEED, max_shift=6.0, integer=True, start=0, dtype=torch.float32,
+                   indices=None):
     """``num_frames`` crops of one canvas at a smoothly varying offset (<= max_shift px/frame) so that
     consecutive pairs have real sub-window displacements.  Returns float32 [T,3,H,W] holding 0..255
-    (integer-valued when ``integer``: the reference consumes float tensors of uint8 range)."""
+    (integer-valued when ``integer``: the reference consumes float tensors of uint8 range).
+    ``start``: return frames start .. start + num_frames - 1 of the (unbounded) sequence -- a rank's shard of a long
+    sequence without materialising the rest; ``indices`` (ascending list, may repeat) picks arbitrary frames instead
+    (``num_frames`` / ``start`` are then ignored); ``dtype=torch.uint8`` stores the (integer) frames as bytes."""
     margin = 64
     canvas = texture_canvas(height, width, seed, margin)
     frames = []
     ox, oy = float(margin), float(margin)
-    for t in range(num_frames):
+    if indices is not None:
+        indices = [int(i) for i in indices]
+        assert all(a <= b for a, b in zip(indices, indices[1:])), "indices must be ascending"
+        count = {}
+        for i in indices:
+            count[i] = count.get(i, 0) + 1
+        start, num_frames = (indices[0], indices[-1] - indices[0] + 1) if indices else (0, 0)
+    for t in range(start + num_frames):
         # deterministic smooth trajectory
         ox += max_shift * math.sin(0.37 * t + 0.5)
         oy += 0.5 * max_shift * math.cos(0.23 * t)
         ox = min(max(ox, 2.0), 2.0 * margin - 2.0)
         oy = min(max(oy, 2.0), 2.0 * margin - 2.0)
+        if t < start or (indices is not None and t not in count):
+            continue
         ix, iy = int(math.floor(ox)), int(math.floor(oy))
         fx, fy = ox - ix, oy - iy
         c = canvas[:, iy:iy + height + 1, ix:ix + width + 1]
         f = ((1 - fy) * (1 - fx)) * c[:, :-1, :-1] + ((1 - fy) * fx) * c[:, :-1, 1:] \
             + (fy * (1 - fx)) * c[:, 1:, :-1] + (fy * fx) * c[:, 1:, 1:]
-        frames.append(f)
-    out = torch.stack(frames, 0)
-    if integer:
-        out = out.round().clamp_(0, 255)
-    return out.contiguous()
+        if integer:
+            f = f.round().clamp_(0, 255)
+        f = f.to(dtype)
+        frames.extend([f] * (count[t] if indices is not None else 1))
+    return torch.stack(frames, 0).contiguous()
 
 
 def synthetic_flows(num, height=376, width=1232, seed=3):

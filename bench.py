@@ -4,9 +4,11 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
   python bench.py --impl reference ...                      (the reference's CPU path, see below)
 
-One step = one pass of the hot path over this rank's 271-frame synthetic sequence (270 pairs;
-BASELINE.json configs[1]); ranks process independent sequence shards (weak scaling) and exchange only
-the [270,512] CLVO features (NCCL all-gather) before the serial LSTM scan.  `value` times the step
+One step = one pass of the hot path over ONE synthetic sequence: at N=1 the 271-frame sequence (270 pairs;
+BASELINE.json configs[1]); at N>1 the 4541-frame sequence (4540 pairs; configs[3]) sharded batch-interleaved
+across the ranks (sequence.run_interleaved): every rank computes its batches of consecutive pairs, the [pairs,512]
+CLVO features of a round are all-gathered asynchronously (NCCL), rank 0 runs the serial LSTM scan one round behind
+between its own (slightly smaller) batches and broadcasts the relative poses.  `value` times the step
 with frames resident in HBM; `e2e` times the public API with frames in pinned HOST memory (H2D of
 the frames and D2H of the relative poses inside the timed region, plus the host pose chain).
 `online_b1` (extra key, rank 0) is the wall-clock latency of the reference's per-frame loop shape
@@ -33,7 +35,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frame_pairs_per_s"
 UNIT = "pairs/s"
-FRAMES = 271
+FRAMES = 271          # BASELINE.json configs[1] (N=1)
+SEQ_FRAMES = 4541     # BASELINE.json configs[3] (N>1): one sequence sharded across the ranks
 H_RAW, W_RAW = 376, 1241
 
 
@@ -261,10 +264,26 @@ def run_ours(args):
     vo = vo.to(dev).eval()
     pipe = OdometryPipeline(flow, vo, batch_pairs=args.batch_pairs, iters=12, use_graphs=not args.no_graphs)
 
-    pairs = args.frames - 1
-    host_frames = synth.frame_sequence(args.frames, H_RAW, W_RAW, seed=synth.FRAME_SEED + rank).pin_memory()
-    dev_frames = preprocess(host_frames.to(dev))
-    total_pairs = pairs * world
+    from atdn_vslam_b200.sequence import interleaved_rounds, local_frame_ranges
+    sharded = world > 1 or args.seq_frames is not None
+    if sharded:
+        # ONE sequence, batch-interleaved across the ranks; every rank materialises only the frames of its own batches
+        seq_frames = args.seq_frames or SEQ_FRAMES
+        total_pairs = seq_frames - 1
+        rounds = interleaved_rounds(total_pairs, world, args.batch_pairs, args.lead_pairs)
+        idx = [t for s, e in local_frame_ranges(rounds, rank) for t in range(s, e + 1)]
+        host_frames = synth.frame_sequence(0, H_RAW, W_RAW, seed=synth.FRAME_SEED, indices=idx, dtype=torch.uint8).pin_memory()
+        dev_frames = torch.cat([preprocess(host_frames[i:i + 64].to(dev).float()) for i in range(0, host_frames.shape[0], 64)], 0)
+        pairs = sum(row[rank][1] - row[rank][0] for row in rounds)
+        workload = f"seq{seq_frames}_376x1241_gma12_clvo"
+    else:
+        pairs = args.frames - 1
+        host_frames = synth.frame_sequence(args.frames, H_RAW, W_RAW, seed=synth.FRAME_SEED).pin_memory()
+        dev_frames = preprocess(host_frames.to(dev))
+        total_pairs = pairs
+        rounds = None
+        workload = f"seq{args.frames}_376x1241_gma12_clvo"
+    group = None if world == 1 else dist.group.WORLD
 
     def barrier():
         if world > 1:
@@ -273,17 +292,16 @@ def run_ours(args):
 
     def step_resident():
         vo.reset_lstm()
-        feats = pipe.pair_features(dev_frames)
-        if world > 1:
-            out = torch.empty(world * pairs, 512, dtype=feats.dtype, device=dev)
-            dist.all_gather_into_tensor(out, feats)
-            feats = out
-        return vo.recurrent_scan(feats)
+        if sharded:
+            return pipe.run_interleaved(dev_frames, rounds, group=group, chain=False)[:2]
+        return vo.recurrent_scan(pipe.pair_features(dev_frames))
 
     def step_e2e():
         vo.reset_lstm()
-        rot, tr, poses, keys = pipe.run(host_frames, num_pairs=total_pairs,
-                                        group=None if world == 1 else dist.group.WORLD)
+        if sharded:
+            rot, tr, poses, keys = pipe.run_interleaved(host_frames, rounds, group=group)
+        else:
+            rot, tr, poses, keys = pipe.run(host_frames)
         return poses, keys
 
     def timed(fn, steps):
@@ -309,20 +327,42 @@ def run_ours(args):
     ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 3)))
 
     value = total_pairs / (ms / 1e3)
+    h2d = torch.tensor([host_frames.numel() * host_frames.element_size()], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d)
+    # exchange / scan timings of one extra sharded step (CUDA events on rank 0's compute stream)
+    shard_timing = None
+    if sharded:
+        pipe.timing = {}
+        step_resident()
+        torch.cuda.synchronize()
+        evs = pipe.timing.get("events", [])
+        pipe.timing = None
+        if rank == 0:
+            shard_timing = {"rounds": len(rounds), "lead_pairs": rounds[0][0][1] - rounds[0][0][0], "pairs_rank0": pairs,
+                            "scan_ms": round(sum(t1.elapsed_time(t2) for _, t1, t2 in evs), 3),
+                            "allgather_wait_ms": round(sum(t0.elapsed_time(t1) for t0, t1, _ in evs), 3),
+                            "note": "per step on rank 0: serial LSTM scan chunks (run between its batches, one round behind) and the "
+                                    "time its compute stream waited for the asynchronous feature all-gathers"}
     # graph replays launch the captured kernels without passing through the C ABI again: count them
     if pipe.use_graphs:
         launches = None
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": "seq271_376x1241_gma12_clvo", "frames_per_rank": args.frames, "pairs_per_step": total_pairs,
+            "config": {"workload": workload, "pairs_per_step": total_pairs, "pairs_this_rank": pairs,
                        "image": "376x1241 -> SLAM resize 376x1232", "iters": 12, "batch_pairs": args.batch_pairs,
-                       "cuda_graphs": pipe.use_graphs, "parallelism": f"pair-range shards x{world}, all-gather of [P,512] features",
+                       "cuda_graphs": pipe.use_graphs,
+                       "parallelism": (f"one sequence, batch-interleaved over {world} rank(s); async all-gather of [pairs,512] features per round, "
+                                       "serial scan on rank 0 one round behind, broadcast of [P,6] poses") if sharded else "single GPU",
+                       "host_frames": str(host_frames.dtype).replace("torch.", ""),
                        "l2": "per-batch working set (corr pyramid + attention, ~0.6 GB/pair) exceeds the 126 MB L2"},
             "e2e": {"value": total_pairs / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(host_frames.numel() * 4), "d2h_bytes_per_step": int(total_pairs * 6 * 4)},
+                    "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(total_pairs * 6 * 4) * world},
             "clocks": clocks.summary()}
+    if shard_timing is not None:
+        line["sharding"] = shard_timing
 
     if rank == 0:
         # ---- per-kernel timing (eager, events on the launching stream) + roofline of the dominant kernel
@@ -344,7 +384,8 @@ def run_ours(args):
         vo.recurrent_scan(torch.zeros(1, 512, device=dev))
         scan_launches = L.LAUNCHES - l1
         # kernels launched inside the timed region (graph replays re-launch the captured kernels)
-        line["gpu_launches"] = int(args.steps * (per_batch_launches * batches + scan_launches * total_pairs))
+        scans = len(rounds) if sharded else 1
+        line["gpu_launches"] = int(args.steps * (per_batch_launches * batches + scan_launches * scans))
         kernels = {}
         for label, a in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
             ent = {"launches": a["launches"], "ms_per_batch": round(a["ms"], 4)}
@@ -418,6 +459,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--seq-frames", type=int, default=None, help="length of the ONE sharded sequence (default 4541 at N>1)")
+    ap.add_argument("--lead-pairs", type=int, default=None, help="pairs per round of rank 0, the sequencer (default: sequence.default_lead_pairs)")
     ap.add_argument("--batch-pairs", type=int, default=54)
     ap.add_argument("--cpu-pairs", type=int, default=12)
     ap.add_argument("--no-graphs", action="store_true")

@@ -363,3 +363,112 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["config"]["workload"] == "seq271_376x1241_gma12_clvo"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+# ----------------------------------------------------------------------------------------------
+# batch-interleaved sharding of one sequence (sequence.run_interleaved): host logic under gloo with stub networks
+# ----------------------------------------------------------------------------------------------
+def test_interleaved_rounds_cover_the_sequence_in_order():
+    from atdn_vslam_b200.sequence import default_lead_pairs, interleaved_rounds, local_frame_ranges
+    for pairs, world, bp, lead in [(4540, 8, 54, None), (4540, 2, 54, None), (270, 4, 54, 50), (7, 2, 3, 2), (5, 4, 3, None), (3, 1, 54, None)]:
+        rounds = interleaved_rounds(pairs, world, bp, lead)
+        flat = [rng for row in rounds for rng in row]
+        assert flat[0][0] == 0 and flat[-1][1] == pairs
+        assert all(a[1] == b[0] for a, b in zip(flat, flat[1:])) and all(0 <= e - s <= bp for s, e in flat)
+        assert all(len(row) == world for row in rounds)
+        ld = default_lead_pairs(world, bp) if lead is None else lead
+        for row in rounds[:-1]:                      # full rounds: rank 0 leads with the smaller batch
+            assert row[0][1] - row[0][0] == ld and all(e - s == bp for s, e in row[1:])
+        sizes = [e - s for s, e in rounds[-1]]
+        assert max(sizes[1:] or [0]) - min(sizes[1:] or [0]) <= 1        # the remainder is spread evenly
+        for r in range(world):
+            assert sum(e - s for s, e in local_frame_ranges(rounds, r)) == sum(row[r][1] - row[r][0] for row in rounds)
+    assert default_lead_pairs(1, 54) == 54 and default_lead_pairs(8, 54) == 50 and default_lead_pairs(2, 54) == 53
+
+
+class _StubFlow(torch.nn.Module):
+    """Stands in for RAFTGMA on CPU: 'flow' of pair t = mean(frame t+1) - mean(frame t) per pair."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(1))
+        self.generation = 0
+
+    def forward_frames(self, frames, iters=12, test_mode=True):
+        m = frames.float().mean(dim=(1, 2, 3))
+        return None, (m[1:] * 3.0 - m[:-1]).view(-1, 1)
+
+
+class _StubVO:
+    """Stands in for ATDNVO: encode = broadcast to 512 features; the 'scan' is an order-sensitive recurrence."""
+    generation = 0
+
+    def __init__(self):
+        self.state = torch.zeros(())
+
+    def encode(self, flow):
+        return flow.repeat(1, 512)
+
+    def recurrent_scan(self, feats):
+        out = []
+        for f in feats[:, 0]:
+            self.state = self.state * 0.9 + f
+            out.append(self.state.clone())
+        o = torch.stack(out) if out else torch.zeros(0)
+        return torch.stack([o, o * 2, o * 3], 1), torch.stack([o + 1, o + 2, o + 3], 1)
+
+
+def _interleaved_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from atdn_vslam_b200 import sequence
+    from atdn_vslam_b200.sequence import OdometryPipeline, interleaved_rounds, local_frame_ranges
+    sequence.SCAN_MIN_PAIRS = 9                                      # several scan calls, each covering >= 2 rounds
+    pairs = 23
+    g = torch.Generator().manual_seed(1)
+    frames = torch.rand(pairs + 1, 3, 376, 1232, generator=g)       # SLAM-sized: preprocess is the identity
+    rounds = interleaved_rounds(pairs, world, 4, lead_pairs=3)
+    local = torch.cat([frames[s:e + 1] for s, e in local_frame_ranges(rounds, rank)], 0)
+    pipe = OdometryPipeline(_StubFlow(), _StubVO(), batch_pairs=4, iters=1, use_graphs=False)
+    rot, tr, _, _ = pipe.run_interleaved(local, rounds, chain=False)
+    q.put((rank, rot.tolist(), tr.tolist()))
+    dist.destroy_process_group()
+
+
+def test_interleaved_run_world2_gloo_equals_single_rank():
+    """R-rank batch-interleaved run == the 1-rank run, bit for bit, on every rank (exchange + lagged scan on rank 0 +
+    final broadcast), with an order-sensitive recurrence standing in for the LSTM."""
+    import torch.multiprocessing as mp
+    from atdn_vslam_b200.sequence import OdometryPipeline, interleaved_rounds
+    pairs = 23
+    g = torch.Generator().manual_seed(1)
+    frames = torch.rand(pairs + 1, 3, 376, 1232, generator=g)
+    ref_pipe = OdometryPipeline(_StubFlow(), _StubVO(), batch_pairs=4, iters=1, use_graphs=False)
+    rot1, tr1, _, _ = ref_pipe.run_interleaved(frames, interleaved_rounds(pairs, 1, 4), chain=False)
+    rot0, tr0, _, _ = OdometryPipeline(_StubFlow(), _StubVO(), batch_pairs=5, iters=1, use_graphs=False).run(frames, chain=False)
+    assert torch.equal(rot1, rot0) and torch.equal(tr1, tr0)        # interleaved (world 1) == contiguous
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_interleaved_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, rot, tr in res:
+        assert rot == rot1.tolist() and tr == tr1.tolist()
+
+
+def test_mapping_encoder_is_inference_only():
+    """the localization drop-in embeds keyframes; the reference MappingVAE keeps __create_map's training
+    (neural_slam.py:305-352).  The class must refuse training mode loudly instead of failing inside the caller."""
+    from atdn_vslam_b200.localization import MappingEncoder
+    m = MappingEncoder()
+    assert not m.training and m.eval() is m
+    with pytest.raises(NotImplementedError):
+        m.train()
+    assert all(not p.requires_grad for p in m.parameters())

@@ -262,3 +262,144 @@ def test_sequence_parity_vs_reference_neural_slam():
     error <= max(1e-4, the reference's own fp16-autocast CUDA path vs its fp32 path, measured on the same frames in
     the same process).  All numbers are written to gpurun_out/parity_sequence.json (committed under profiles/)."""
     assert gpu_e2e.check_sequence()
+
+
+def test_forward_graph_replay_is_bit_identical_to_eager():
+    """RAFTGMA.forward / ATDNVO.forward capture a CUDA graph per shape on the second call (the reference's caller runs
+    one pair per call, neural_slam.py:202-203): eager, captured and replayed calls must agree bit for bit, on changing
+    inputs, with the stateful LSTM carried across calls."""
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.odometry import ATDNVO
+    m, _ = gpu_e2e._gma()
+    fr = synth.frame_sequence(5, 128, 160, seed=5, max_shift=3.0).cuda()
+    vsd = synth.atdnvo_state_dict()
+    outs = {}
+    for mode in ("graph", "eager"):
+        m.capture_forward = mode == "graph"
+        m._graphs = {}
+        vo = ATDNVO()
+        vo.load_state_dict(vsd)
+        vo = vo.to("cuda").eval()
+        vo.capture_forward = mode == "graph"
+        res = []
+        for t in range(4):
+            lo, up = m(fr[t:t + 1], fr[t + 1:t + 2], iters=3, test_mode=True)
+            big = torch.nn.functional.interpolate(up, size=(376, 1232), mode="bilinear")    # CLVO-sized input
+            rot, tr = vo(big)
+            res.append((lo.clone(), up.clone(), rot.clone(), tr.clone(), vo.lstm2_h.clone()))
+        outs[mode] = res
+        if mode == "graph":
+            assert any(isinstance(g, tuple) for g in m._graphs.values()) and any(isinstance(g, tuple) for g in vo._graphs.values())
+    m.capture_forward = True
+    for a, b in zip(outs["graph"], outs["eager"]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+
+
+def test_corrblock_corr_static():
+    """CorrBlock.corr (corr.py:55-63): [B,H,W,1,H,W] fp32 all-pairs volume."""
+    from atdn_vslam_b200.gma import CorrBlock
+    from oracle import gma_oracle
+    g = torch.Generator().manual_seed(3)
+    f1, f2 = torch.randn(2, 256, 16, 20, generator=g).half().float(), torch.randn(2, 256, 16, 20, generator=g).half().float()
+    vol = CorrBlock.corr(f1.cuda(), f2.cuda())
+    assert tuple(vol.shape) == (2, 16, 20, 1, 16, 20) and vol.dtype == torch.float32
+    ref = gma_oracle.corr_volume(f1, f2).reshape(2, 16, 20, 1, 16, 20)
+    assert (vol.cpu() - ref).abs().max() <= 2e-5 * ref.abs().max()
+
+
+def test_graphs_are_retired_when_weights_change():
+    """A captured graph holds raw pointers to the packed weights: loading another checkpoint must retire it
+    (OdometryPipeline graphs and the forward() graphs), not replay stale weights."""
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.odometry import ATDNVO
+    from atdn_vslam_b200.sequence import OdometryPipeline
+    m, _ = gpu_e2e._gma()
+    vo = ATDNVO()
+    vo.load_state_dict(synth.atdnvo_state_dict())
+    vo = vo.to("cuda").eval()
+    frames = synth.frame_sequence(5, 128, 160, seed=9, max_shift=3.0).cuda()
+    pipe = OdometryPipeline(m, vo, batch_pairs=2, iters=2, use_graphs=True)
+    rot_a, _, _, _ = pipe.run(frames)
+    m.load_state_dict(synth.gma_state_dict(seed=123))
+    vo.load_state_dict(synth.atdnvo_state_dict(seed=124))
+    vo.reset_lstm()
+    rot_b, _, _, _ = pipe.run(frames)
+    fresh = OdometryPipeline(m, vo, batch_pairs=2, iters=2, use_graphs=False)
+    vo.reset_lstm()
+    rot_c, _, _, _ = fresh.run(frames)
+    assert torch.equal(rot_b, rot_c) and not torch.equal(rot_a, rot_b)
+
+
+def test_keyframe_search_nan_and_inf_follow_torch_argmin():
+    """A NaN distance is the arg-min for torch (first NaN wins); all-inf distances give index 0: never a sentinel."""
+    from atdn_vslam_b200.localization import KeyframeIndex
+    g = torch.Generator().manual_seed(4)
+    db = torch.randn(40, 15360, generator=g)
+    q = torch.randn(15360, generator=g)
+    db[17, 5] = float("nan")
+    db[23, 9] = float("nan")
+    idx = KeyframeIndex(capacity=64)
+    idx.add(db.cuda())
+    i, d = idx.search(q.cuda())
+    ref = torch.stack([torch.norm(db[k] - q, p=2) for k in range(40)])
+    assert i == int(torch.argmin(ref)) == 17
+    db2 = torch.full((5, 15360), float("inf"))
+    idx2 = KeyframeIndex(capacity=8)
+    idx2.add(db2.cuda())
+    i2, _ = idx2.search(q.cuda())
+    assert i2 == int(torch.argmin(torch.stack([torch.norm(db2[k] - q, p=2) for k in range(5)])))
+
+
+def _nccl_interleaved_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.odometry import ATDNVO
+    from atdn_vslam_b200.sequence import OdometryPipeline, interleaved_rounds, local_frame_ranges
+    m, _ = gpu_e2e._gma(f"cuda:{rank}")
+    vo = ATDNVO()
+    vo.load_state_dict(synth.atdnvo_state_dict(pose_gain=synth.SEQUENCE_POSE_GAIN))
+    vo = vo.to(f"cuda:{rank}").eval()
+    pairs = 26
+    rounds = interleaved_rounds(pairs, world, 4, lead_pairs=3)
+    idx = [t for s, e in local_frame_ranges(rounds, rank) for t in range(s, e + 1)]
+    host = synth.frame_sequence(0, 376, 1241, seed=77, indices=idx, dtype=torch.uint8).pin_memory()
+    pipe = OdometryPipeline(m, vo, batch_pairs=4, iters=12, use_graphs=True)
+    rot, tr, poses, keys = pipe.run_interleaved(host, rounds)
+    q.put((rank, rot.cpu(), tr.cpu(), poses, keys))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_interleaved_run_is_bit_identical_to_one_rank():
+    """SURVEY.md 8(e) / BASELINE configs[3]: ONE sequence sharded batch-interleaved over 2 GPUs (NCCL) gives the same
+    relative poses, chained poses and keyframes, bit for bit, as the single-GPU run -- on both ranks."""
+    import torch.multiprocessing as mp
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.odometry import ATDNVO
+    from atdn_vslam_b200.sequence import OdometryPipeline
+    m, _ = gpu_e2e._gma()
+    vo = ATDNVO()
+    vo.load_state_dict(synth.atdnvo_state_dict(pose_gain=synth.SEQUENCE_POSE_GAIN))
+    vo = vo.to("cuda").eval()
+    host = synth.frame_sequence(27, 376, 1241, seed=77, dtype=torch.uint8).pin_memory()
+    rot1, tr1, poses1, keys1 = OdometryPipeline(m, vo, batch_pairs=5, iters=12, use_graphs=True).run(host)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 34500 + __import__("os").getpid() % 2000
+    procs = [ctx.Process(target=_nccl_interleaved_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert len(keys1) >= 3
+    for _, rot, tr, poses, keys in res:
+        assert torch.equal(rot, rot1.cpu()) and torch.equal(tr, tr1.cpu()) and torch.equal(poses, poses1) and keys == keys1

@@ -79,3 +79,19 @@ def test_mismatched_store_is_rejected(tmp_path):
         KeyframeStore.load(str(tmp_path))
     with pytest.raises(RuntimeError):
         KeyframeStore(str(tmp_path / "empty")).save_poses()
+
+
+def test_fresh_store_removes_stale_files(tmp_path):
+    """Cold start (neural_slam.py:108-123): a second run with fewer keyframes must not see the first run's files."""
+    import torch
+    from atdn_vslam_b200.keyframes import KeyframeStore
+    a = KeyframeStore(str(tmp_path))
+    for i in range(3):
+        a.add(torch.full((3, 8, 8), float(i)), torch.eye(4))
+    a.save_poses()
+    a.close()
+    b = KeyframeStore(str(tmp_path), fresh=True)
+    b.add(torch.zeros(3, 8, 8), torch.eye(4))
+    b.save_poses()
+    b.close()
+    assert len(KeyframeStore.load(str(tmp_path))) == 1

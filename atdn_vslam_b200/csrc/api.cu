@@ -64,12 +64,9 @@ const EnvSwitches& env_switches() {
     EnvSwitches v;
     v.no_out_tma = on("ATDN_NO_OUT_TMA");
     v.b_resident = on("ATDN_B_RESIDENT");
-    v.lookup_v2 = on("ATDN_LOOKUP_V2");
     v.corr_no_pair = on("ATDN_CORR_NO_PAIR");
     const char* dbg = getenv("ATDN_CORR_DBG");
     v.corr_dbg = dbg ? atoi(dbg) : 0;
-    const char* ld = getenv("ATDN_LOOKUP_LD");
-    v.lookup_ld = ld ? atoi(ld) : 0;
     return v;
   }();
   return s;

@@ -55,8 +55,8 @@ int num_sms();
 
 // environment switches (A/B experiments), read ONCE per process
 struct EnvSwitches {
-  bool no_out_tma, b_resident, lookup_v2, corr_no_pair;
-  int corr_dbg, lookup_ld;
+  bool no_out_tma, b_resident, corr_no_pair;
+  int corr_dbg;
 };
 const EnvSwitches& env_switches();
 

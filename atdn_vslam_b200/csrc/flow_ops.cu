@@ -6,7 +6,7 @@
 #include <cuda_fp16.h>
 
 #include "common.h"
-#include "corr_lookup_v2.cuh"
+#include "corr_lookup_strip.cuh"
 
 namespace atdn {
 
@@ -169,166 +169,6 @@ __global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_kernel(LookupParams
     const float4 f0 = *reinterpret_cast<const float4*>(&outs[c8 * 8]);
     if (c8 < 40) {
       const float4 f1 = *reinterpret_cast<const float4*>(&outs[c8 * 8 + 4]);
-      if (out16) {
-        __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
-        __half2 h2 = __floats2half2_rn(f1.x, f1.y), h3 = __floats2half2_rn(f1.z, f1.w);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2);
-        u.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(out16 + q * out_pitch + c8 * 8) = u;
-      }
-      if (out32) {
-        *reinterpret_cast<float4*>(out32 + q * 324 + c8 * 8) = f0;
-        *reinterpret_cast<float4*>(out32 + q * 324 + c8 * 8 + 4) = f1;
-      }
-    } else {   // channels 320..323
-      if (out16) {
-        __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
-        uint2 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(out16 + q * out_pitch + 320) = u;
-      }
-      if (out32) *reinterpret_cast<float4*>(out32 + q * 324 + 320) = f0;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Correlation lookup on the fp16 pyramid (the sequence pipeline's layout, atdn_corr_pyramid half_levels = 4).
-//
-// ncu on the kernel above (B200, 8 pairs): 1175 warp instructions per query, issue slots 70% busy, L1/TEX 84% busy
-// (3.1-way bank conflicts on the 4-tap gathers), DRAM at 37% -- it is bound by instruction issue and shared-memory
-// wavefronts, not by HBM.  This kernel does the same lookup with a third of the instructions:
-//   * all 81 taps of a level share ONE fractional offset (integer tap offsets), so the 9 x 9 bilinear samples are a
-//     separable blend of the 10 x 10 texel window: 10 horizontal + 9 vertical lerps per window column instead of
-//     81 four-tap gathers; the per-tap coordinate round trip of grid_sample (ulp-level perturbation) is dropped;
-//   * window staging: lane = (row, 4-texel segment), one 8-byte load per lane and pass, 5 passes for the 4 levels
-//     (rows 0..7 of level k in pass k, rows 8..9 of all levels in pass 4), all loads issued before the first use;
-//   * blend: lane = (level, window column a); two rounds of 18 lanes; 2 conflict-free scalar shared loads per row;
-//   * output: 324 fp32 results staged in shared memory (aliasing the windows), written as 16-byte fp16 vectors.
-// ------------------------------------------------------------------------------------------------
-struct LookupHalfParams {
-  const __half* lvl[4];     // tiled: level l = [query][tile][(8 >> l) x (32 >> l)], tile = (y >> (3-l)) * tiles_w + (x >> (5-l))
-  int tiles, tiles_w;       // ceil(h0 / 8) * tiles_w, ceil(w0 / 32): the same tile grid at every level
-  int h0, w0;
-  int ldmode;               // experiment (ATDN_LOOKUP_LD): 0 = ld.global.nc, 1 = ld.global.cg, 2 = ld.global.nc.L1::no_allocate
-};
-
-__device__ __forceinline__ uint2 lk_load(const uint2* ptr, int mode) {
-  uint2 v;
-  if (mode == 1) {
-    v = __ldcg(ptr);
-  } else if (mode == 2) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ptr));
-  } else {
-    v = __ldg(ptr);
-  }
-  return v;
-}
-
-constexpr int kLkLevelStride = 176;   // floats per staged level: 10 rows x 16 texels + 16 (bank offset between the levels of a round)
-
-__device__ __forceinline__ void lk_origin(float c, int l, int size, int& i0, float& frac) {
-  // level coordinate c / 2^l (exact), clamped so that far-away coordinates cannot overflow; windows that start
-  // 8 texels outside the map are all zeros either way
-  const float inv = __int_as_float((127 - l) << 23);
-  const float v = fminf(fmaxf(c * inv, -8.0f), static_cast<float>(size + 8));
-  const float f = floorf(v);
-  frac = v - f;
-  i0 = static_cast<int>(f) - 4;
-}
-
-__global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_half_kernel(const __grid_constant__ LookupHalfParams p, const float* __restrict__ coords,
-                                                                         __half* __restrict__ out16, long long out_pitch,
-                                                                         float* __restrict__ out32, long long nq) {
-  __shared__ __align__(16) float win[kLkWarps][4 * kLkLevelStride];
-  const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long q = static_cast<long long>(blockIdx.x) * kLkWarps + wq;
-  if (q >= nq) return;
-  const float2 cxy = *reinterpret_cast<const float2*>(coords + q * 2);
-  const int h0 = p.h0, w0 = p.w0;
-  float* w_s = &win[wq][0];
-
-  // 1. window staging: item (level l, window row r, segment s) -> texels [xa + 4s, xa + 4s + 4) of row y0 + r
-  uint2 raw[5];
-  int dsto[5], xs[5], ws[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const int l = k < 4 ? k : (lane >> 3);
-    const int r = k < 4 ? (lane >> 2) : 8 + ((lane >> 2) & 1);
-    const int s = lane & 3;
-    const int H = h0 >> l, W = w0 >> l;
-    int ix, iy;
-    float fdummy;
-    lk_origin(cxy.x, l, W, ix, fdummy);
-    lk_origin(cxy.y, l, H, iy, fdummy);
-    const int x = (ix & ~3) + 4 * s, y = iy + r;
-    const __half* lv = k < 4 ? p.lvl[k] : p.lvl[l];
-    raw[k] = make_uint2(0u, 0u);
-    dsto[k] = l * kLkLevelStride + r * 16 + 4 * s;
-    xs[k] = x;
-    ws[k] = W;
-    if (y >= 0 && y < H && x >= 0 && x < W) {        // a 4-texel segment never straddles a tile (tile widths are multiples of 4)
-      const int tile = (y >> (3 - l)) * p.tiles_w + (x >> (5 - l));
-      const int within = ((y & ((8 >> l) - 1)) << (5 - l)) + (x & ((32 >> l) - 1));
-      raw[k] = lk_load(reinterpret_cast<const uint2*>(lv + ((q * p.tiles + tile) << (8 - 2 * l)) + within), p.ldmode);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw[k].x));
-    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw[k].y));
-    float4 t = make_float4(lo.x, lo.y, hi.x, hi.y);
-    const int x = xs[k], W = ws[k];
-    if (x + 3 >= W) {                                 // texels past the map edge inside a tile hold whatever the pooling left there
-      if (x + 1 >= W) t.y = 0.0f;
-      if (x + 2 >= W) t.z = 0.0f;
-      t.w = 0.0f;
-    }
-    *reinterpret_cast<float4*>(w_s + dsto[k]) = t;
-  }
-  __syncwarp();
-
-  // 2. separable blend: lane (level, a) sweeps the 10 window rows of column pair (a, a + 1)
-  float res[2][9];
-  const int hi_half = lane >= 9 ? 1 : 0;
-  const int a = lane - 9 * hi_half;
-#pragma unroll
-  for (int rd = 0; rd < 2; ++rd) {
-    if (lane < 18) {
-      const int l = 2 * rd + hi_half;
-      int ix, iy;
-      float fx, fy;
-      lk_origin(cxy.x, l, w0 >> l, ix, fx);
-      lk_origin(cxy.y, l, h0 >> l, iy, fy);
-      const float* wp = w_s + l * kLkLevelStride + (ix & 3) + a;
-      float hprev = 0.0f;
-#pragma unroll
-      for (int r = 0; r < 10; ++r) {
-        const float t0 = wp[r * 16], t1 = wp[r * 16 + 1];
-        const float h = fmaf(fx, t1 - t0, t0);
-        if (r > 0) res[rd][r - 1] = fmaf(fy, h - hprev, hprev);
-        hprev = h;
-      }
-    }
-  }
-  __syncwarp();                                      // every lane is done with the windows: reuse them as output staging
-  if (lane < 18) {
-#pragma unroll
-    for (int rd = 0; rd < 2; ++rd)
-#pragma unroll
-      for (int b = 0; b < 9; ++b) w_s[(2 * rd + hi_half) * 81 + a * 9 + b] = res[rd][b];   // channel = l*81 + a*9 + b (corr.py:40-46)
-  }
-  __syncwarp();
-
-  // 3. coalesced output: 8 consecutive channels per lane and store
-  for (int c8 = lane; c8 < 41; c8 += 32) {
-    const float4 f0 = *reinterpret_cast<const float4*>(&w_s[c8 * 8]);
-    if (c8 < 40) {
-      const float4 f1 = *reinterpret_cast<const float4*>(&w_s[c8 * 8 + 4]);
       if (out16) {
         __half2 h0 = __floats2half2_rn(f0.x, f0.y), h1 = __floats2half2_rn(f0.z, f0.w);
         __half2 h2 = __floats2half2_rn(f1.x, f1.y), h3 = __floats2half2_rn(f1.z, f1.w);
@@ -857,39 +697,36 @@ extern "C" int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitc
   }
   const unsigned grid = static_cast<unsigned>((nq + kLkWarps - 1) / kLkWarps);
   if (half_levels) {
-    LookupHalfParams p;
+    // fp16 STRIP layout written by atdn_corr_pyramid (corr_lookup_strip.cuh)
+    lks::Params p;
+    const int tiles_w = (w8 + 31) / 32, tiles_h = (h8 + 7) / 8;
+    const int tiles = tiles_w * tiles_h, tiles_w3 = (tiles_w + 1) & ~1;
+    const int expect[4] = {256, 64, 16, 4};
     for (int l = 0; l < 4; ++l) {
-      ATDN_REQUIRE(lvl_pitch[l] == (256 >> (2 * l)), ATDN_ERR_ARG, "atdn_corr_lookup: tiled level %d has %d elements per tile, expected %d", l, lvl_pitch[l], 256 >> (2 * l));
+      ATDN_REQUIRE(lvl_pitch[l] == expect[l], ATDN_ERR_ARG, "atdn_corr_lookup: strip-layout level %d has %d elements per tile, expected %d", l, lvl_pitch[l], expect[l]);
       p.lvl[l] = static_cast<const __half*>(lvl[l]);
+      p.qstride[l] = l < 3 ? static_cast<long long>(tiles) * expect[l] : static_cast<long long>(tiles_h) * tiles_w3 * 4;
+      p.rowmul[l] = l < 3 ? tiles_w * expect[l] : tiles_w3 * 4;
+      p.hp[l] = l < 3 ? tiles_h * (8 >> l) : tiles_h;
+      p.xs[l] = l < 3 ? (tiles_w * 4) >> l : tiles_w3 / 2;
     }
-    p.tiles_w = (w8 + 31) / 32;
-    p.tiles = ((h8 + 7) / 8) * p.tiles_w;
     p.h0 = h8;
     p.w0 = w8;
-    p.ldmode = env_switches().lookup_ld;
-    const bool use_v2 = env_switches().lookup_v2;
-    if (use_v2 && out16 && !out32) {
-      // experimental CTA-of-32-queries layout (corr_lookup_v2.cuh): same fp16 results, ~2.3x fewer instructions; opt-in
-      // until it has been timed on a GPU
-      lk2::Params v;
-      for (int l = 0; l < 4; ++l) v.lvl[l] = p.lvl[l];
-      v.tiles = p.tiles;
-      v.tiles_w = p.tiles_w;
-      v.h0 = h8;
-      v.w0 = w8;
-      v.coords = coords;
-      v.out16 = static_cast<__half*>(out16);
-      v.out_pitch = out_pitch;
-      v.nq = nq;
-      static DeviceOnce configured;
-      if (configured.pending()) {
-        ATDN_CUDA(cudaFuncSetAttribute(lk2::corr_lookup_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lk2::kSmemBytes));
-        configured.done();
-      }
-      lk2::corr_lookup_v2_kernel<<<static_cast<unsigned>((nq + lk2::kQ - 1) / lk2::kQ), lk2::kThreads, lk2::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(v);
-    } else {
-      corr_lookup_half_kernel<<<grid, kLkWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(p, coords, static_cast<__half*>(out16), out_pitch, out32, nq);
+    p.coords = coords;
+    p.out16 = static_cast<__half*>(out16);
+    p.out32 = out32;
+    p.out_pitch = out_pitch;
+    p.nq = nq;
+    static DeviceOnce configured;
+    if (configured.pending()) {
+      ATDN_CUDA(cudaFuncSetAttribute(lks::corr_lookup_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lks::kSmemBytes));
+      ATDN_CUDA(cudaFuncSetAttribute(lks::corr_lookup_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lks::kSmemBytes));
+      configured.done();
     }
+    const long long per_cta = static_cast<long long>(lks::kWarps) * lks::kQueriesPerWarp;
+    const unsigned ctas = static_cast<unsigned>((nq + per_cta - 1) / per_cta);
+    if (out32) lks::corr_lookup_strip_kernel<true><<<ctas, lks::kWarps * 32, lks::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+    else lks::corr_lookup_strip_kernel<false><<<ctas, lks::kWarps * 32, lks::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
   } else {
     LookupParams p;
     int h = h8;

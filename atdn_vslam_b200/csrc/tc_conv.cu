@@ -412,6 +412,7 @@ static int dispatch_conv(int mt, int bn, const ConvParams& p, int smem, cudaStre
   if (mt == 1 && bn == 256) return launch_conv<1, 256, EPI, PAIR>(p, smem, s);
   if (mt == 1 && bn == 192) return launch_conv<1, 192, EPI, PAIR>(p, smem, s);
   if (mt == 1 && bn == 128) return launch_conv<1, 128, EPI, PAIR>(p, smem, s);
+  if (mt == 1 && bn == 64) return launch_conv<1, 64, EPI, PAIR>(p, smem, s);    // small problems (batch 1 at 1/8 resolution): more, smaller CTAs
   if (mt == 2 && bn == 128) return launch_conv<2, 128, EPI, PAIR>(p, smem, s);
   if (mt == 2 && bn == 96) return launch_conv<2, 96, EPI, PAIR>(p, smem, s);
   if (mt == 2 && bn == 64) return launch_conv<2, 64, EPI, PAIR>(p, smem, s);

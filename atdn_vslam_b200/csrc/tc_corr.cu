@@ -42,11 +42,12 @@ struct alignas(64) CorrParams {
   CUtensorMap tmA, tmB, tmL[4];
   int h, w, tiles_w, tiles;
   float alpha;
-  int dbg;                // experiment switches (ATDN_CORR_DBG): 1 = no level 1..3 stores, 2 = no stores, 4 = LSU level-0 stores
+  int dbg;                // experiment switches (ATDN_CORR_DBG): 1 = no level 1..3 stores, 2 = no stores, 4 = LSU level-0 stores (fp32)
   float* l0;
   int n, pitch0;
   __half* l3;             // HALF: level 3 is stored by the threads directly
   int pitch3;
+  int tiles_w3, tiles3;   // HALF: level-3 tile columns rounded up to even (16-byte rows for the lookup's cp.async), tiles per query
 };
 
 // PAIR: a cluster of two CTAs (the two SMs of a TPC) owns 256 queries and executes cta_group::2 MMAs of M = 256: each CTA
@@ -115,8 +116,21 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
         mbar_wait(&b_empty[stage], phase ^ 1u);
         if (elect_one_sync()) {
           if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], CL * kCorrBStageBytes);
-          if constexpr (PAIR) tma_load_4d_pair(smem_b + stage * kCorrBStageBytes, &p.tmB, &b_full[stage], c * 64, bw0, bh0, batch);
-          else tma_load_4d(smem_b + stage * kCorrBStageBytes, &p.tmB, &b_full[stage], c * 64, bw0, bh0, batch);
+          if constexpr (HALF) {
+            // strip order: B row (= accumulator column) strip * 64 + row * 8 + col; boxes of 8 cols x 8 rows (8 KiB); a CTA
+            // of a pair stages strips 2 * rank, 2 * rank + 1
+            constexpr int kStrips = 4 / CL;
+#pragma unroll
+            for (int sidx = 0; sidx < kStrips; ++sidx) {
+              uint8_t* dst = smem_b + stage * kCorrBStageBytes + sidx * 8192;
+              const int x0 = (t % p.tiles_w) * 32 + (rank * kStrips + sidx) * 8, y0 = (t / p.tiles_w) * 8;
+              if constexpr (PAIR) tma_load_4d_pair(dst, &p.tmB, &b_full[stage], c * 64, x0, y0, batch);
+              else tma_load_4d(dst, &p.tmB, &b_full[stage], c * 64, x0, y0, batch);
+            }
+          } else {
+            if constexpr (PAIR) tma_load_4d_pair(smem_b + stage * kCorrBStageBytes, &p.tmB, &b_full[stage], c * 64, bw0, bh0, batch);
+            else tma_load_4d(smem_b + stage * kCorrBStageBytes, &p.tmB, &b_full[stage], c * 64, bw0, bh0, batch);
+          }
         }
         __syncwarp();
         if (++stage == kCorrBStages) { stage = 0; phase ^= 1u; }
@@ -160,8 +174,11 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
     }
   } else if (warp >= 4) {
     // ===== epilogue =====
+    // group g (4 warps) drains every second tile (accumulator buffer g).  (Letting both groups drain every tile, two strips
+    // each, was measured: no gain on level 0 and slower pooled-level stores -- the kernel is bound by the store path, not by
+    // the epilogue arithmetic: profiles/r02k_*.)
     const int q = warp & 3, g = (warp - 4) >> 2;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * 256);
+    const uint32_t trow_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* st_ptr = smem_st + (warp - 4) * 2 * kCorrSlotBytes;
     const uint32_t st_u32 = smem_u32(st_ptr);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
@@ -189,87 +206,112 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
 
     for (int t = g; t < T; t += 2) {
       const int bh0 = (t / p.tiles_w) * 8, bw0 = (t % p.tiles_w) * 32;
-      mbar_wait(&acc_full[g], pf);
+      const int buf = g;
+      const uint32_t trow = trow_base + static_cast<uint32_t>(buf * 256);
+      mbar_wait(&acc_full[buf], pf);
       pf ^= 1u;
       tcgen05_fence_after();
       if constexpr (HALF) {
-        // fp16 pyramid in the TILED layout [query][tile][(8 >> l) x (32 >> l)]: everything this tile contributes to one
-        // query's maps is contiguous (512 / 128 / 32 / 8 bytes at levels 0..3), so level 0 leaves as four boxes of
-        // 128-byte rows (two tile rows each) and levels 1, 2 as one box each: 6 TMA stores per tile instead of 14, with
-        // runs twice as long (the row-major layout wrote 64-byte pieces 320 bytes apart: 3.1 TB/s of a 7.5 TB/s write peak)
-        float hs1[16], hs2[8], hs3[4];
-        uint32_t prev[16];                 // packed even level-0 row, stored together with the odd row below it
-        uint32_t l1p[4][8], l2p[2][4];     // packed level-1 / level-2 rows of this tile
-        uint2 l3p = make_uint2(0u, 0u);
+        // fp16 pyramid, STRIP layout (include/atdn_b200.h): the target tile is loaded as four 8-column strips, so
+        // accumulator column = strip * 64 + row * 8 + col and everything a strip contributes to one query's level-0 map is
+        // one contiguous 128-byte run [8 rows][8 cols] -- a 64-byte DRAM fetch granule of the lookup is a 4 x 8 texel
+        // block instead of a 1 x 32 texel tile row (6.9 instead of 14 granules per 10 x 10 window).
+        // The strip is drained as two units of 32 columns (4 rows x 8 cols); the tcgen05.ld of unit u + 1 is in flight
+        // while unit u is scaled, packed and pooled.  Level 1 (4 x 4 per strip), level 2 (2 x 2) and level 3 (1) are
+        // the hierarchical 2 x 2 means of corr.py:28-30, kept in registers until the end of the tile; pooled texels
+        // outside the level's map are written as zeros (the lookup stages windows without masking).
+        uint32_t va[32], vb[32];
+        uint32_t w0[16];                   // packed level-0 words of the strip's first unit (rows 0..3)
+        uint32_t l1w[32], l2w[8];          // level-1 chunk [pair][row 4][col 8], level-2 chunk [row 2][col 8] of this tile
+        float l3v[4];
+        float l2a[2];                      // level-2 row 0 of the current strip (2 cols), waiting for level 3
+        // valid pooled texels of this tile (floor semantics of avg_pool2d: maps are (h >> l) x (w >> l))
+        const int nx1 = (p.w >> 1) - (bw0 >> 1), ny1 = (p.h >> 1) - (bh0 >> 1);
+        const int nx2 = (p.w >> 2) - (bw0 >> 2), ny2 = (p.h >> 2) - (bh0 >> 2);
+        const int nx3 = (p.w >> 3) - (bw0 >> 3), ny3 = (p.h >> 3) - (bh0 >> 3);
+        const bool unit_scale = p.alpha == 1.0f;     // the flow net folds 1/sqrt(C) = 2^-4 into its feature maps (exact)
+        // (Measured and dropped: sending every second box through coalesced 16-byte LSU stores instead of a TMA store -- 8 lanes
+        // x 16 B per query row -- to use both store engines side by side: 2.09 vs 1.93 ms per 54 pairs, profiles/r02l_*.)
+        const long long q_first = static_cast<long long>(batch) * p.n + qrow;
+        tmem_ld_32x32(trow, va);
 #pragma unroll
-        for (int hl = 0; hl < 8; ++hl) {
-          uint32_t v[32];
-          tmem_ld_32x32(trow + hl * 32, v);
+        for (int u = 0; u < 8; ++u) {
+          const int strip = u >> 1, hh = u & 1;     // unit = rows 4 * hh .. 4 * hh + 3 of the strip
+          uint32_t (&cur)[32] = (u & 1) ? vb : va;
           tmem_ld_wait();
+          if (u < 7) tmem_ld_32x32(trow + (u + 1) * 32, (u & 1) ? va : vb);
           float c[32];
+          if (unit_scale) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) c[j] = p.alpha * __uint_as_float(v[j]);
-          if ((hl & 1) == 0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              prev[j] = pack_half2(c[2 * j], c[2 * j + 1]);
-              hs1[j] = c[2 * j] + c[2 * j + 1];
-            }
+            for (int j = 0; j < 32; ++j) c[j] = __uint_as_float(cur[j]);
           } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c[j] = p.alpha * __uint_as_float(cur[j]);
+          }
+          // level 1: rows 2 * hh, 2 * hh + 1 of the strip's 4 x 4 block: ((a + b) + (c + d)) * 0.25
+          float l1r[8];
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+              l1r[r * 4 + x] = ((c[(2 * r) * 8 + 2 * x] + c[(2 * r) * 8 + 2 * x + 1]) + (c[(2 * r + 1) * 8 + 2 * x] + c[(2 * r + 1) * 8 + 2 * x + 1])) * 0.25f;
+          // level 2: row hh of the strip's 2 x 2 block
+          float l2r[2];
+#pragma unroll
+          for (int x = 0; x < 2; ++x) l2r[x] = ((l1r[2 * x] + l1r[2 * x + 1]) + (l1r[4 + 2 * x] + l1r[4 + 2 * x + 1])) * 0.25f;
+          // zero the pooled texels outside the maps, then pack: level-1 word index = pair * 16 + row * 4 + (strip & 1) * 2 + x / 2
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const bool yok = 2 * hh + r < ny1;
+            const float a0 = (yok && strip * 4 + 0 < nx1) ? l1r[r * 4 + 0] : 0.0f, a1 = (yok && strip * 4 + 1 < nx1) ? l1r[r * 4 + 1] : 0.0f;
+            const float a2 = (yok && strip * 4 + 2 < nx1) ? l1r[r * 4 + 2] : 0.0f, a3 = (yok && strip * 4 + 3 < nx1) ? l1r[r * 4 + 3] : 0.0f;
+            l1w[(strip >> 1) * 16 + (2 * hh + r) * 4 + (strip & 1) * 2] = pack_half2(a0, a1);
+            l1w[(strip >> 1) * 16 + (2 * hh + r) * 4 + (strip & 1) * 2 + 1] = pack_half2(a2, a3);
+          }
+          {
+            const bool yok = hh < ny2;
+            l2w[hh * 4 + strip] = pack_half2((yok && strip * 2 < nx2) ? l2r[0] : 0.0f, (yok && strip * 2 + 1 < nx2) ? l2r[1] : 0.0f);
+          }
+          if (hh == 0) {
+            l2a[0] = l2r[0];
+            l2a[1] = l2r[1];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w0[j] = pack_half2(c[2 * j], c[2 * j + 1]);
+          } else {
+            const float l3 = ((l2a[0] + l2a[1]) + (l2r[0] + l2r[1])) * 0.25f;
+            l3v[strip] = (0 < ny3 && strip < nx3) ? l3 : 0.0f;
             if (!(p.dbg & 2)) {
+              // level-0 strip: 128 bytes per query = [8 rows][8 cols] fp16, 16-byte chunk j = row j, 128B swizzle
               const int off = acquire();
 #pragma unroll
-              for (int ch = 0; ch < 4; ++ch) {
-                st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4),
-                             make_uint4(prev[4 * ch], prev[4 * ch + 1], prev[4 * ch + 2], prev[4 * ch + 3]));
-                st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(ch + 4) ^ sw) << 4),
-                             make_uint4(pack_half2(c[8 * ch], c[8 * ch + 1]), pack_half2(c[8 * ch + 2], c[8 * ch + 3]),
-                                        pack_half2(c[8 * ch + 4], c[8 * ch + 5]), pack_half2(c[8 * ch + 6], c[8 * ch + 7])));
+              for (int j = 0; j < 4; ++j) {
+                st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(j) ^ sw) << 4),
+                             make_uint4(w0[4 * j], w0[4 * j + 1], w0[4 * j + 2], w0[4 * j + 3]));
+                st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(j + 4) ^ sw) << 4),
+                             make_uint4(pack_half2(c[8 * j], c[8 * j + 1]), pack_half2(c[8 * j + 2], c[8 * j + 3]),
+                                        pack_half2(c[8 * j + 4], c[8 * j + 5]), pack_half2(c[8 * j + 6], c[8 * j + 7])));
               }
-              commit(&p.tmL[0], off, (hl - 1) * 32, t);
-            }
-            float l1[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) l1[j] = (hs1[j] + (c[2 * j] + c[2 * j + 1])) * 0.25f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) l1p[hl >> 1][j] = pack_half2(l1[2 * j], l1[2 * j + 1]);
-            if ((hl & 3) == 1) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) hs2[j] = l1[2 * j] + l1[2 * j + 1];
-            } else {
-              float l2[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) l2[j] = (hs2[j] + (l1[2 * j] + l1[2 * j + 1])) * 0.25f;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) l2p[hl >> 2][j] = pack_half2(l2[2 * j], l2[2 * j + 1]);
-              if (hl == 3) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) hs3[j] = l2[2 * j] + l2[2 * j + 1];
-              } else {
-                l3p = make_uint2(pack_half2((hs3[0] + (l2[0] + l2[1])) * 0.25f, (hs3[1] + (l2[2] + l2[3])) * 0.25f),
-                                 pack_half2((hs3[2] + (l2[4] + l2[5])) * 0.25f, (hs3[3] + (l2[6] + l2[7])) * 0.25f));
-              }
+              commit(&p.tmL[0], off, strip * 64, t);
             }
           }
         }
         if (!(p.dbg & 3)) {
-          int off = acquire();               // level 1: 4 rows x 32 bytes = one 128-byte row per query, 128B swizzle
+          int off = acquire();               // level 1: [pair 2][row 4][col 8] = 128 bytes per query, 128B swizzle
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
-              st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(2 * r + ch) ^ sw) << 4),
-                           make_uint4(l1p[r][4 * ch], l1p[r][4 * ch + 1], l1p[r][4 * ch + 2], l1p[r][4 * ch + 3]));
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(st_u32 + off + lane * 128 + ((static_cast<uint32_t>(j) ^ sw) << 4),
+                         make_uint4(l1w[4 * j], l1w[4 * j + 1], l1w[4 * j + 2], l1w[4 * j + 3]));
           commit(&p.tmL[1], off, 0, t);
-          off = acquire();                   // level 2: 2 rows x 16 bytes = 32 bytes per query, 32B swizzle
+          off = acquire();                   // level 2: [row 2][col 8] = 32 bytes per query, 32B swizzle
 #pragma unroll
           for (int r = 0; r < 2; ++r)
             st_shared_v4(st_u32 + off + lane * 32 + ((static_cast<uint32_t>(r) ^ (static_cast<uint32_t>(lane >> 2) & 1u)) << 4),
-                         make_uint4(l2p[r][0], l2p[r][1], l2p[r][2], l2p[r][3]));
+                         make_uint4(l2w[4 * r], l2w[4 * r + 1], l2w[4 * r + 2], l2w[4 * r + 3]));
           commit(&p.tmL[2], off, 0, t);
           // level 3: 4 fp16 = 8 bytes per query and tile, below the 16-byte TMA granularity: stored by the thread
           if (qrow + lane < p.n)
-            *reinterpret_cast<uint2*>(p.l3 + ((static_cast<long long>(batch) * p.n + qrow + lane) * T + t) * 4) = l3p;
+            *reinterpret_cast<uint2*>(p.l3 + ((q_first + lane) * p.tiles3 + (t / p.tiles_w) * p.tiles_w3 + t % p.tiles_w) * 4) =
+                make_uint2(pack_half2(l3v[0], l3v[1]), pack_half2(l3v[2], l3v[3]));
         }
       } else {
       float hs1[16];   // horizontal pair sums of the previous (even) level-0 row
@@ -399,8 +441,8 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_cluster(&acc_empty[g], 0);   // the leader's MMA warp owns the accumulators of both CTAs
-        else mbar_arrive(&acc_empty[g]);
+        if constexpr (PAIR) mbar_arrive_cluster(&acc_empty[buf], 0);   // the leader's MMA warp owns the accumulators of both CTAs
+        else mbar_arrive(&acc_empty[buf]);
       }
     }
     if (lane == 0) bulk_wait_read<0>();             // shared memory stays valid until the last store has read it
@@ -440,6 +482,8 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
   p.w = w8;
   p.tiles_w = ceil_div(w8, 32);
   p.tiles = p.tiles_w * ceil_div(h8, 8);
+  p.tiles_w3 = (p.tiles_w + 1) & ~1;
+  p.tiles3 = p.tiles_w3 * ceil_div(h8, 8);
   p.alpha = alpha;
   p.dbg = env_switches().corr_dbg;
   p.l0 = static_cast<float*>(lvl[0]);
@@ -457,16 +501,18 @@ extern "C" int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t f
   {
     const int64_t dims[4] = {channels, w8, h8, batch};
     const int64_t str[3] = {fmap_pitch, (int64_t)w8 * fmap_pitch, (int64_t)n * fmap_pitch};
-    const uint32_t box[4] = {64, 32, pair ? 4u : 8u, 1};          // a CTA of a pair stages 4 of the 8 tile rows
+    // fp32 pyramid: whole 8 x 32 tile (a CTA of a pair stages 4 of its 8 rows); fp16 pyramid: 8 x 8 strips (see the kernel)
+    const uint32_t box[4] = {64, half_levels ? 8u : 32u, half_levels ? 8u : (pair ? 4u : 8u), 1};
     if (int e = make_map_f16(&p.tmB, fmap2, dims, str, box, ones, "fmap2")) return e;
   }
   if (half_levels) {
-    // tiled fp16 layout: level l = [batch * n, tiles, (8 >> l) * (32 >> l)], tiles = ceil(h8 / 8) * ceil(w8 / 32)
+    // strip fp16 layout (include/atdn_b200.h): level l = [batch * n, tiles, (8 >> l) * (32 >> l)], tiles = ceil(h8 / 8) * ceil(w8 / 32);
+    // level 3 = [batch * n, ceil(h8 / 8) * tiles_w3, 4] with tiles_w3 = tiles_w rounded up to even (pad tiles stay zero)
     for (int l = 0; l < 4; ++l) {
       const int el = 256 >> (2 * l);
       ATDN_REQUIRE(lvl[l] != nullptr && aligned16(lvl[l]) && lvl_pitch[l] == el, ATDN_ERR_ALIGN,
                    "atdn_corr_pyramid: tiled level %d needs a 16-byte aligned buffer with %d elements per tile (got %d)", l, el, lvl_pitch[l]);
-      if (l == 3) break;                             // 8-byte tiles: stored without TMA
+      if (l == 3) continue;                          // 8-byte tiles: stored without TMA
       const int64_t dims[4] = {el, p.tiles, n, batch};
       const int64_t str[3] = {el, (int64_t)p.tiles * el, (int64_t)n * p.tiles * el};
       const uint32_t box[4] = {l == 2 ? 16u : 64u, 1, 32, 1};

@@ -202,11 +202,16 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
-// arrive on the mbarrier at the same shared-memory offset in CTA `cta_rank` of this cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta_rank` of this cluster.
+// Plain form (default .release at CTA scope), as used for the "accumulator drained" hand-off of 2-CTA kernels: the
+// tcgen05.ld -> remote tcgen05.mma ordering is carried by tcgen05.fence::before_thread_sync / after_thread_sync around the
+// barrier.  The explicit `.release.cluster` form compiles to MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front
+// of the arrive, which also waits for every outstanding global / bulk store of the warp: 21% of all stall samples of the
+// pair corr-pyramid kernel sat on those fences (profiles/r02e_ncu_corr_pyramid_pair_*).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -75,6 +75,7 @@ _HALO_CFG = {64: (4, 64, True), 96: (2, 96, True), 128: (2, 128, True), 192: (1,
              576: (1, 192, False)}
 
 
+FMAP_SCALE = 0.25      # plan.buffer("fmap*") holds fnet(x) * FMAP_SCALE (see _EncoderWeights.out)
 _NO_FUSED_STATS = os.environ.get("ATDN_NO_FUSED_STATS") == "1"      # A/B switches (bench only)
 _NO_GRU_PRE = os.environ.get("ATDN_NO_GRU_PRE") == "1"
 _GRU_PRE32 = os.environ.get("ATDN_GRU_PRE32") == "1"
@@ -85,7 +86,21 @@ _Z16 = 0 if os.environ.get("ATDN_GRU_Z32") == "1" else L.F_Z16
 _H16 = 0 if os.environ.get("ATDN_GRU_H32") == "1" else L.F_H16
 
 
-def _halo(cout, taps=(3, 3)):
+# Small problems -- the reference's per-frame call (batch 1: 60 tiles of 16 x 8 pixels at 1/8 resolution for 148 SMs): the
+# throughput configurations above would occupy 15..60 CTAs, so the work is cut into single-CTA tiles of 128 pixels x 64
+# (128) outputs instead: 120 CTAs per layer (profiles/r02d_ncu_launches_batch1_forward.csv: 18..29 us per GRU conv launch).
+_HALO_SMALL = {64: (1, 64), 128: (1, 64), 192: (1, 64), 256: (1, 128)}
+_SMALL_TILES = 128       # "small" = at most this many 16 x 8-pixel tiles in the whole batch
+
+
+def _is_small(x):
+    return x.B * math.ceil(x.H / 16) * math.ceil(x.W / 8) <= _SMALL_TILES
+
+
+def _halo(cout, taps=(3, 3), small=False):
+    if small and cout in _HALO_SMALL:
+        mt, bn = _HALO_SMALL[cout]
+        return {"mt": mt, "bn": bn, "flags": 0}
     mt, bn, pair = _HALO_CFG[cout]
     if taps == (1, 1) and cout == 256:
         pair = False
@@ -94,7 +109,7 @@ def _halo(cout, taps=(3, 3)):
 
 def _conv_s1(x, c, out, *, cout, taps, flags=0, **kw):
     """Stride-1 convolution on the halo kernel; `c` is a _Conv."""
-    cfg = _halo(cout, taps)
+    cfg = _halo(cout, taps, _is_small(x) and not (flags & L.F_STATS))
     return ops.conv_tc(x, c.wp, c.bias, out, cout=cout, taps=taps, pad=(taps[0] // 2, taps[1] // 2), bn=cfg["bn"],
                        mt=cfg["mt"], flags=flags | cfg["flags"], **kw)
 
@@ -126,7 +141,7 @@ class _Conv:
 
 
 class _EncoderWeights:
-    def __init__(self, sd, p, norm):
+    def __init__(self, sd, p, norm, out_scale=1.0):
         self.norm = norm
 
         def conv(name, bn_name=None):
@@ -148,14 +163,16 @@ class _EncoderWeights:
                 if st != 1:
                     blk["down"] = _Conv(*conv(q + "downsample.0", q + "downsample.1"))
                 self.blocks.append(blk)
-        self.out = _Conv(sd[p + "conv2.weight"], sd[p + "conv2.bias"])
+        # out_scale (a power of two, exact in fp16): the feature net stores fmap / 4, so that <fmap1, fmap2> already carries
+        # the 1/sqrt(256) = 2^-4 of corr.py:62 and the pyramid epilogue skips 256 multiplies per query and tile
+        self.out = _Conv(sd[p + "conv2.weight"].float() * out_scale, sd[p + "conv2.bias"].float() * out_scale)
 
 
 class _Packed:
     """All GMA weights in kernel layouts (built once per device from the module's state dict)."""
 
     def __init__(self, sd):
-        self.fnet = _EncoderWeights(sd, "fnet.", "instance")
+        self.fnet = _EncoderWeights(sd, "fnet.", "instance", out_scale=FMAP_SCALE)
         self.cnet = _EncoderWeights(sd, "cnet.", "batch")
         u = "update_block."
         g = lambda n: (sd[u + n + ".weight"], sd[u + n + ".bias"])
@@ -454,7 +471,7 @@ class RAFTGMA(nn.Module):
         h8, w8, n, np_ = plan.h8, plan.w8, plan.n, plan.np_
         m_tiles = b * math.ceil(h8 / 8) * math.ceil(w8 / 16)
         # fp32-accumulated all-pairs correlation pyramid (corr.py:16-30), rounded to fp16 on store
-        ops.corr_pyramid_build(fmap1, fmap2, plan.pyr)
+        ops.corr_pyramid_build(fmap1, fmap2, plan.pyr, alpha=1.0 / (math.sqrt(256.0) * FMAP_SCALE * FMAP_SCALE))
 
         # context network: net = tanh(.) -> HX[0:128] + h32, inp = relu(.) -> HX[128:256]
         hx = plan.hx
@@ -516,7 +533,7 @@ class RAFTGMA(nn.Module):
         d.out, d.out_pitch = L.ptr(plan.vt), np_
         L.tc_gemm(d)
         ops.gemm_rows(L.ptr(plan.p16), n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
-                      b_bstride=128 * np_, bn=128, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
+                      b_bstride=128 * np_, bn=64 if b * math.ceil(n / 128) <= _SMALL_TILES else 128, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
                       aux32=plan.inv_sum, gamma=wts.gamma)
 
     def _update(self, plan, wts, m_tiles):
@@ -531,11 +548,12 @@ class RAFTGMA(nn.Module):
         _conv_s1(View(plan.c1), c, View(plan.corflo, 0, 192), cout=192, taps=(3, 3), flags=R)
         ops.flow_pack(plan.flow, plan.fpack)
         c = wts.convf1
-        ops.conv_tc(View(plan.fpack, 0, 14), c.wp, c.bias, View(plan.f1), cout=128, taps=(7, 1), pad=(3, 0), bn=128, mt=2,
-                    flags=R | L.F_PAIR)
+        small = _is_small(View(plan.f1))
+        ops.conv_tc(View(plan.fpack, 0, 14), c.wp, c.bias, View(plan.f1), cout=128, taps=(7, 1), pad=(3, 0), bn=64 if small else 128,
+                    mt=1 if small else 2, flags=R | (0 if small else L.F_PAIR))
         c = wts.convf2
-        ops.conv_tc(View(plan.f1), c.wp, c.bias, View(plan.corflo, 192, 64), cout=64, taps=(3, 3), pad=(1, 1), bn=64, mt=2,
-                    flags=R | L.F_PAIR)
+        ops.conv_tc(View(plan.f1), c.wp, c.bias, View(plan.corflo, 192, 64), cout=64, taps=(3, 3), pad=(1, 1), bn=64, mt=1 if small else 2,
+                    flags=R | (0 if small else L.F_PAIR))
         c = wts.conv
         _conv_s1(View(plan.corflo), c, View(hx, 256, 128), cout=128, taps=(3, 3), flags=R | L.F_FLOWTAIL, aux32=plan.flow)
         self._aggregate(plan, wts)

@@ -197,25 +197,41 @@ def pyramid_shapes(h8, w8):
 
 def alloc_pyramid(batch, h8, w8, device, half_levels=0):
     """The four pyramid levels.  ``half_levels=0``: the reference's fp32 pyramid, row-major [B*N, H_l, pitch_l]
-    (``CorrBlock`` drop-in).  ``half_levels=4`` (the sequence pipeline): fp16 in the TILED layout of
-    ``atdn_corr_pyramid``: level l = [B*N, tiles, (8 >> l) * (32 >> l)], tiles = ceil(h8/8) * ceil(w8/32) -- what one
-    8 x 32 target tile contributes to a query's map is contiguous, so the kernel's stores are long runs."""
+    (``CorrBlock`` drop-in).  ``half_levels=4`` (the sequence pipeline): fp16 in the STRIP layout of
+    ``atdn_corr_pyramid`` (include/atdn_b200.h): level l = [B*N, tiles, chunk_l] with tiles = ceil(h8/8) * ceil(w8/32)
+    8 x 32-texel target tiles and, inside a tile's chunk,
+      level 0: [strip 4][row 8][col 8]   level 1: [strip pair 2][row 4][col 8]   level 2: [row 2][col 8]
+    level 3: [B*N, ceil(h8/8) * tiles_w3, 4] (one row of 4 texels per tile, tile columns padded to an even count; the pad
+    tiles are never written and must stay zero, hence ``zeros``).  A 64-byte DRAM fetch granule of the lookup is a
+    4 x 8-texel block at levels 0 / 1, and every row piece of 8 texels is 16-byte aligned at every level."""
     n = h8 * w8
     if half_levels:
         assert half_levels == 4
-        tiles = ((h8 + 7) // 8) * ((w8 + 31) // 32)
-        return [torch.empty(batch * n, tiles, 256 >> (2 * l), dtype=torch.float16, device=device) for l in range(4)]
+        th, tw = (h8 + 7) // 8, (w8 + 31) // 32
+        lv = [torch.empty(batch * n, th * tw, 256 >> (2 * l), dtype=torch.float16, device=device) for l in range(3)]
+        lv.append(torch.zeros(batch * n, th * ((tw + 1) // 2 * 2), 4, dtype=torch.float16, device=device))
+        return lv
     return [torch.empty(batch * n, h, p, dtype=torch.float32, device=device) for (h, w, p) in pyramid_shapes(h8, w8)]
 
 
-def pyramid_untile(levels, h8, w8):
-    """Tiled fp16 pyramid -> list of row-major fp32 [B*N, H_l, W_l] tensors (tests / inspection)."""
+def pyramid_untile(levels, h8, w8, padded=False):
+    """Strip-layout fp16 pyramid -> list of row-major fp32 [B*N, H_l, W_l] tensors (tests / inspection);
+    ``padded``: keep the whole tile grid (the texels outside the maps, which the kernel writes as zeros)."""
     th, tw = (h8 + 7) // 8, (w8 + 31) // 32
+    nq = levels[0].shape[0]
     out = []
-    for l, t in enumerate(levels):
-        rh, rw = 8 >> l, 32 >> l
-        x = t.float().view(t.shape[0], th, tw, rh, rw).permute(0, 1, 3, 2, 4).reshape(t.shape[0], th * rh, tw * rw)
-        out.append(x[:, : h8 >> l, : w8 >> l].contiguous())
+    # level 0: [q, th, tw, strip 4, row 8, col 8] -> [q, th*8, tw*32]
+    x = levels[0].float().view(nq, th, tw, 4, 8, 8).permute(0, 1, 4, 2, 3, 5).reshape(nq, th * 8, tw * 32)
+    out.append(x if padded else x[:, :h8, :w8].contiguous())
+    # level 1: [q, th, tw, pair 2, row 4, col 8] -> [q, th*4, tw*16]
+    x = levels[1].float().view(nq, th, tw, 2, 4, 8).permute(0, 1, 4, 2, 3, 5).reshape(nq, th * 4, tw * 16)
+    out.append(x if padded else x[:, : h8 >> 1, : w8 >> 1].contiguous())
+    # level 2: [q, th, tw, row 2, col 8] -> [q, th*2, tw*8]
+    x = levels[2].float().view(nq, th, tw, 2, 8).permute(0, 1, 3, 2, 4).reshape(nq, th * 2, tw * 8)
+    out.append(x if padded else x[:, : h8 >> 2, : w8 >> 2].contiguous())
+    # level 3: [q, th, tw3, 4] -> [q, th, tw3*4]
+    x = levels[3].float().view(nq, th, -1)
+    out.append(x if padded else x[:, : h8 >> 3, : w8 >> 3].contiguous())
     return out
 
 
@@ -223,8 +239,9 @@ def _half_levels(levels):
     return sum(1 for t in levels if t.dtype == torch.float16)
 
 
-def corr_pyramid_build(fmap1, fmap2, levels, legacy=False, pair=False):
-    """fmap1/fmap2: Views [B,H8,W8,256] fp16 -> the 4 fp32 pyramid levels (corr.py:16-30, 55-63)."""
+def corr_pyramid_build(fmap1, fmap2, levels, legacy=False, pair=False, alpha=None):
+    """fmap1/fmap2: Views [B,H8,W8,256] fp16 -> the 4 pyramid levels (corr.py:16-30, 55-63).  ``alpha``: scale of the
+    volume, default 1/sqrt(C) (corr.py:62); the flow net passes 1.0 after folding 2^-2 into each feature map."""
     b, h8, w8 = fmap1.B, fmap1.H, fmap1.W
     n = h8 * w8
     if not legacy:
@@ -234,7 +251,7 @@ def corr_pyramid_build(fmap1, fmap2, levels, legacy=False, pair=False):
 
         def go():
             L.check(L.load().atdn_corr_pyramid(fmap1.ptr(), fmap2.ptr(), C.c_int64(fmap1.pitch), fmap1.c, lv, lp, _half_levels(levels), b, h8, w8,
-                                               C.c_float(1.0 / math.sqrt(fmap1.c)), L.stream_ptr()), "atdn_corr_pyramid")
+                                               C.c_float(1.0 / math.sqrt(fmap1.c) if alpha is None else alpha), L.stream_ptr()), "atdn_corr_pyramid")
         if L.PROFILER is not None:
             # algorithmic: 2*N*N*C flop; bytes = the four levels written + both feature maps read once
             nbytes = sum(float(levels[l].element_size()) * b * n * (h8 >> l) * (w8 >> l) for l in range(4)) + 2.0 * b * n * fmap1.c * 2

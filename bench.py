@@ -192,7 +192,7 @@ def online_latency(flow, vo, dev_frames, reps=10, warm=2):
     dt = (time.perf_counter() - t0) / reps
     vo.reset_lstm()
     return {"ms_per_pair": 1e3 * dt, "pairs_per_s": 1.0 / dt, "pairs": reps,
-            "note": "batch 1, eager launches, host sync per frame (wall clock); the metric above batches 54 pairs"}
+            "note": "batch 1, forward() graph replays, host sync per frame (wall clock); the metric above batches 54 pairs"}
 
 
 def localization_extras(dev, frame, pk, keyframes=8192, reps=10):
@@ -230,6 +230,107 @@ def localization_extras(dev, frame, pk, keyframes=8192, reps=10):
     return {"embed_ms_per_frame": embed_ms, "embedding_dim": dim,
             "search": {"keyframes": len(index), "ms": search_ms, "gbs": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"],
                        "found_planted_row": found == len(index) - 1}}
+
+
+def training_shape_extra(flow, vo, dev, reps=2):
+    """BASELINE.json configs[2] (train_odometry.py:32-48): 24 sequences x 7 frames = 144 frame pairs at 376x1241 (resized to
+    the SLAM size), flow for every pair, then ATDNVO on batch 24 x 6 steps (one stateful scan with a reset before it).
+    CUDA events on the launching stream; frames resident."""
+    from atdn_vslam_b200 import synth
+    from atdn_vslam_b200.sequence import preprocess
+    seqs, steps, per = 24, 6, 8                      # 8 sequences (48 pairs) per flow batch
+    frames = torch.stack([preprocess(synth.frame_sequence(steps + 1, H_RAW, W_RAW, seed=500 + i).to(dev)) for i in range(seqs)])   # [24,7,3,376,1232]
+    vo24 = type(vo)(batch_size=seqs)
+    vo24.load_state_dict(vo.state_dict())
+    vo24 = vo24.to(dev).eval()
+
+    def step():
+        feats = []
+        for s in range(0, seqs, per):
+            im1 = frames[s:s + per, :-1].reshape(-1, 3, *frames.shape[-2:])
+            im2 = frames[s:s + per, 1:].reshape(-1, 3, *frames.shape[-2:])
+            _, up = flow(im1, im2, iters=12, test_mode=True)
+            feats.append(vo24.encode(up).view(per, steps, 512))
+        f = torch.cat(feats, 0).transpose(0, 1).contiguous()      # [6, 24, 512]
+        vo24.reset_lstm()
+        return vo24.recurrent_scan(f)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(reps):
+        rot, tr = step()
+    s1.record()
+    torch.cuda.synchronize()
+    ms = s0.elapsed_time(s1) / reps
+    return {"workload": "24 sequences x 6 pairs (144 pairs), flow batch 48 through forward(), ATDNVO batch 24 x 6-step scan",
+            "ms_per_step": ms, "pairs_per_s": seqs * steps / (ms / 1e3), "finite": bool(torch.isfinite(rot).all() and torch.isfinite(tr).all())}
+
+
+def sharded_search_extra(dev, rank, world, pk, rows_per_gpu=131072, dim=15360, reps=5):
+    """BASELINE.json configs[4] (neural_slam.py:373-384 over a synthetic database): K = 1 048 576 / 8 keyframe embeddings PER GPU
+    (8 GB of fp32 rows each), row-sharded across the ranks, planted duplicates of the query on two different ranks: the global
+    first minimum must be the LOWER global index.  Reports the local scan as HBM GB/s per GPU (max time over ranks)."""
+    import torch.distributed as dist
+    from atdn_vslam_b200.localization import KeyframeIndex
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    index = KeyframeIndex(dim=dim, capacity=rows_per_gpu, device=dev)
+    for s in range(0, rows_per_gpu, 8192):
+        index.add(torch.randn(min(8192, rows_per_gpu - s), dim, device=dev, generator=g))
+    q = torch.randn(dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    # plant the query itself at local row 1234 of the LAST rank and at local row 77 of the middle rank
+    plant = {world - 1: 1234, world // 2: 77} if world > 1 else {0: 1234}
+    if rank in plant:
+        index._db[plant[rank]] = q
+    expect = min(r * rows_per_gpu + i for r, i in plant.items())
+    if world > 1:
+        gi, gd = index.search_sharded(q)
+    else:
+        gi, d = index.search(q)
+        gd = float(d[gi])
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(reps):
+        index.search_device(q)
+    s1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s0.elapsed_time(s1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    gbs = rows_per_gpu * dim * 4 / (ms * 1e-3) / 1e9
+    return {"keyframes_total": rows_per_gpu * world, "rows_per_gpu": rows_per_gpu, "embedding_dim": dim, "local_scan_ms_max": ms,
+            "gbs_per_gpu": gbs, "frac_of_hbm_peak": gbs / pk["hbm_gbs"], "global_index": int(gi), "expected_index": int(expect),
+            "index_exact": int(gi) == int(expect), "distance": float(gd)}
+
+
+def torch_eager_extra(dev, dev_frames, pairs=6):
+    """The 'bar to beat' of SURVEY.md 8(d): the reference's own CUDA path = PyTorch eager (cuDNN / cuBLAS) under its fp16 autocast
+    regions, one pair per call with a host read per frame -- here the oracle port (same ATen calls, same cast regions) on THIS
+    GPU.  Wall clock over consecutive pairs after 2 warm-up pairs."""
+    from atdn_vslam_b200 import synth
+    from oracle import clvo_oracle, gma_oracle
+    gsd = {k: v.to(dev) for k, v in synth.gma_state_dict().items()}
+    vsd = {k: v.to(dev) for k, v in synth.atdnvo_state_dict().items()}
+    st = clvo_oracle.zero_state(device=dev)
+
+    def pair(t):
+        _, up = gma_oracle.raftgma_forward(gsd, dev_frames[t:t + 1], dev_frames[t + 1:t + 2], iters=12, aten_ops=True, mixed_precision=True)
+        rot, tr = clvo_oracle.atdnvo_forward(vsd, up.float(), st)
+        return rot.cpu(), tr.cpu()
+
+    for t in range(2):
+        pair(t)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(2, 2 + pairs):
+        pair(t)
+    dt = (time.perf_counter() - t0) / pairs
+    return {"ms_per_pair": 1e3 * dt, "pairs_per_s": 1.0 / dt, "pairs": pairs,
+            "note": "oracle port on cuda: torch eager, cuDNN/cuBLAS, fp16 autocast regions of network.py:85,93,112, batch 1, host read per pair"}
 
 
 def run_ours(args):
@@ -364,9 +465,15 @@ def run_ours(args):
     if shard_timing is not None:
         line["sharding"] = shard_timing
 
+    pk = peaks()
+    if not args.no_extras:
+        try:     # every rank takes part (row-sharded database, NCCL exchange of the per-rank minima)
+            line["sharded_keyframe_search"] = sharded_search_extra(dev, rank, world, pk)
+        except Exception as exc:
+            line["sharded_keyframe_search"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        torch.cuda.empty_cache()
     if rank == 0:
         # ---- per-kernel timing (eager, events on the launching stream) + roofline of the dominant kernel
-        pk = peaks()
         prof = KernelProfile()
         eager = OdometryPipeline(flow, vo, batch_pairs=args.batch_pairs, iters=12, use_graphs=False)
         eager.pair_features(dev_frames[: args.batch_pairs + 1])
@@ -441,6 +548,15 @@ def run_ours(args):
             line["localization"] = localization_extras(dev, dev_frames[0:1], pk)
         except Exception as exc:
             line["localization"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        if world == 1 and not args.no_extras:
+            try:
+                line["training_shape_b24x6"] = training_shape_extra(flow, vo, dev)
+            except Exception as exc:
+                line["training_shape_b24x6"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+            try:
+                line["torch_eager_b200"] = torch_eager_extra(dev, dev_frames)
+            except Exception as exc:
+                line["torch_eager_b200"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         # ---- CPU baseline (oracle port of the reference device=cpu path) on a bounded sample
         if world == 1 and not args.no_cpu_baseline:
             v, dt = cpu_pairs_per_s(args.cpu_pairs, warm=1)
@@ -465,6 +581,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=12)
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2] / configs[4] / torch-eager extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

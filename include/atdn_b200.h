@@ -155,12 +155,22 @@ int atdn_tc_gemm(const atdn_tc_desc* desc, void* stream);
  * and written with TMA stores (full 128-byte runs per query row); columns [W_l, ceil4(W_l)) of a row may be
  * overwritten with pad values (16-byte store granularity).
  * half_levels = 0: all four levels fp32 (the reference's corr_pyramid, bit-for-bit layout of its values).
- * half_levels = 4: all levels are stored as fp16 in a TILED layout, lvl[l] = [batch*n, tiles, (8>>l)*(32>>l)] with
- *   tiles = ceil(h8/8)*ceil(w8/32) and texel (y, x) of level l at tile (y >> (3-l))*ceil(w8/32) + (x >> (5-l)),
- *   offset (y & ((8>>l)-1))*(32>>l) + (x & ((32>>l)-1)); lvl_pitch[l] must be the tile size (256, 64, 16, 4).  Each
- *   level is pooled from the un-rounded fp32 values of the level below and rounded once.  The kernel is bound by its HBM stores, so this halves its time
- *   (and the lookup's read traffic); the end-to-end flow moves by 8e-4 px mean
- *   (tools/fp16_pyramid_sensitivity.py), inside the 1e-2 px bar.
+ * half_levels = 4: all levels are stored as fp16 in the STRIP layout: the target map is cut into tiles of 8 x 32 texels
+ *   (tiles_w = ceil(w8/32), tiles = ceil(h8/8) * tiles_w) and lvl[l] = [batch*n, tiles, chunk_l], chunk = 256 / 64 / 16;
+ *   lvl_pitch[l] must be the chunk size (256, 64, 16, 4).  Texel (y, x) of level l lives in tile
+ *   (y >> (3-l)) * tiles_w + (x >> (5-l)) at chunk offset
+ *     level 0: ((x >> 3) & 3) * 64 + (y & 7) * 8 + (x & 7)      [strip 4][row 8][col 8]
+ *     level 1: ((x >> 3) & 1) * 32 + (y & 3) * 8 + (x & 7)      [strip pair 2][row 4][col 8]
+ *     level 2:                      (y & 1) * 8 + (x & 7)       [row 2][col 8]
+ *   and level 3 is lvl[3] = [batch*n, ceil(h8/8) * tiles_w3, 4] with tiles_w3 = tiles_w rounded up to even: texel (y, x) at
+ *   (y * tiles_w3 + (x >> 2)) * 4 + (x & 3); the pad tile column is never written and must be zero (allocate it zeroed).
+ *   Equivalently, at every level the half offset inside a query's maps is rowpart(y) + (x >> 3) * (64 >> l) + (x & 7) with
+ *   rowpart(y) = (y >> (3-l)) * tiles_w * chunk_l + (y & ((8 >> l) - 1)) * 8: every 8-texel row piece is 16-byte aligned, and
+ *   a 64-byte HBM fetch granule is a 4 x 8-texel block at levels 0 / 1 (the L2 of the B200 fetches 64-byte granules).
+ *   Texels of a tile that lie outside the level's map (H_l x W_l) are written as ZEROS, so a reader can stage windows
+ *   without masking.  Each level is pooled from the un-rounded fp32 values of the level below and rounded once.  The kernel
+ *   is bound by its HBM stores, so fp16 halves its time (and the lookup's read traffic); the end-to-end flow moves by
+ *   8e-4 px mean (tools/fp16_pyramid_sensitivity.py), inside the 1e-2 px bar.
  * ---------------------------------------------------------------------------------------------- */
 int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t fmap_pitch, int32_t channels,
                       void* const lvl[4], const int32_t lvl_pitch[4], int32_t half_levels, int32_t batch,
@@ -181,9 +191,11 @@ int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, int64_t p_pit
 /* ------------------------------------------------------------------------------------------------
  * Correlation lookup -- GMA.whl!/GMA/core/corr.py:32-53 + utils/utils.py:59-73 (grid_sample).
  * coords: fp32 [B, H8, W8, 2] (x, y); levels and half_levels (0 or 4) as written by atdn_corr_pyramid;
- * the fp16 path blends the 10x10 window separably with one fractional offset per level (grid_sample's per-tap
- * coordinate round trip, an ulp-level perturbation, is dropped);
- * out: fp16 [B*H8*W8, out_pitch], channel = level*81 + a*9 + b  (a offsets x, b offsets y).
+ * the fp16 path stages the windows with cp.async (zero fill outside the padded maps) and blends the 10x10 window
+ * separably with one fractional offset per level (grid_sample's per-tap coordinate round trip, an ulp-level
+ * perturbation, is dropped);
+ * out: fp16 [B*H8*W8, out_pitch], channel = level*81 + a*9 + b  (a offsets x, b offsets y); out32 (optional): the
+ * un-rounded fp32 results [B*H8*W8, 324].
  * ---------------------------------------------------------------------------------------------- */
 int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitch[4], int32_t half_levels, const float* coords,
                      void* out16, int64_t out_pitch, float* out32_or_null,

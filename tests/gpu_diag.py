@@ -85,7 +85,7 @@ def check_conv(cin=64, cout=64, kh=3, kw=3, stride=1, h=20, w=37, batch=2, bn=64
 
 
 
-def check_gru(mt=2, kind="zr", h=37, w=45, batch=2, taps=(1, 5), pair=False, bn=128):
+def check_gru(mt=2, kind="zr", h=37, w=45, batch=2, taps=(1, 5), pair=False, bn=128, qbn=None):
     """SepConvGRU epilogues of the halo kernel against a PyTorch fp32 reference of the same op (update.py:48-63)."""
     import torch
     import torch.nn.functional as F
@@ -122,7 +122,7 @@ def check_gru(mt=2, kind="zr", h=37, w=45, batch=2, taps=(1, 5), pair=False, bn=
         hxd = hx.cuda()
         out = torch.full((batch, h, w, 128), float("nan"), dtype=torch.half, device="cuda")
         ops.conv_tc(ops.View(rhx.cuda()), ops.pack_conv_weight(wt.float().cuda()), ops.pad_bias(bias.cuda()), ops.View(out), cout=128,
-                    taps=taps, pad=pad, bn=128 if mt <= 2 else 64, epi=L.EPI_GRU_Q, a2=ops.View(hxd, 128, 384), h32=h32d,
+                    taps=taps, pad=pad, bn=qbn or (128 if mt <= 2 else 64), epi=L.EPI_GRU_Q, a2=ops.View(hxd, 128, 384), h32=h32d,
                     z32=ops.state_from_nhwc(z.view(batch, h, w, 128).cuda()), mt=mt, flags=L.F_PAIR if pair else 0)
         torch.cuda.synchronize()
         ok &= _cmp(f"gru_q h32 mt={mt} taps={taps} pair={pair}", ops.state_to_nhwc(h32d, h, w).reshape(-1, 128), h_ref, 2e-3)
@@ -436,6 +436,13 @@ CHECKS = {
     "halo_conv5x1": lambda: check_conv(cin=128, cout=128, kh=5, kw=1, bn=64, relu=True, mt=4),
     "halo_conv_big": lambda: check_conv(cin=64, cout=64, bn=64, mt=4, h=94, w=154, batch=3),
     "halo_gru_zr": lambda: check_gru(2, "zr"),
+    "small_gru_zr_mt1_bn128": lambda: check_gru(1, "zr", bn=128),
+    "small_gru_zr_mt1_bn128_5x1": lambda: check_gru(1, "zr", taps=(5, 1), bn=128),
+    "small_gru_q_mt1_bn64": lambda: check_gru(1, "q", qbn=64),
+    "small_gru_q_mt1_bn64_5x1": lambda: check_gru(1, "q", taps=(5, 1), qbn=64),
+    "small_conv3x3_mt1_bn64": lambda: check_conv(cin=256, cout=192, bn=64, mt=1, relu=True),
+    "small_conv1x1_mt1_bn128": lambda: check_conv(cin=324, cout=256, kh=1, kw=1, bn=128, mt=1),
+    "small_conv3x3_c64_mt1_bn64": lambda: check_conv(cin=128, cout=64, bn=64, mt=1, relu=True),
     "halo_gru_zr_5x1": lambda: check_gru(2, "zr", taps=(5, 1)),
     "halo_gru_q": lambda: check_gru(2, "q"),
     "halo_gru_q_mt4": lambda: check_gru(4, "q", taps=(5, 1)),

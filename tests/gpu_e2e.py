@@ -60,7 +60,8 @@ def check_gma_small():
     torch.cuda.synchronize()
     plan = next(iter(m._plans.values()))
     ok = True
-    fm = plan.buffer("fmap", (2, 16, 20, 256), torch.float16).float().permute(0, 3, 1, 2)
+    from atdn_vslam_b200.gma import FMAP_SCALE
+    fm = plan.buffer("fmap", (2, 16, 20, 256), torch.float16).float().permute(0, 3, 1, 2) / FMAP_SCALE
     ok &= _stat("fnet fmap1", fm[:1], torch.from_numpy(g["fmap1"]), 5e-3)
     ok &= _stat("fnet fmap2", fm[1:], torch.from_numpy(g["fmap2"]), 5e-3)
     ok &= _stat("cnet inp", plan.hx[..., 128:256].float().permute(0, 3, 1, 2), torch.from_numpy(g["inp"]), 5e-3)

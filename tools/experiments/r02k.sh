@@ -1,0 +1,8 @@
+#!/bin/bash
+set -x
+O=gpurun_out
+python -m pytest tests -m gpu -q -x > $O/k_pytest.log 2>&1; echo "rc=$?" >> $O/k_pytest.log
+python tools/experiments/lookup_bench.py > $O/k_lookup.txt 2>&1
+python tools/experiments/exp_corr.py > $O/k_exp_corr.txt 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'corr_lookup|corr_pyramid' -c 2 -o $O/k_ncu python tools/ncu_batch.py 27 1 > $O/k_ncu.log 2>&1
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras > $O/k_bench.json 2> $O/k_bench.err

@@ -38,6 +38,15 @@ def main():
     bp = int(sys.argv[1]) if len(sys.argv) > 1 else 27
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     dev = torch.device("cuda:0")
+    torch.zeros(1, device=dev)
+    if os.environ.get("ATDN_L2_GRAN"):      # experiment: cudaLimitMaxL2FetchGranularity (0x05) = 32 / 64 / 128
+        import ctypes
+        import glob
+        rt = ctypes.CDLL(glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*"))[0] if glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*")) else "libcudart.so.12")
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["ATDN_L2_GRAN"])))
+        got = ctypes.c_size_t(0)
+        rt.cudaDeviceGetLimit(ctypes.byref(got), 5)
+        print("cudaLimitMaxL2FetchGranularity ->", got.value, "rc", rc, flush=True)
     flow = RAFTGMA(Args())
     flow.load_state_dict(synth.gma_state_dict(module_prefix=True))
     flow = flow.to(dev).eval()

@@ -305,11 +305,16 @@ class RAFTGMA(nn.Module):
         self._graphs = {}          # captured forward() graphs per (batch, H, W, iters, device)
         self.generation = 0        # bumped whenever packed weights / plans are dropped: captured CUDA graphs hold raw pointers
         self.capture_forward = os.environ.get("ATDN_NO_FORWARD_GRAPH") != "1"
+        # feature-map reuse across consecutive calls (the caller's loop passes the previous frame again as image1,
+        # neural_slam.py:199-217): (plan key, previous image2 tensor -- kept alive so that its memory cannot be recycled --, version)
+        self.reuse_fmap = os.environ.get("ATDN_NO_FMAP_REUSE") != "1"
+        self._last_pair = None
 
     # -- weight handling --------------------------------------------------------------------------
     def _invalidate(self, plans=False):
         self._packed = {}
         self._graphs = {}
+        self._last_pair = None
         if plans:
             self._plans = {}
         self.generation += 1
@@ -339,8 +344,10 @@ class RAFTGMA(nn.Module):
         return self._plans[key]
 
     # -- encoders -----------------------------------------------------------------------------------
-    def _encoder(self, plan, ew, images, out_view, final_flags=0, h32=None):
-        """BasicEncoder (extractor.py:165-189) on ``images`` [n,3,H,W] fp32 -> out_view [n,H8,W8,256]."""
+    def _encoder(self, plan, ew, images, out_view, final_flags=0, h32=None, xpack=None):
+        """BasicEncoder (extractor.py:165-189) on ``images`` [n,3,H,W] fp32 -> out_view [n,H8,W8,256].  ``xpack``: the
+        row-packed normalised input of these images when another encoder call already produced it (both networks see
+        2 * x / 255 - 1, network.py:75-76): the context net reuses the feature net's pack of the same frames."""
         n = images.shape[0]
         sc = plan.encoder_scratch(n, images.device)
         inst = ew.norm == "instance"
@@ -358,9 +365,11 @@ class RAFTGMA(nn.Module):
         # 64-channel layers at 1/2 resolution (70% of the normalised bytes): statistics come out of the conv epilogue
         fuse64 = inst and not _NO_FUSED_STATS
         st64 = {"flags": L.F_STATS, "aux32": sc["scratch"]} if fuse64 else {"flags": 0}
-        ops.stem_pack(images, sc["xpack"])
+        if xpack is None:
+            xpack = sc["xpack"]
+            ops.stem_pack(images, xpack)
         r2 = sc["r2"]
-        ops.conv_tc(View(sc["xpack"]), ew.stem.wp, ew.stem.bias, View(r2[0]), cout=64, taps=(4, 1), pad=(2, 0), bn=64, mt=4,
+        ops.conv_tc(View(xpack), ew.stem.wp, ew.stem.bias, View(r2[0]), cout=64, taps=(4, 1), pad=(2, 0), bn=64, mt=4,
                     flags=relu | st64["flags"], aux32=st64.get("aux32"), out_hw=(h2, w2))   # single CTAs: measured faster than pairs for K = 4 x 48
         x = View(r2[0])
         if inst:
@@ -411,35 +420,57 @@ class RAFTGMA(nn.Module):
         dev = image1.device
         L.check(L.load().atdn_check_device(dev.index if dev.index is not None else torch.cuda.current_device()),
                 "atdn_check_device")
+        reuse = self._same_as_last_image2(image1)
         if test_mode and self.capture_forward and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graphed(image1, image2, iters, flow_init)
-        return self._forward_eager(image1, image2, iters, flow_init, test_mode)
+            out = self._forward_graphed(image1, image2, iters, flow_init, reuse)
+        else:
+            out = self._forward_eager(image1, image2, iters, flow_init, test_mode, reuse)
+        self._last_pair = ((tuple(image1.shape), str(dev)), image2, image2._version) if self.reuse_fmap else None
+        return out
 
-    def _forward_eager(self, image1, image2, iters, flow_init, test_mode):
+    def _same_as_last_image2(self, image1):
+        """True when ``image1`` is (a view of) the tensor that was ``image2`` of the previous call, unmodified: its feature
+        map is still in the plan's buffer, so the feature net only has to run on the new frame (instance norm is per
+        image: same values as running both frames)."""
+        lp = self._last_pair
+        if lp is None or not self.reuse_fmap:
+            return False
+        key, prev, version = lp
+        return (key == (tuple(image1.shape), str(image1.device)) and prev.data_ptr() == image1.data_ptr() and prev.dtype == image1.dtype
+                and prev.stride() == image1.stride() and prev._version == version == image1._version)
+
+    def _forward_eager(self, image1, image2, iters, flow_init, test_mode, reuse=False):
         dev = image1.device
         b, _, h, w = image1.shape
         image1 = image1.float().contiguous()
         image2 = image2.float().contiguous()
         wts = self._weights(dev)
         plan = self._plan(b, h, w, dev)
-        # feature network on both frames as one batch of 2B (extractor.py:168-171)
         fmap = plan.buffer("fmap", (2 * b, plan.h8, plan.w8, 256), torch.float16)
-        self._encoder(plan, wts.fnet, torch.cat([image1, image2], 0), View(fmap))
-        return self._flow(plan, wts, image1, View(fmap[:b]), View(fmap[b:]), iters, flow_init, test_mode)
+        if reuse:
+            # fmap[b:] still holds fnet(previous image2) = fnet(image1): move it, encode the new frame only
+            fmap[:b].copy_(fmap[b:])
+            self._encoder(plan, wts.fnet, image2, View(fmap[b:]))
+            xpack = None
+        else:
+            # feature network on both frames as one batch of 2B (extractor.py:168-171)
+            self._encoder(plan, wts.fnet, torch.cat([image1, image2], 0), View(fmap))
+            xpack = plan.encoder_scratch(2 * b, dev)["xpack"][:b]
+        return self._flow(plan, wts, image1, View(fmap[:b]), View(fmap[b:]), iters, flow_init, test_mode, xpack=xpack)
 
-    def _forward_graphed(self, image1, image2, iters, flow_init):
-        key = (tuple(image1.shape), image1.dtype, iters, str(image1.device), None if flow_init is None else tuple(flow_init.shape))
+    def _forward_graphed(self, image1, image2, iters, flow_init, reuse=False):
+        key = (tuple(image1.shape), image1.dtype, iters, str(image1.device), None if flow_init is None else tuple(flow_init.shape), reuse)
         g = self._graphs.get(key)
         if g is None:                       # first sighting of this shape: eager (packs weights, sizes the plan)
             self._graphs[key] = "seen"
-            return self._forward_eager(image1, image2, iters, flow_init, True)
+            return self._forward_eager(image1, image2, iters, flow_init, True, reuse)
         if g == "seen":                     # second sighting: capture
             s1, s2 = image1.clone(), image2.clone()
             sf = None if flow_init is None else flow_init.clone()
             torch.cuda.synchronize(image1.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                out = self._forward_eager(s1, s2, iters, sf, True)
+                out = self._forward_eager(s1, s2, iters, sf, True, reuse)
             g = self._graphs[key] = (graph, s1, s2, sf, out)
         graph, s1, s2, sf, out = g
         s1.copy_(image1)
@@ -463,9 +494,10 @@ class RAFTGMA(nn.Module):
         plan = self._plan(b, h, w, dev)
         fmap = plan.buffer("fmap_seq", (nb, plan.h8, plan.w8, 256), torch.float16)
         self._encoder(plan, wts.fnet, frames, View(fmap))
-        return self._flow(plan, wts, frames[:b], View(fmap[:b]), View(fmap[1:]), iters, None, test_mode)
+        return self._flow(plan, wts, frames[:b], View(fmap[:b]), View(fmap[1:]), iters, None, test_mode,
+                          xpack=plan.encoder_scratch(nb, dev)["xpack"][:b])
 
-    def _flow(self, plan, wts, image1, fmap1, fmap2, iters, flow_init, test_mode):
+    def _flow(self, plan, wts, image1, fmap1, fmap2, iters, flow_init, test_mode, xpack=None):
         dev = image1.device
         b, h, w = plan.b, plan.h, plan.w
         h8, w8, n, np_ = plan.h8, plan.w8, plan.n, plan.np_
@@ -475,7 +507,7 @@ class RAFTGMA(nn.Module):
 
         # context network: net = tanh(.) -> HX[0:128] + h32, inp = relu(.) -> HX[128:256]
         hx = plan.hx
-        self._encoder(plan, wts.cnet, image1, View(hx, 0, 256), final_flags=L.F_TANH_LO | _H16, h32=plan.h32)
+        self._encoder(plan, wts.cnet, image1, View(hx, 0, 256), final_flags=L.F_TANH_LO | _H16, h32=plan.h32, xpack=xpack)
 
         if wts.gru_pre:
             per_buf = plan.state_numel

@@ -27,10 +27,10 @@ from .poses import PoseChain
 
 SLAM_SIZE = (376, 1232)   # neural_slam.py:54,198: every frame is resized to this before the flow net
 
-# measured on B200 (profiles/r02d_bench_2gpu.json): one scan call costs ~1.2 ms (weights into shared memory, the batched
-# input / head products) + ~7.4 us per pair; the pair-parallel part costs ~1.3 ms per pair.  Rounds are scanned in groups
-# of at least SCAN_MIN_PAIRS pairs so that the per-call cost stays small against the per-pair cost.
-SCAN_US_PER_CALL, SCAN_US_PER_PAIR, FLOW_US_PER_PAIR, SCAN_MIN_PAIRS = 1200.0, 7.4, 1320.0, 400
+# measured on B200 (profiles/r02o_scan_bench.txt, r02n_bench_8gpu.json): one scan call costs ~0.1 ms + ~14-15 us per pair
+# (two grid barriers per LSTM step); in the sharded run rank 0 spent 82.6 ms per 4540 pairs in 11 calls.  The pair-parallel
+# part costs ~1.3 ms per pair.  Rounds are scanned in groups of at least SCAN_MIN_PAIRS pairs.
+SCAN_US_PER_CALL, SCAN_US_PER_PAIR, FLOW_US_PER_PAIR, SCAN_MIN_PAIRS = 500.0, 17.0, 1320.0, 400
 
 
 def shard_ranges(num_pairs, world):

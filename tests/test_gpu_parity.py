@@ -255,9 +255,10 @@ def test_forward_graph_replay_is_bit_identical_to_eager():
     fr = synth.frame_sequence(5, 128, 160, seed=5, max_shift=3.0).cuda()
     vsd = synth.atdnvo_state_dict()
     outs = {}
-    for mode in ("graph", "eager"):
+    for mode in ("graph", "eager", "eager-no-fmap-reuse"):
         m.capture_forward = mode == "graph"
-        m._graphs = {}
+        m.reuse_fmap = mode != "eager-no-fmap-reuse"     # consecutive calls pass the previous image2 as image1: its fmap is reused
+        m._graphs, m._last_pair = {}, None
         vo = ATDNVO()
         vo.load_state_dict(vsd)
         vo = vo.to("cuda").eval()
@@ -271,10 +272,11 @@ def test_forward_graph_replay_is_bit_identical_to_eager():
         outs[mode] = res
         if mode == "graph":
             assert any(isinstance(g, tuple) for g in m._graphs.values()) and any(isinstance(g, tuple) for g in vo._graphs.values())
-    m.capture_forward = True
-    for a, b in zip(outs["graph"], outs["eager"]):
-        for x, y in zip(a, b):
-            assert torch.equal(x, y)
+    m.capture_forward = m.reuse_fmap = True
+    for other in ("eager", "eager-no-fmap-reuse"):
+        for a, b in zip(outs["graph"], outs[other]):
+            for x, y in zip(a, b):
+                assert torch.equal(x, y), other
 
 
 def test_corrblock_corr_static():

@@ -517,17 +517,27 @@ def run_ours(args):
         lab, a = max(table.items(), key=lambda kv: kv[1]["ms"])
         t_tensor = a["flops"] / (pk["tflops_sustained"] * 1e12)
         t_hbm = a["bytes"] / (pk["hbm_gbs"] * 1e9)
-        traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from the committed ncu --set full captures
-        if os.path.exists(tp):
-            caps = json.load(open(tp)).get(lab, [])
+
+        def ncu_traffic(label):
+            """(dram bytes per launch at this batch size, note) from the committed captures, or (None, None)."""
+            if not os.path.exists(tp):
+                return None, None
+            caps = json.load(open(tp)).get(label, [])
             exact = [c for c in caps if c.get("batch_pairs") == args.batch_pairs]
             if exact:
-                traffic = exact[-1]["dram_bytes_per_launch"]
-            elif caps:   # the launch processes independent pairs: bytes scale with the pairs per launch
+                return exact[-1]["dram_bytes_per_launch"], None
+            if caps:   # the launch processes independent pairs: bytes scale with the pairs per launch
                 c = caps[-1]
-                traffic = c["dram_bytes_per_launch"] * args.batch_pairs / c["batch_pairs"]
-                traffic_note = f"scaled from the batch_pairs={c['batch_pairs']} capture"
+                return c["dram_bytes_per_launch"] * args.batch_pairs / c["batch_pairs"], f"scaled from the batch_pairs={c['batch_pairs']} capture"
+            return None, None
+
+        traffic, traffic_note = ncu_traffic(lab)
+        for key in ("corr_pyramid", "corr_lookup"):     # the two north-star kernels: measured DRAM traffic next to the algorithmic bytes
+            t, _ = ncu_traffic(key)
+            if t is not None and key in table:
+                line["north_star_kernels"][key + "_traffic_bytes_per_launch"] = t
+                line["north_star_kernels"][key + "_algorithmic_bytes_per_launch"] = table[key]["bytes"] / table[key]["launches"]
         if t_tensor >= t_hbm:
             ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
             line["roofline"] = {"kernel": lab, "bound": "tensor", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",

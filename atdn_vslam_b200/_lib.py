@@ -16,8 +16,8 @@ F_RELU, F_RESID, F_FLOWTAIL, F_TANH_LO, F_B_BATCHED, F_A_SHARED, F_PAIR, F_STATS
 
 EXPORTS = (
     "atdn_last_error", "atdn_version", "atdn_check_device", "atdn_tc_gemm", "atdn_corr_lookup",
-    "atdn_stem_pack", "atdn_flow_pack", "atdn_inorm_stats", "atdn_inorm_apply", "atdn_softmax_rows",
-    "atdn_flow_head_update", "atdn_convex_upsample", "atdn_coords_init", "atdn_conv32", "atdn_linear32",
+    "atdn_stem_pack", "atdn_flow_pack", "atdn_inorm_stats", "atdn_inorm_apply",
+    "atdn_convex_upsample", "atdn_coords_init", "atdn_conv32", "atdn_linear32",
     "atdn_lstm_cell", "atdn_keyframe_search", "atdn_attn_probs", "atdn_corr_pyramid", "atdn_clvo_lstm_scan", "atdn_pose_chain", "atdn_flow_head_gather", "atdn_inorm_finalize",
 )
 

@@ -468,110 +468,6 @@ static void launch_inorm_apply_fixed(const __half* x, long long pitch, const flo
   inorm_apply_fixed_kernel<C><<<dim3((hw + LANES * U - 1) / (LANES * U), batch), T, 0, s>>>(x, pitch, stats, resid, rpitch, y, ypitch, hw, relu);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Row softmax of the attention logits: un-normalised fp16 probabilities + 1/sum
-// ------------------------------------------------------------------------------------------------
-constexpr int kSoftmaxThreads = 256;
-constexpr int kSoftmaxMaxPerThread = 40;   // cols <= 10240
-
-__global__ void __launch_bounds__(kSoftmaxThreads) softmax_rows_kernel(const float* __restrict__ s, long long spitch,
-                                                                       __half* __restrict__ p, long long ppitch,
-                                                                       float* __restrict__ inv_sum, int cols) {
-  __shared__ float red[kSoftmaxThreads / 32];
-  __shared__ float bcast;
-  const long long row = blockIdx.x;
-  const float* sr = s + row * spitch;
-  float v[kSoftmaxMaxPerThread];
-  float m = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < kSoftmaxMaxPerThread; ++i) {
-    const int c = threadIdx.x + i * kSoftmaxThreads;
-    v[i] = c < cols ? sr[c] : -INFINITY;
-    m = fmaxf(m, v[i]);
-  }
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = red[0];
-    for (int i = 1; i < kSoftmaxThreads / 32; ++i) t = fmaxf(t, red[i]);
-    bcast = t;
-  }
-  __syncthreads();
-  m = bcast;
-  float sum = 0.0f;
-  __half* pr = p + row * ppitch;
-#pragma unroll
-  for (int i = 0; i < kSoftmaxMaxPerThread; ++i) {
-    const int c = threadIdx.x + i * kSoftmaxThreads;
-    if (c < cols) {
-      const __half e = __float2half_rn(expf(v[i] - m));
-      pr[c] = e;
-      sum += __half2float(e);   // normalise by what the P.V GEMM will actually read
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.0f;
-    for (int i = 0; i < kSoftmaxThreads / 32; ++i) t += red[i];
-    inv_sum[row] = 1.0f / t;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// flow_head.conv2 (3x3, 256 -> 2) fused with the coordinate update: one warp per pixel
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) flow_head_update_kernel(const __half* __restrict__ x, long long pitch,
-                                                               const float* __restrict__ w,
-                                                               const float* __restrict__ bias,
-                                                               float* __restrict__ coords1, float* __restrict__ flow,
-                                                               int B, int H, int W) {
-  __shared__ float2 ws[9 * 256];   // [tap][c] -> (w_out0, w_out1)
-  for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) {
-    const int tap = i / 256, c = i - tap * 256;
-    ws[i] = make_float2(w[(0 * 256 + c) * 9 + tap], w[(1 * 256 + c) * 9 + tap]);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long pix = static_cast<long long>(blockIdx.x) * 8 + warp;
-  const long long npix = static_cast<long long>(B) * H * W;
-  if (pix >= npix) return;
-  const int xw = static_cast<int>(pix % W);
-  const long long t = pix / W;
-  const int yh = static_cast<int>(t % H);
-  const long long b = t / H;
-  float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-    const uint4 u = *reinterpret_cast<const uint4*>(x + ((b * H + iy) * W + ix) * pitch + lane * 8);
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      const float2 w0 = ws[tap * 256 + lane * 8 + 2 * j], w1 = ws[tap * 256 + lane * 8 + 2 * j + 1];
-      a0 += f.x * w0.x + f.y * w1.x;
-      a1 += f.x * w0.y + f.y * w1.y;
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-  }
-  if (lane == 0) {
-    const float cxn = coords1[pix * 2] + (a0 + bias[0]);
-    const float cyn = coords1[pix * 2 + 1] + (a1 + bias[1]);
-    coords1[pix * 2] = cxn;
-    coords1[pix * 2 + 1] = cyn;
-    flow[pix * 2] = cxn - static_cast<float>(xw);
-    flow[pix * 2 + 1] = cyn - static_cast<float>(yh);
-  }
-}
-
 // flow_head.conv2 as "1x1 conv + gather": the tensor-core kernel evaluates all nine taps on the UNSHIFTED pixel,
 //   d[q, tap*2 + co] = sum_c w2[co, c, tap] * x[q, c]        (a 256 -> 18 1x1 convolution: x is read once, not 9x),
 // and this kernel sums the shifted contributions  delta[p, co] = bias[co] + sum_tap d[p + off(tap), tap*2 + co]
@@ -604,7 +500,8 @@ __global__ void __launch_bounds__(256) flow_head_gather_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 // Convex upsampling: block = 4 low-res pixels (x) x 8 x 8 sub-pixels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) convex_upsample_kernel(const float* __restrict__ mask, long long mpitch,
+template <typename MaskT>
+__global__ void __launch_bounds__(256) convex_upsample_kernel(const MaskT* __restrict__ mask, long long mpitch,
                                                               const float* __restrict__ flow,
                                                               float* __restrict__ up, float* __restrict__ lo, int B,
                                                               int H, int W) {
@@ -613,11 +510,11 @@ __global__ void __launch_bounds__(256) convex_upsample_kernel(const float* __res
   const int x = blockIdx.x * 4 + px, y = blockIdx.y, b = blockIdx.z;
   if (x >= W) return;
   const long long pix = (static_cast<long long>(b) * H + y) * W + x;
-  const float* mrow = mask + pix * mpitch + i * 8 + j;
+  const MaskT* mrow = mask + pix * mpitch + i * 8 + j;
   float mk[9], mx = -INFINITY;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
-    mk[k] = mrow[k * 64];
+    mk[k] = static_cast<float>(mrow[k * 64]);
     mx = fmaxf(mx, mk[k]);
   }
   float sum = 0.0f;
@@ -811,29 +708,6 @@ extern "C" int atdn_inorm_apply(const void* x16, int64_t pitch, const float* sta
   return 0;
 }
 
-extern "C" int atdn_softmax_rows(const float* s32, int64_t s_pitch, void* p16, int64_t p_pitch, float* inv_sum, int64_t rows,
-                                 int32_t cols, void* stream) {
-  if (int e = require_sm100()) return e;
-  ATDN_REQUIRE(s32 && p16 && inv_sum && rows > 0, ATDN_ERR_ARG, "atdn_softmax_rows: null argument");
-  ATDN_REQUIRE(cols > 0 && cols <= kSoftmaxThreads * kSoftmaxMaxPerThread, ATDN_ERR_UNSUP, "atdn_softmax_rows: cols=%d > %d", cols, kSoftmaxThreads * kSoftmaxMaxPerThread);
-  softmax_rows_kernel<<<static_cast<unsigned>(rows), kSoftmaxThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      s32, s_pitch, static_cast<__half*>(p16), p_pitch, inv_sum, cols);
-  ATDN_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int atdn_flow_head_update(const void* x16, int64_t pitch, const float* w, const float* bias, float* coords1,
-                                     float* flow, int32_t batch, int32_t h8, int32_t w8, void* stream) {
-  if (int e = require_sm100()) return e;
-  ATDN_REQUIRE(x16 && w && bias && coords1 && flow, ATDN_ERR_ARG, "atdn_flow_head_update: null argument");
-  ATDN_REQUIRE(pitch % 8 == 0 && pitch >= 256 && aligned16(x16), ATDN_ERR_ALIGN, "atdn_flow_head_update: alignment");
-  const long long npix = static_cast<long long>(batch) * h8 * w8;
-  flow_head_update_kernel<<<static_cast<unsigned>((npix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x16), pitch, w, bias, coords1, flow, batch, h8, w8);
-  ATDN_CUDA(cudaGetLastError());
-  return 0;
-}
-
 extern "C" int atdn_flow_head_gather(const float* d32, int64_t pitch, const float* bias, float* coords1, float* flow,
                                      int32_t batch, int32_t h8, int32_t w8, void* stream) {
   if (int e = require_sm100()) return e;
@@ -846,12 +720,15 @@ extern "C" int atdn_flow_head_gather(const float* d32, int64_t pitch, const floa
   return 0;
 }
 
-extern "C" int atdn_convex_upsample(const float* mask32, int64_t mask_pitch, const float* flow, float* flow_up, float* flow_lo,
-                                    int32_t batch, int32_t h8, int32_t w8, void* stream) {
+extern "C" int atdn_convex_upsample(const void* mask, int32_t mask_is_half, int64_t mask_pitch, const float* flow, float* flow_up,
+                                    float* flow_lo, int32_t batch, int32_t h8, int32_t w8, void* stream) {
   if (int e = require_sm100()) return e;
-  ATDN_REQUIRE(mask32 && flow && flow_up && mask_pitch >= 576, ATDN_ERR_ARG, "atdn_convex_upsample: bad arguments");
-  convex_upsample_kernel<<<dim3((w8 + 3) / 4, h8, batch), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      mask32, mask_pitch, flow, flow_up, flow_lo, batch, h8, w8);
+  ATDN_REQUIRE(mask && flow && flow_up && mask_pitch >= 576, ATDN_ERR_ARG, "atdn_convex_upsample: bad arguments");
+  const dim3 grid((w8 + 3) / 4, h8, batch), block(32, 8);
+  if (mask_is_half)
+    convex_upsample_kernel<__half><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(mask), mask_pitch, flow, flow_up, flow_lo, batch, h8, w8);
+  else
+    convex_upsample_kernel<float><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(mask), mask_pitch, flow, flow_up, flow_lo, batch, h8, w8);
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -78,6 +78,7 @@ _HALO_CFG = {64: (4, 64, True), 96: (2, 96, True), 128: (2, 128, True), 192: (1,
 FMAP_SCALE = 0.25      # plan.buffer("fmap*") holds fnet(x) * FMAP_SCALE (see _EncoderWeights.out)
 _NO_FUSED_STATS = os.environ.get("ATDN_NO_FUSED_STATS") == "1"      # A/B switches (bench only)
 _NO_GRU_PRE = os.environ.get("ATDN_NO_GRU_PRE") == "1"
+_MASK32 = os.environ.get("ATDN_MASK32") == "1"
 _GRU_PRE32 = os.environ.get("ATDN_GRU_PRE32") == "1"
 _PRE16 = 0 if _GRU_PRE32 else L.F_PRE16
 _Z16 = 0 if os.environ.get("ATDN_GRU_Z32") == "1" else L.F_Z16
@@ -257,7 +258,8 @@ class _Plan:
         self.fh = f16(b, h8, w8, 256)
         self.fh2d = f32(b, h8, w8, 32)      # flow_head.conv2 per-tap partial products [.., tap*2 + co]
         self.mh = f16(b, h8, w8, 256)
-        self.mask32 = f32(b * n, 576)
+        # up-sampling mask: fp16 like the reference's autocast path (+4e-5 px, tools/fp16_mask_sensitivity.py); ATDN_MASK32=1: fp32
+        self.mask32 = f32(b * n, 576) if _MASK32 else f16(b * n, 576)
 
     def buffer(self, name, shape, dtype):
         t = self.__dict__.get("_buf_" + name)
@@ -534,7 +536,7 @@ class RAFTGMA(nn.Module):
                 _conv_s1(View(hx, 0, 128), c, View(plan.mh), cout=256, taps=(3, 3), flags=L.F_RELU)
                 c = wts.mask2
                 d_out = View(plan.mask32.view(b, h8, w8, 576))
-                _conv_s1(View(plan.mh), c, d_out, cout=576, taps=(1, 1), epi=L.EPI_STORE32, alpha=0.25)
+                _conv_s1(View(plan.mh), c, d_out, cout=576, taps=(1, 1), epi=L.EPI_STORE32 if _MASK32 else L.EPI_STORE16, alpha=0.25)
                 flow_up = torch.empty(b, 2, h, w, dtype=torch.float32, device=dev)
                 flow_lo = torch.empty(b, 2, h8, w8, dtype=torch.float32, device=dev)
                 ops.convex_upsample(plan.mask32, plan.flow, flow_up, flow_lo)

@@ -363,12 +363,6 @@ def inorm_apply(x, stats, y, resid=None, relu=True):
                                       x.B, x.H * x.W, x.c, int(relu), L.stream_ptr()), "atdn_inorm_apply")
 
 
-@_profiled
-def softmax_rows(s32, p16, inv_sum, rows, cols):
-    L.check(L.load().atdn_softmax_rows(L.ptr(s32), C.c_int64(s32.shape[-1]), L.ptr(p16), C.c_int64(p16.shape[-1]),
-                                       L.ptr(inv_sum), C.c_int64(rows), cols, L.stream_ptr()), "atdn_softmax_rows")
-
-
 def attn_probs(qk, p16, inv_sum, scale):
     """qk fp16 [B,H8,W8,256] (q | k) -> p16 [B,N,Np] un-normalised probabilities, inv_sum [B*N] (gma.py:66-73)."""
     b, h8, w8, pitch = qk.shape
@@ -386,12 +380,6 @@ def attn_probs(qk, p16, inv_sum, scale):
 
 
 @_profiled
-def flow_head_update(x, w, bias, coords1, flow):
-    L.check(L.load().atdn_flow_head_update(x.ptr(), C.c_int64(x.pitch), L.ptr(w), L.ptr(bias), L.ptr(coords1),
-                                           L.ptr(flow), x.B, x.H, x.W, L.stream_ptr()), "atdn_flow_head_update")
-
-
-@_profiled
 def flow_head_gather(d32, bias, coords1, flow):
     """d32 fp32 [B,H8,W8,pitch] per-tap partial products of flow_head.conv2 -> coords1 += delta, flow = coords1 - grid."""
     b, h8, w8, pitch = d32.shape
@@ -400,9 +388,10 @@ def flow_head_gather(d32, bias, coords1, flow):
 
 
 @_profiled
-def convex_upsample(mask32, flow, flow_up, flow_lo=None):
+def convex_upsample(mask, flow, flow_up, flow_lo=None):
+    """mask [pix, >=576] fp32 or fp16"""
     b, h8, w8, _ = flow.shape
-    L.check(L.load().atdn_convex_upsample(L.ptr(mask32), C.c_int64(mask32.shape[-1]), L.ptr(flow), L.ptr(flow_up),
+    L.check(L.load().atdn_convex_upsample(L.ptr(mask), 1 if mask.dtype == torch.float16 else 0, C.c_int64(mask.shape[-1]), L.ptr(flow), L.ptr(flow_up),
                                           L.ptr(flow_lo), b, h8, w8, L.stream_ptr()), "atdn_convex_upsample")
 
 

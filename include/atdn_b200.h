@@ -226,22 +226,16 @@ int atdn_inorm_finalize(const float* scratch, int32_t parts, int32_t batch, int3
 /* y = relu((x - mean) * rstd); if resid16: y = relu(resid16 + y) (extractor.py:47-55).  In place ok. */
 int atdn_inorm_apply(const void* x16, int64_t pitch, const float* stats, const void* resid16, int64_t resid_pitch,
                      void* y16, int64_t y_pitch, int32_t batch, int32_t hw, int32_t c, int32_t relu, void* stream);
-/* softmax over keys of fp32 logits (gma.py:73): p16[row, :] = exp(s - max) (un-normalised, fp16),
- * inv_sum[row] = 1 / sum(p16).  rows = B*N, cols = N, pitches in elements.                          */
-int atdn_softmax_rows(const float* s32, int64_t s_pitch, void* p16, int64_t p_pitch, float* inv_sum,
-                      int64_t rows, int32_t cols, void* stream);
-/* update.py:14 flow_head.conv2 (3x3, 256 -> 2) + network.py:116: delta = conv(x16) + bias;
- * coords1 += delta; flow = coords1 - coords0 (coords0 = pixel grid).  x16 NHWC [B,H8,W8,256].       */
-int atdn_flow_head_update(const void* x16, int64_t pitch, const float* w, const float* bias,
-                          float* coords1, float* flow, int32_t batch, int32_t h8, int32_t w8, void* stream);
-/* The same update from the per-tap partial products of a 256 -> 18 1x1 convolution on atdn_tc_gemm (STORE32):
+/* update.py:14 flow_head.conv2 (3x3, 256 -> 2) + network.py:116 (coords1 += delta; flow = coords1 - coords0) from the per-tap
+ * partial products of a 256 -> 18 1x1 convolution on atdn_tc_gemm (STORE32):
  * d32[pix, tap*2 + co] = sum_c w[co, c, tap] x[pix, c], tap = dy*3 + dx;  delta[p, co] = bias[co] + sum over the taps whose
  * neighbour p + (dy-1, dx-1) lies inside the image of d32[that neighbour, tap*2 + co].  d32: fp32 [B*H8*W8, pitch].        */
 int atdn_flow_head_gather(const float* d32, int64_t pitch, const float* bias, float* coords1, float* flow,
                           int32_t batch, int32_t h8, int32_t w8, void* stream);
-/* network.py:59-70 convex upsampling: mask fp32 [pix, 576] (already x0.25), flow fp32 [B,H8,W8,2]
- * -> flow_up fp32 NCHW [B,2,8*H8,8*W8]; flow_lo NCHW [B,2,H8,W8] is written when non-NULL.          */
-int atdn_convex_upsample(const float* mask32, int64_t mask_pitch, const float* flow, float* flow_up,
+/* network.py:59-70 convex upsampling: mask [pix, mask_pitch >= 576] (already x0.25), fp32 or -- mask_is_half != 0 -- fp16
+ * (the reference's autocast path hands upsample_flow an fp16 mask too; +4e-5 px, tools/fp16_mask_sensitivity.py),
+ * flow fp32 [B,H8,W8,2] -> flow_up fp32 NCHW [B,2,8*H8,8*W8]; flow_lo NCHW [B,2,H8,W8] is written when non-NULL.          */
+int atdn_convex_upsample(const void* mask, int32_t mask_is_half, int64_t mask_pitch, const float* flow, float* flow_up,
                          float* flow_lo_or_null, int32_t batch, int32_t h8, int32_t w8, void* stream);
 /* coords_grid (utils.py:76-79): coords[b,y,x,:] = (x, y) (+ flow_init NCHW [B,2,H8,W8] when non-NULL) */
 int atdn_coords_init(float* coords1, float* flow, const float* flow_init_or_null, int32_t batch, int32_t h8,

@@ -92,7 +92,7 @@ def check_gma_stages():
         plan = next(iter(m._plans.values()))
         ok &= _stat(f"iters={iters} lookup corr (last iter)", plan.corrfeat[..., :324].float().permute(0, 3, 1, 2), it["corr"][-1], 5e-3)
         ok &= _stat(f"iters={iters} net", ops.state_to_nhwc(plan.h32, 16, 20).permute(0, 3, 1, 2), it["net"], 3e-2)
-        ok &= _stat(f"iters={iters} mask", plan.mask32.view(1, 16, 20, 576).permute(0, 3, 1, 2), it["mask"], 5e-3)
+        ok &= _stat(f"iters={iters} mask", plan.mask32.float().view(1, 16, 20, 576).permute(0, 3, 1, 2), it["mask"], 5e-3)
         ok &= _epe(f"iters={iters} flow_lo", lo, lo_o, 1e-3)
         ok &= _epe(f"iters={iters} flow_up", up, up_o, 5e-3)
     return ok

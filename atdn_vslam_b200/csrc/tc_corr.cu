@@ -281,7 +281,10 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_pyramid_kernel(const __g
             const float l3 = ((l2a[0] + l2a[1]) + (l2r[0] + l2r[1])) * 0.25f;
             l3v[strip] = (0 < ny3 && strip < nx3) ? l3 : 0.0f;
             if (!(p.dbg & 2)) {
-              // level-0 strip: 128 bytes per query = [8 rows][8 cols] fp16, 16-byte chunk j = row j, 128B swizzle
+              // level-0 strip: 128 bytes per query = [8 rows][8 cols] fp16
+              // 16-byte chunk j = row j, 128B swizzle, one TMA store of [32 queries][128 B].  (Measured and dropped: four 256-bit
+              // stores per thread straight from the registers for every / every second strip -- 2.23 / 2.04 ms against 1.92 ms
+              // for TMA only, profiles/r02r_exp_corr_direct_256bit_stores.txt: the store paths do not add up.)
               const int off = acquire();
 #pragma unroll
               for (int j = 0; j < 4; ++j) {

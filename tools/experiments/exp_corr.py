@@ -1,7 +1,7 @@
 """Experiment (not a test): corr-pyramid kernel timing.  The switches are read once per process, so each variant runs in
 its own process:  python tools/experiments/exp_corr.py            (runs all variants as sub-processes)
-ATDN_CORR_DBG: 1 = no level 1..3 stores, 2 = no stores at all (MMA + operand feed + epilogue arithmetic only), 8 = every
-box by TMA (default: half of the fp16 boxes take the coalesced LSU path); ATDN_CORR_NO_PAIR=1: cta_group::1 kernel."""
+ATDN_CORR_DBG: 1 = no level 1..3 stores, 2 = no stores at all (MMA + operand feed + epilogue arithmetic only), 8 / 16 = every
+level-0 strip by TMA / by 256-bit register stores (default: odd strips direct, even strips TMA); ATDN_CORR_NO_PAIR=1: cta_group::1 kernel."""
 import os, subprocess, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
@@ -27,6 +27,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             print(f"pair={os.environ.get('ATDN_CORR_NO_PAIR') != '1'} dbg={os.environ.get('ATDN_CORR_DBG', '0')} half_levels={half} alpha={alpha} batch={b}: {ms:.3f} ms  "
                   f"{2.0 * b * n * n * 256 / ms / 1e9:.0f} TFLOP/s", flush=True)
 else:
-    for nopair, dbg in (("0", "0"), ("0", "8"), ("0", "1"), ("0", "9"), ("0", "2"), ("1", "0"), ("1", "8")):
+    for nopair, dbg in (("0", "0"), ("0", "8"), ("0", "16"), ("0", "1"), ("0", "9"), ("0", "17"), ("0", "2"), ("1", "0")):
         env = dict(os.environ, ATDN_CORR_NO_PAIR=nopair, ATDN_CORR_DBG=dbg)
         subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env)

@@ -16,7 +16,7 @@
 //   * arithmetic: the eight window origins of a query (4 levels x 2 axes) are computed by eight lanes and broadcast by
 //     shuffles instead of being recomputed by every lane in every pass; address = row part + strip * S_l.
 // The blend itself is the separable form of the first kernel: all 81 taps of a level share one fractional offset, so
-// the 9 x 9 samples are 10 horizontal + 9 vertical lerps per window column; lane = (level, column), two rounds of 18.
+// the 9 x 9 samples are 10 horizontal + 9 vertical lerps per window column; lane = (level, column pair): one pass of 20 lanes.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -29,11 +29,11 @@ namespace lks {
 constexpr int kWarps = 8;                       // warps per CTA
 constexpr int kQueriesPerWarp = 8;              // consecutive queries walked by one warp
 constexpr int kRows = 10, kCols = 24;           // staged window per level: rows iy .. iy + 9, cols x0 .. x0 + 23 (x0 = ix & ~7)
-constexpr int kLevelBytes = kRows * kCols * 2 + 96;  // 480 + 96 = 144 words: the two levels of a blend round (lanes 0..8 / 9..17) sit 16 banks apart and a lane group spans <= 8
-constexpr int kWinBytes = 4 * kLevelBytes;      // 2304 per query
+constexpr int kLevelBytes = kRows * kCols * 2 + 64;  // 480 + 64 = 136 words: the four levels of the blend pass (5 lanes each, <= 7 words wide) start 8 banks apart
+constexpr int kWinBytes = 4 * kLevelBytes;      // 2176 per query
 constexpr int kOutBytes = 672;                  // 324 fp16 results (648 B) rounded up to 16 bytes
 constexpr int kWarpBytes = 2 * kWinBytes + kOutBytes;
-constexpr int kSmemBytes = kWarps * kWarpBytes; // 42240: dynamic shared memory, 5 CTAs per SM
+constexpr int kSmemBytes = kWarps * kWarpBytes; // 40192: dynamic shared memory, 4 CTAs per SM (64 registers per thread)
 
 struct Params {
   const __half* lvl[4];     // level l: [query][tiles_l][chunk_l], chunk = 256 / 64 / 16 / 4 halves (strip layout)
@@ -110,7 +110,7 @@ __device__ __forceinline__ void stage(const LevelLane& c, const float* coords, l
 }
 
 template <bool OUT32>
-__global__ void __launch_bounds__(kWarps * 32) corr_lookup_strip_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kWarps * 32, 4) corr_lookup_strip_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wbase = smem + warp * kWarpBytes;
@@ -143,9 +143,8 @@ __global__ void __launch_bounds__(kWarps * 32) corr_lookup_strip_kernel(const __
     c.dst0 = lg * kLevelBytes + c.r0 * (kCols * 2);
     c.dst3 = lg * kLevelBytes + c.r3 * (kCols * 2) + c.sx3 * 16;
   }
-  // blend role: lane (level 2 * rd + hi, column a), lanes 0..17
-  const int hi = lane >= 9 ? 1 : 0;
-  const int a = lane - 9 * hi;
+  // blend role: lane (level bl, column pair ap), lanes 0..19
+  const int bl = lane / 5, ap = lane - 5 * bl;
 
   int ix_cur, ix_nxt = 0;
   float fx_cur, fy_cur, fx_nxt = 0.0f, fy_nxt = 0.0f;
@@ -161,37 +160,57 @@ __global__ void __launch_bounds__(kWarps * 32) corr_lookup_strip_kernel(const __
     __syncwarp();                                    // ... and every other lane's
     const uint8_t* win = wbase + cur_off;
 
-    // separable blend: lane (level, a) sweeps the 10 window rows of column pair (a, a + 1); channel = l*81 + a*9 + b.
-    // The origin / fractions of level l live in the lanes of its staging group (8 l .. 8 l + 7).
-#pragma unroll
-    for (int rd = 0; rd < 2; ++rd) {
-      const int l = 2 * rd + hi;
+    // separable blend: lane (level l = lane / 5, ap = lane % 5), lanes 0..19, sweeps the 10 window rows of columns a = 2 ap and
+    // a + 1 (three texel loads for two columns); channel = l*81 + a*9 + b.  The origin / fractions of level l live in the
+    // lanes of its staging group (8 l .. 8 l + 7).
+    {
+      const int l = bl < 4 ? bl : 3;
       const int ix = __shfl_sync(0xffffffffu, ix_cur, 8 * l);
       const float fxl = __shfl_sync(0xffffffffu, fx_cur, 8 * l), fyl = __shfl_sync(0xffffffffu, fy_cur, 8 * l);
-      if (lane < 18) {
-        const __half* wp = reinterpret_cast<const __half*>(win + l * kLevelBytes) + (ix & 7) + a;
-        float v[9];
-        float hprev = 0.0f;
+      if (lane < 20) {
+        const __half* wp = reinterpret_cast<const __half*>(win + l * kLevelBytes) + (ix & 7) + 2 * ap;
+        float va[9], vb[9];
+        float ha_prev = 0.0f, hb_prev = 0.0f;
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
-          const float t0 = __half2float(wp[r * kCols]), t1 = __half2float(wp[r * kCols + 1]);
-          const float h = fmaf(fxl, t1 - t0, t0);
+          const float t0 = __half2float(wp[r * kCols]), t1 = __half2float(wp[r * kCols + 1]), t2 = __half2float(wp[r * kCols + 2]);
+          const float ha = fmaf(fxl, t1 - t0, t0), hb = fmaf(fxl, t2 - t1, t1);
           if (r > 0) {
-            v[r - 1] = fmaf(fyl, h - hprev, hprev);
-            if constexpr (OUT32) p.out32[(q0 + i) * 324 + l * 81 + a * 9 + r - 1] = v[r - 1];
+            va[r - 1] = fmaf(fyl, ha - ha_prev, ha_prev);
+            vb[r - 1] = fmaf(fyl, hb - hb_prev, hb_prev);
+            if constexpr (OUT32) {
+              p.out32[(q0 + i) * 324 + l * 81 + (2 * ap) * 9 + r - 1] = va[r - 1];
+              if (ap < 4) p.out32[(q0 + i) * 324 + l * 81 + (2 * ap + 1) * 9 + r - 1] = vb[r - 1];
+            }
           }
-          hprev = h;
+          ha_prev = ha;
+          hb_prev = hb;
         }
-        // the lane's 9 consecutive halves start at half l * 81 + a * 9 (odd or even): 4 aligned words + 1 single half
-        const int start = l * 81 + a * 9;
-        const bool odd = (start & 1) != 0;
+        // the lane's 18 (ap = 4: 9) consecutive halves start at half l * 81 + 18 ap, odd for odd levels: aligned words plus
+        // one single half at the front (odd) or at the back
+        const int start = l * 81 + 18 * ap;
+        const bool odd = (l & 1) != 0;
         uint32_t* ow = reinterpret_cast<uint32_t*>(out_s) + ((start + 1) >> 1);
+        const float s9[18] = {va[0], va[1], va[2], va[3], va[4], va[5], va[6], va[7], va[8], vb[0], vb[1], vb[2], vb[3], vb[4], vb[5], vb[6], vb[7], vb[8]};
+        const int nwords = ap < 4 ? 8 : 4;                        // whole words after the (possible) leading single
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const __half2 pk = __floats2half2_rn(odd ? v[2 * k + 1] : v[2 * k], odd ? v[2 * k + 2] : v[2 * k + 1]);
-          ow[k] = *reinterpret_cast<const uint32_t*>(&pk);
+        for (int k = 0; k < 8; ++k) {
+          if (k < nwords) {
+            const __half2 pk = __floats2half2_rn(odd ? s9[2 * k + 1] : s9[2 * k], odd ? s9[2 * k + 2] : s9[2 * k + 1]);
+            ow[k] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
         }
-        out_s[odd ? start : start + 8] = __float2half_rn(odd ? v[0] : v[8]);
+        if (ap < 4) {
+          if (odd) {                                               // halves 0 and 17 are singles
+            out_s[start] = __float2half_rn(s9[0]);
+            out_s[start + 17] = __float2half_rn(s9[17]);
+          } else {                                                 // ninth word
+            const __half2 pk = __floats2half2_rn(s9[16], s9[17]);
+            ow[8] = *reinterpret_cast<const uint32_t*>(&pk);
+          }
+        } else {
+          out_s[odd ? start : start + 8] = __float2half_rn(odd ? s9[0] : s9[8]);
+        }
       }
     }
     __syncwarp();

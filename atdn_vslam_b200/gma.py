@@ -79,6 +79,7 @@ FMAP_SCALE = 0.25      # plan.buffer("fmap*") holds fnet(x) * FMAP_SCALE (see _E
 _NO_FUSED_STATS = os.environ.get("ATDN_NO_FUSED_STATS") == "1"      # A/B switches (bench only)
 _NO_GRU_PRE = os.environ.get("ATDN_NO_GRU_PRE") == "1"
 _MASK32 = os.environ.get("ATDN_MASK32") == "1"
+_PV_PAIR = os.environ.get("ATDN_PV_PAIR") == "1"      # A/B: P.V on CTA pairs (half the V^T stream per SM)
 _GRU_PRE32 = os.environ.get("ATDN_GRU_PRE32") == "1"
 _PRE16 = 0 if _GRU_PRE32 else L.F_PRE16
 _Z16 = 0 if os.environ.get("ATDN_GRU_Z32") == "1" else L.F_Z16
@@ -566,8 +567,9 @@ class RAFTGMA(nn.Module):
         d.n_valid, d.alpha = n, 1.0
         d.out, d.out_pitch = L.ptr(plan.vt), np_
         L.tc_gemm(d)
+        small = b * math.ceil(n / 128) <= _SMALL_TILES
         ops.gemm_rows(L.ptr(plan.p16), n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
-                      b_bstride=128 * np_, bn=64 if b * math.ceil(n / 128) <= _SMALL_TILES else 128, epi=L.EPI_PV, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
+                      b_bstride=128 * np_, bn=64 if small else 128, epi=L.EPI_PV, flags=L.F_PAIR if (_PV_PAIR and not small) else 0, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
                       aux32=plan.inv_sum, gamma=wts.gamma)
 
     def _update(self, plan, wts, m_tiles):

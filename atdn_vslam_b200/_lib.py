@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libatdn_b200.so")
 MODE_ROWS, MODE_PATCH = 0, 1
 EPI_STORE16, EPI_STORE32, EPI_CORR, EPI_GRU_ZR, EPI_GRU_Q, EPI_PV, EPI_FLOW = range(7)
 F_RELU, F_RESID, F_FLOWTAIL, F_TANH_LO, F_B_BATCHED, F_A_SHARED, F_PAIR, F_STATS, F_TILED32, F_PRE16, F_Z16, F_H16 = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048
+F_A_TILED = 4096
 
 EXPORTS = (
     "atdn_last_error", "atdn_version", "atdn_check_device", "atdn_tc_gemm", "atdn_corr_lookup",
@@ -114,7 +115,7 @@ def tc_label(d: TcDesc):
             name = "gru_context_pre"
     else:
         batch = d.b_dims[3] if (d.flags & F_A_SHARED) else d.a_dims[3]
-        flops = 2.0 * d.a_dims[1] * d.n_valid * d.a_dims[0] * batch
+        flops = 2.0 * d.a_dims[1] * d.n_valid * min(d.a_dims[0], d.b_dims[0]) * batch
         if d.epi == EPI_PV:   # P [rows, pitch] + V^T [128, pitch] read, residual read + output written (fp16)
             nbytes = batch * 2.0 * (d.a_dims[1] * d.a_strides[0] + d.n_valid * d.b_strides[0] + 2 * d.a_dims[1] * d.n_valid)
         name = {EPI_CORR: "corr_gemm", EPI_PV: "attn_pv", EPI_STORE32: "attn_qk"}.get(

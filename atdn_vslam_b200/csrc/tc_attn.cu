@@ -33,6 +33,7 @@ constexpr int kAttnSmem = kAttnQBytes + kAttnKStages * kAttnKStageBytes + 8 * 2 
 struct alignas(64) AttnParams {
   CUtensorMap tmQ, tmK, tmP;
   int n, tiles;
+  int p_tiled, row_blocks;    // P in blocks of 32 rows x 64 columns ([batch][row block][column block][32][64]); ceil(n / 32)
   float scale_log2;       // softmax scale * log2(e)
   float* inv_sum;         // [batch * n]
 };
@@ -204,7 +205,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&p.tmP, st_ptr + b * kAttnStoreBytes, cb, m0 + q * 32, 0, batch);
+            if (!p.p_tiled) {
+              tma_store_4d(&p.tmP, st_ptr + b * kAttnStoreBytes, cb, m0 + q * 32, 0, batch);
+            } else if ((m0 >> 5) + q < p.row_blocks) {   // (the last CTA overhangs the last row block of the batch element)
+              tma_store_4d(&p.tmP, st_ptr + b * kAttnStoreBytes, 0, 0, cb >> 6, batch * p.row_blocks + (m0 >> 5) + q);
+            }
             bulk_commit();
           }
           ++nstore;
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
 
 using namespace atdn;
 
-extern "C" int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, int64_t p_pitch, float* inv_sum,
+extern "C" int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, int64_t p_pitch, int32_t p_tiled, float* inv_sum,
                                int32_t batch, int32_t n, float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int e = require_sm100()) return e;
@@ -244,6 +249,7 @@ extern "C" int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, in
   ATDN_REQUIRE(qk_pitch >= 256 && qk_pitch % 8 == 0 && p_pitch >= n && p_pitch % 8 == 0, ATDN_ERR_ALIGN,
                "atdn_attn_probs: qk_pitch %lld / p_pitch %lld", (long long)qk_pitch, (long long)p_pitch);
   ATDN_REQUIRE(scale > 0.0f, ATDN_ERR_ARG, "atdn_attn_probs: scale must be positive (row maxima are taken before scaling)");
+  ATDN_REQUIRE(!p_tiled || p_pitch % 64 == 0, ATDN_ERR_ALIGN, "atdn_attn_probs: the tiled layout needs p_pitch %% 64 == 0, got %lld", (long long)p_pitch);
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.n = n;
@@ -256,9 +262,18 @@ extern "C" int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, in
   const uint32_t qbox[4] = {64, 128, 1, 1}, kbox[4] = {64, kAttnBN, 1, 1}, pbox[4] = {64, 32, 1, 1};
   if (int e = make_map_f16(&p.tmQ, qk16, qdims, qstr, qbox, ones, "Q")) return e;
   if (int e = make_map_f16(&p.tmK, static_cast<const __half*>(qk16) + 128, qdims, qstr, kbox, ones, "K")) return e;
-  const int64_t pdims[4] = {n, n, 1, batch};
-  const int64_t pstr[3] = {p_pitch, (int64_t)n * p_pitch, (int64_t)n * p_pitch};
-  if (int e = make_map_f16(&p.tmP, p16, pdims, pstr, pbox, ones, "P")) return e;
+  p.p_tiled = p_tiled ? 1 : 0;
+  p.row_blocks = ceil_div(n, 32);
+  if (p_tiled) {
+    const int64_t cb = p_pitch / 64;
+    const int64_t pdims[4] = {64, 32, cb, (int64_t)batch * p.row_blocks};
+    const int64_t pstr[3] = {64, 2048, cb * 2048};
+    if (int e = make_map_f16(&p.tmP, p16, pdims, pstr, pbox, ones, "P (tiled)")) return e;
+  } else {
+    const int64_t pdims[4] = {n, n, 1, batch};
+    const int64_t pstr[3] = {p_pitch, (int64_t)n * p_pitch, (int64_t)n * p_pitch};
+    if (int e = make_map_f16(&p.tmP, p16, pdims, pstr, pbox, ones, "P")) return e;
+  }
   static DeviceOnce configured;
   if (configured.pending()) {
     ATDN_CUDA(cudaFuncSetAttribute(attn_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));

@@ -29,6 +29,7 @@ struct alignas(64) TcParams {
   int taps_w, pad_h, pad_w, stride;
   int chunks_a, chunks_a2, c_a, c_a2, num_k_iters;
   int b_batched, a_shared;
+  int a_tiled, a_row_blocks;   // ATDN_F_A_TILED: A in blocks of 32 rows x 64 columns, ceil(rows / 32) row blocks per batch element
   int corr_h, corr_w, corr_tiles_w;
   int lvl_pitch[4];
   float* lvl[3];
@@ -181,7 +182,8 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
           if (chunk < p.chunks_a) tma_load_4d(sA, &p.tmA, &full_bar[stage], chunk * kChunkK, cw, chh, batch);
           else tma_load_4d(sA, &p.tmA2, &full_bar[stage], (chunk - p.chunks_a) * kChunkK, cw, chh, batch);
         } else {
-          tma_load_4d(sA, &p.tmA, &full_bar[stage], it * kChunkK, m0, 0, p.a_shared ? 0 : batch);
+          if (p.a_tiled) tma_load_4d(sA, &p.tmA, &full_bar[stage], 0, 0, it, batch * p.a_row_blocks + (m0 >> 5));
+          else tma_load_4d(sA, &p.tmA, &full_bar[stage], it * kChunkK, m0, 0, p.a_shared ? 0 : batch);
         }
         if constexpr (EPI == ATDN_EPI_CORR) {
           tma_load_4d(sB, &p.tmB, &full_bar[stage], it * kChunkK, bw0, bh0, batch);
@@ -581,8 +583,20 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
     p.num_k_iters = d->taps_h * d->taps_w * (p.chunks_a + p.chunks_a2);
     grid.x = pair ? 2 * p.tiles_w * ceil_div(d->out_h, 16) : p.tiles_w * ceil_div(d->out_h, 8);
   } else {
-    const uint32_t box[4] = {64, 128, 1, 1};
-    if (int e = make_map_f16(&p.tmA, d->a, d->a_dims, d->a_strides, box, ones, "A")) return e;
+    if (d->flags & ATDN_F_A_TILED) {
+      ATDN_REQUIRE(!pair && !(d->flags & ATDN_F_A_SHARED) && c_a % 64 == 0, ATDN_ERR_ARG,
+                   "atdn_tc_gemm: A_TILED needs the single-CTA kernel, a batched A and a column count that is a multiple of 64");
+      p.a_tiled = 1;
+      p.a_row_blocks = ceil_div((int)d->a_dims[1], 32);
+      const int64_t cb = c_a / 64;
+      const int64_t dims[4] = {64, 32, cb, d->a_dims[3] * p.a_row_blocks};
+      const int64_t str[3] = {64, 2048, cb * 2048};
+      const uint32_t box[4] = {64, 32, 1, 4};            // 4 row blocks = the 128 rows of an M tile, 4 KiB contiguous each
+      if (int e = make_map_f16(&p.tmA, d->a, dims, str, box, ones, "A (tiled)")) return e;
+    } else {
+      const uint32_t box[4] = {64, 128, 1, 1};
+      if (int e = make_map_f16(&p.tmA, d->a, d->a_dims, d->a_strides, box, ones, "A")) return e;
+    }
     p.c_a = (int)c_a;
     p.chunks_a = (int)((c_a + 63) / 64);
     p.num_k_iters = p.chunks_a;

@@ -80,6 +80,9 @@ _NO_FUSED_STATS = os.environ.get("ATDN_NO_FUSED_STATS") == "1"      # A/B switch
 _NO_GRU_PRE = os.environ.get("ATDN_NO_GRU_PRE") == "1"
 _MASK32 = os.environ.get("ATDN_MASK32") == "1"
 _PV_PAIR = os.environ.get("ATDN_PV_PAIR") == "1"      # A/B: P.V on CTA pairs (half the V^T stream per SM)
+# attention probabilities in blocks of 32 rows x 64 columns: the store boxes of attn_probs and the operand boxes of P.V are
+# contiguous 4 KiB runs instead of 128-byte rows 14.6 KB apart (ATDN_P_ROWMAJOR=1: plain [N, Np] rows)
+_P_TILED = os.environ.get("ATDN_P_ROWMAJOR") != "1" and not _PV_PAIR
 _GRU_PRE32 = os.environ.get("ATDN_GRU_PRE32") == "1"
 _PRE16 = 0 if _GRU_PRE32 else L.F_PRE16
 _Z16 = 0 if os.environ.get("ATDN_GRU_Z32") == "1" else L.F_Z16
@@ -246,7 +249,7 @@ class _Plan:
         self.rh = f16(b, h8, w8, 128)
         self.pyr = ops.alloc_pyramid(b, h8, w8, dev, half_levels=4)
         self.qk = f16(b, h8, w8, 256)
-        self.p16 = f16(b, n, self.np_)
+        self.p16 = f16(b, (n + 31) // 32, self.np_ // 64, 32, 64) if _P_TILED else f16(b, n, self.np_)
         self.inv_sum = f32(b * n)
         self.vt = f16(b, 128, self.np_)
         self.coords1 = f32(b, h8, w8, 2)
@@ -550,7 +553,7 @@ class RAFTGMA(nn.Module):
         """Attention.forward (gma.py:54-76) on the context features HX[128:256]: q.k^T * scale -> un-normalised softmax
         numerators P (fp16) + 1 / row sums."""
         _conv_s1(View(plan.hx, 128, 128), wts.to_qk, View(plan.qk), cout=256, taps=(1, 1))
-        ops.attn_probs(plan.qk, plan.p16, plan.inv_sum, 128 ** -0.5)
+        ops.attn_probs(plan.qk, plan.p16, plan.inv_sum, 128 ** -0.5, tiled=_P_TILED)
 
     def _aggregate(self, plan, wts):
         """Aggregate.forward (gma.py:102-115) on the motion features HX[256:384] -> HX[384:512]:
@@ -568,8 +571,9 @@ class RAFTGMA(nn.Module):
         d.out, d.out_pitch = L.ptr(plan.vt), np_
         L.tc_gemm(d)
         small = b * math.ceil(n / 128) <= _SMALL_TILES
-        ops.gemm_rows(L.ptr(plan.p16), n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
-                      b_bstride=128 * np_, bn=64 if small else 128, epi=L.EPI_PV, flags=L.F_PAIR if (_PV_PAIR and not small) else 0, resid_ptr=L.ptr(hx, 256), resid_pitch=512,
+        ops.gemm_rows(L.ptr(plan.p16), np_ if _P_TILED else n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
+                      b_bstride=128 * np_, bn=64 if small else 128, epi=L.EPI_PV, b_k=n,
+                      flags=(L.F_PAIR if (_PV_PAIR and not small) else 0) | (L.F_A_TILED if _P_TILED else 0), resid_ptr=L.ptr(hx, 256), resid_pitch=512,
                       aux32=plan.inv_sum, gamma=wts.gamma)
 
     def _update(self, plan, wts, m_tiles):

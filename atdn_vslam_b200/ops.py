@@ -129,9 +129,10 @@ def conv_tc(a, wp, bias, out, *, cout, taps=(1, 1), pad=(0, 0), stride=1, bn=128
 
 def gemm_rows(a, a_k, a_rows, a_pitch, batch, b, b_rows, b_pitch, out_ptr, out_pitch, *, n_valid, a_bstride=None,
               b_bstride=None, bn=128, epi=L.EPI_STORE16, flags=0, alpha=1.0, bias=None, resid_ptr=None,
-              resid_pitch=0, aux32=None, gamma=None):
+              resid_pitch=0, aux32=None, gamma=None, b_k=None):
     """Batched D[b] = A[b] (a_rows x a_k) . B[b]^T (b_rows x a_k); pointers are ctypes void pointers,
-    pitches in elements.  ``b_bstride=None`` shares B across the batch."""
+    pitches in elements.  ``b_bstride=None`` shares B across the batch.  ``b_k``: true K extent of B when A's column
+    count is padded (F_A_TILED: A is read in whole 64-column blocks, B is zero-filled past its extent)."""
     d = L.TcDesc()
     d.bn, d.epi, d.a_mode, d.b_mode = bn, epi, L.MODE_ROWS, L.MODE_ROWS
     d.flags = flags | (L.F_B_BATCHED if b_bstride is not None else 0)
@@ -142,7 +143,7 @@ def gemm_rows(a, a_k, a_rows, a_pitch, batch, b, b_rows, b_pitch, out_ptr, out_p
     d.b = b
     nb = batch if b_bstride is not None else 1
     bs = b_bstride if b_bstride is not None else b_rows * b_pitch
-    L._set(d.b_dims, (a_k, b_rows, 1, nb))
+    L._set(d.b_dims, (a_k if b_k is None else b_k, b_rows, 1, nb))
     L._set(d.b_strides, (b_pitch, bs, bs))
     d.n_valid, d.alpha, d.bias = n_valid, alpha, L.ptr(bias)
     d.out, d.out_pitch, d.out_ch_off = out_ptr, out_pitch, 0
@@ -363,14 +364,15 @@ def inorm_apply(x, stats, y, resid=None, relu=True):
                                       x.B, x.H * x.W, x.c, int(relu), L.stream_ptr()), "atdn_inorm_apply")
 
 
-def attn_probs(qk, p16, inv_sum, scale):
-    """qk fp16 [B,H8,W8,256] (q | k) -> p16 [B,N,Np] un-normalised probabilities, inv_sum [B*N] (gma.py:66-73)."""
+def attn_probs(qk, p16, inv_sum, scale, tiled=False):
+    """qk fp16 [B,H8,W8,256] (q | k) -> p16 [B,N,Np] un-normalised probabilities, inv_sum [B*N] (gma.py:66-73).
+    ``tiled``: p16 is [B, ceil(N/32), Np/64, 32, 64] (blocks of 32 rows x 64 columns, see atdn_attn_probs)."""
     b, h8, w8, pitch = qk.shape
     n = h8 * w8
 
     def go():
-        L.check(L.load().atdn_attn_probs(L.ptr(qk), C.c_int64(pitch), L.ptr(p16), C.c_int64(p16.shape[-1]), L.ptr(inv_sum),
-                                         b, n, C.c_float(scale), L.stream_ptr()), "atdn_attn_probs")
+        L.check(L.load().atdn_attn_probs(L.ptr(qk), C.c_int64(pitch), L.ptr(p16), C.c_int64(p16.shape[-1] if not tiled else p16.shape[2] * 64),
+                                         1 if tiled else 0, L.ptr(inv_sum), b, n, C.c_float(scale), L.stream_ptr()), "atdn_attn_probs")
     if L.PROFILER is not None:
         # algorithmic: one q.k^T (2*N*N*128 flop) and N*N fp16 probabilities written per image
         with L.PROFILER("attn_probs", 2.0 * b * n * n * 128, 2.0 * b * n * n):

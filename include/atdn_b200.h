@@ -90,6 +90,10 @@ enum {
                              rounding (2.4e-4 absolute) is below the fp16 rounding of the hidden state it blends        */
   ATDN_F_H16       = 2048, /* h32 points to fp16 (same tiled index space): the hidden state has no fp32 master copy, as in the
                              reference's own fp16-autocast path (GRU_ZR / GRU_Q / STORE16|TANH_LO)                      */
+  ATDN_F_A_TILED   = 4096, /* ROWS A (single-CTA kernel) is stored in blocks of 32 rows x 64 columns, [batch][ceil(rows/32)][cols/64][32][64]
+                              (the layout atdn_attn_probs writes with p_tiled != 0: its 32 x 64 store boxes and the 128 x 64 operand
+                              boxes read here are contiguous 4 KiB runs); a_dims = {cols, rows, 1, batch}, a_strides are ignored,
+                              cols must be a multiple of 64 with every column block fully written (zeros past the true extent) */
   ATDN_F_STATS     = 128, /* STORE16 on the halo kernel with mt = 4, bn = 64 (n_valid = 64): per-channel partial sums of
                             (acc + bias) and its square over the in-image pixels each epilogue warp sees in one tile go to
                             aux32 as [batch, parts, 64, 2] fp32, parts = ceil(H/16) * ceil(W/(32*cl)) * cl * 4 (cl = 2 with
@@ -184,8 +188,12 @@ int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t fmap_pitch, 
  *   p16[b, i, j]  = exp((q_i . k_j - max_j q_i . k_j) * scale)   fp16, un-normalised, j < n; columns [n, ceil8(n)) are
  *                   written as zeros (16-byte store granularity), the rest of the row pad is untouched
  *   inv_sum[b, i] = 1 / sum_j p16[b, i, j]                       fp32
+ * p_tiled != 0: p16 is written in blocks of 32 rows x 64 columns, [batch][ceil(n/32)][p_pitch/64][32][64] (p_pitch a multiple
+ *   of 64 >= n; columns [n, p_pitch) of the last written block are zeros): every store box is one contiguous 4 KiB run
+ *   instead of 32 rows p_pitch apart (strided rows cost the TMA store path ~27%, tools/tma_store_bench.cu), and the P.V GEMM
+ *   reads it with ATDN_F_A_TILED.
  * ---------------------------------------------------------------------------------------------- */
-int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, int64_t p_pitch, float* inv_sum,
+int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, int64_t p_pitch, int32_t p_tiled, float* inv_sum,
                     int32_t batch, int32_t n, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -359,6 +359,16 @@ def check_attn(n=1000, batch=2, reps=0):
     isum = 1.0 / p16[:, :, :n].float().sum(2).reshape(-1)
     ok &= _cmp("attn inv_sum", inv, isum, 1e-4)
     ok &= _cmp("attn softmax", p16[:, :, :n].float() * inv.view(batch, n, 1), torch.softmax(s, 2), 2e-3)
+    # tiled layout (blocks of 32 rows x 64 columns): the same values, zeros in the pad columns of the last column block
+    rb = (n + 31) // 32
+    pt = torch.full((batch, rb, np_ // 64, 32, 64), float("nan"), dtype=torch.half, device="cuda")
+    inv_t = torch.full_like(inv, float("nan"))
+    ops.attn_probs(qk, pt, inv_t, scale, tiled=True)
+    torch.cuda.synchronize()
+    flat = pt.permute(0, 1, 3, 2, 4).reshape(batch, rb * 32, np_)
+    same = bool(torch.equal(flat[:, :n, :n], p16[:, :, :n])) and bool((flat[:, :n, n:] == 0).all()) and bool(torch.equal(inv_t, inv))
+    print(f"{'PASS' if same else 'FAIL'} attn P tiled layout == row-major, pad columns zero", flush=True)
+    ok &= same
     if reps:
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()

@@ -14,12 +14,13 @@ MODE_ROWS, MODE_PATCH = 0, 1
 EPI_STORE16, EPI_STORE32, EPI_CORR, EPI_GRU_ZR, EPI_GRU_Q, EPI_PV, EPI_FLOW = range(7)
 F_RELU, F_RESID, F_FLOWTAIL, F_TANH_LO, F_B_BATCHED, F_A_SHARED, F_PAIR, F_STATS, F_TILED32, F_PRE16, F_Z16, F_H16 = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048
 F_A_TILED = 4096
+F_A_MIXED = 8192
 
 EXPORTS = (
     "atdn_last_error", "atdn_version", "atdn_check_device", "atdn_tc_gemm", "atdn_corr_lookup",
     "atdn_stem_pack", "atdn_flow_pack", "atdn_inorm_stats", "atdn_inorm_apply",
     "atdn_convex_upsample", "atdn_coords_init", "atdn_conv32", "atdn_linear32",
-    "atdn_lstm_cell", "atdn_keyframe_search", "atdn_attn_probs", "atdn_corr_pyramid", "atdn_clvo_lstm_scan", "atdn_pose_chain", "atdn_flow_head_gather", "atdn_inorm_finalize",
+    "atdn_lstm_cell", "atdn_keyframe_search", "atdn_attn_probs", "atdn_corr_pyramid", "atdn_clvo_lstm_scan", "atdn_pose_chain", "atdn_flow_head_gather", "atdn_inorm_finalize", "atdn_attn_harmonize",
 )
 
 
@@ -37,6 +38,7 @@ class TcDesc(C.Structure):
         ("h32", C.c_void_p), ("z32", C.c_void_p), ("rh16", C.c_void_p), ("aux32", C.c_void_p), ("gamma", C.c_void_p),
         ("lvl", C.c_void_p * 3), ("lvl_pitch", C.c_int32 * 4), ("corr_h", C.c_int32), ("corr_w", C.c_int32),
         ("mt", C.c_int32),
+        ("out8", C.c_void_p), ("b8", C.c_void_p), ("a_hot", C.c_void_p),
     ]
 
 
@@ -75,6 +77,7 @@ def load():
     return lib
 
 
+PV_HOT_FRACTION = 0.0   # fp16 share of the mixed-precision P blocks of the last profiled attention (gma._attention)
 LAUNCHES = 0          # kernels launched through the C ABI by this process (bench.py reports it)
 PROFILER = None       # optional callable(label, flops, bytes) -> context manager, installed by bench.py
 
@@ -117,7 +120,8 @@ def tc_label(d: TcDesc):
         batch = d.b_dims[3] if (d.flags & F_A_SHARED) else d.a_dims[3]
         flops = 2.0 * d.a_dims[1] * d.n_valid * min(d.a_dims[0], d.b_dims[0]) * batch
         if d.epi == EPI_PV:   # P [rows, pitch] + V^T [128, pitch] read, residual read + output written (fp16)
-            nbytes = batch * 2.0 * (d.a_dims[1] * d.a_strides[0] + d.n_valid * d.b_strides[0] + 2 * d.a_dims[1] * d.n_valid)
+            p_bytes = 2.0 if not (d.flags & F_A_MIXED) else 1.0 + PV_HOT_FRACTION    # mixed: e4m3 blocks are 1 byte per probability
+            nbytes = batch * (p_bytes * d.a_dims[1] * d.a_strides[0] + 2.0 * d.n_valid * d.b_strides[0] + 4.0 * d.a_dims[1] * d.n_valid)
         name = {EPI_CORR: "corr_gemm", EPI_PV: "attn_pv", EPI_STORE32: "attn_qk"}.get(
             d.epi, "to_v" if (d.flags & F_A_SHARED) else f"rows_k{d.a_dims[0]}to{d.n_valid}")
     return name, flops, nbytes

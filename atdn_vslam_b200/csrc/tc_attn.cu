@@ -13,6 +13,14 @@
 // MMA issuer, warps 4..11 = epilogue.  The 512 TMEM columns hold two 128 x 256 fp32 accumulators; epilogue group
 // g (warps 4+4g .. 7+4g, warp w reads TMEM lanes 32 (w & 3) ..) drains accumulator g, i.e. every second key
 // tile, while the MMA warp fills the other one.  Row maxima / sums of the two groups meet in shared memory.
+//
+// MIXED storage (block_hot != NULL): P.V re-reads P twelve times per pair at the HBM roofline, so every 32-row x
+// 64-column sub-block whose rounding error cannot matter is stored as e4m3 (64-byte rows, half the bytes) and read back
+// by a kind::f8f6f4 MMA; the sub-blocks that carry a row's mass stay fp16.  All values are stored scaled by 256 (e4m3 then keeps
+// its 3 mantissa bits down to 2^-14 of the row maximum; the factor cancels against the row sum).  A sub-block is "hot"
+// (fp16) when for one of its rows  sqrt(sum_block p^2) > hot_energy * sum_row p  -- the e4m3 rounding error of the block
+// relative to that row's output (tools/fp8_attention_sensitivity.py, variants mixed-e*).  The row sums this needs are
+// estimated in pass 1 with an online softmax; pass 2 still sums the ROUNDED values for the normalisation.
 #include <math.h>
 #include <string.h>
 
@@ -31,13 +39,19 @@ constexpr int kAttnStoreBytes = 32 * 128;          // one 32-row x 64-column fp1
 constexpr int kAttnSmem = kAttnQBytes + kAttnKStages * kAttnKStageBytes + 8 * 2 * kAttnStoreBytes + 1024;
 
 struct alignas(64) AttnParams {
-  CUtensorMap tmQ, tmK, tmP;
+  CUtensorMap tmQ, tmK, tmP, tmP8;
   int n, tiles;
   int p_tiled, row_blocks;    // P in blocks of 32 rows x 64 columns ([batch][row block][column block][32][64]); ceil(n / 32)
   float scale_log2;       // softmax scale * log2(e)
   float* inv_sum;         // [batch * n]
+  uint8_t* block_hot;     // MIXED: [batch][row_blocks][col_blocks] 1 = fp16 sub-block (32 rows x 64 columns), 0 = e4m3
+  int col_blocks;
+  float hot_thr;          // (hot_energy * 256)^2
 };
 
+constexpr float kAttnStoreLog2 = 8.0f;   // MIXED: stored value = 256 * exp(s - rowmax)
+
+template <bool MIXED>
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, k_full[kAttnKStages], k_empty[kAttnKStages], acc_full[2], acc_empty[2];
@@ -65,6 +79,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmP);
+    if constexpr (MIXED) tma_prefetch_desc(&p.tmP8);
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
   tcgen05_fence_before();
@@ -132,6 +147,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
     const uint8_t* st_ptr = smem_st + (warp - 4) * 2 * kAttnStoreBytes;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     float mx = -INFINITY, mxs = 0.0f, sum = 0.0f;
+    float s1 = 0.0f, thr = 0.0f;                     // MIXED: pass-1 row sum (relative to mx), hot threshold on sum_block p^2
     uint32_t pf = 0;
     bool exchanged = false;
     int nstore = 0;
@@ -139,8 +155,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
     auto exchange = [&]() {
       xbuf[g][row_local] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(xbuf[0][row_local], xbuf[1][row_local]);
+      const float m0v = xbuf[0][row_local], m1v = xbuf[1][row_local];
+      mx = fmaxf(m0v, m1v);
       mxs = mx * p.scale_log2;
+      if constexpr (MIXED) {   // second round through the same buffer: the pass-1 row sums, each relative to its group's maximum
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        xbuf[g][row_local] = s1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // a group that saw no tile holds (-inf, 0): ex2(-inf) = 0
+        const float srow = xbuf[0][row_local] * ex2_approx((m0v - mx) * p.scale_log2) +
+                           xbuf[1][row_local] * ex2_approx((m1v - mx) * p.scale_log2);
+        const float sfl = fmaxf(srow, 1.0f);          // the row maximum itself contributes 1: a floor under the sampled estimate
+        thr = p.hot_thr * sfl * sfl;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");   // xbuf is reused for the row sums
       exchanged = true;
     };
@@ -160,13 +187,41 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
           uint32_t v[32];
           tmem_ld_32x32(trow + c * 32, v);
           tmem_ld_wait();
-          if (cb + 32 <= p.n) {
+          if constexpr (!MIXED) {
+            if (cb + 32 <= p.n) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-          } else {
+              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cb + j < p.n) mx = fmaxf(mx, __uint_as_float(v[j]));
+            }
+          } else {   // online softmax: running maximum and the row sum relative to it
+            const bool full = cb + 32 <= p.n;
+            float cm = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cb + j < p.n) mx = fmaxf(mx, __uint_as_float(v[j]));
+              if (full || cb + j < p.n) cm = fmaxf(cm, __uint_as_float(v[j]));
+            if (cm > mx) {
+              s1 *= ex2_approx((mx - cm) * p.scale_log2);
+              mx = cm;
+              mxs = mx * p.scale_log2;
+            }
+            // The sum only feeds the hot / cold criterion: every 4th column stands for its group of four (exact for the flat
+            // rows where the criterion matters; a peaked row is over-estimated by at most 4x, i.e. still decided at the
+            // 4 * hot_energy level, tools/fp8_attention_sensitivity.py mixed-e30).  25% of the MUFU work of a full pass.
+            float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -mxs));
+              float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 4]), p.scale_log2, -mxs));
+              if (!full) {
+                if (cb + j >= p.n) e0 = 0.0f;
+                if (cb + j + 4 >= p.n) e1 = 0.0f;
+              }
+              a0 += e0; a1 += e1;
+            }
+            s1 += 4.0f * (a0 + a1);
           }
         }
       } else {
@@ -182,25 +237,74 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
           tmem_ld_32x32(trow + cg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           tmem_ld_wait();
           const bool full = cb + 64 <= p.n;
+          bool hot = true;
+          if constexpr (MIXED) {
+            // exp once, in place; the sub-block's energy decides its storage format
+            const float off = kAttnStoreLog2 - mxs;
+            float en0 = 0.0f, en1 = 0.0f;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {          // 16-byte chunk = 8 probabilities
-            uint32_t w[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const int j = ch * 8 + h * 2;
-              float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -mxs));
-              float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mxs));
+            for (int j = 0; j < 64; j += 2) {
+              float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, off));
+              float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, off));
               if (!full) {
                 if (cb + j >= p.n) e0 = 0.0f;
                 if (cb + j + 1 >= p.n) e1 = 0.0f;
               }
-              const __half2 hh = __floats2half2_rn(e0, e1);
-              const float2 r = __half22float2(hh);   // normalise by what the P.V GEMM will actually read
-              sum += r.x + r.y;
-              w[h] = *reinterpret_cast<const uint32_t*>(&hh);
+              en0 = fmaf(e0, e0, en0);
+              en1 = fmaf(e1, e1, en1);
+              v[j] = __float_as_uint(e0);
+              v[j + 1] = __float_as_uint(e1);
             }
-            st_shared_v4(st_u32 + b * kAttnStoreBytes + lane * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4),
-                         make_uint4(w[0], w[1], w[2], w[3]));
+            // one decision per warp = per 32-row sub-block (no cross-warp traffic); atdn_attn_harmonize makes the eight
+            // sub-blocks of a 256-row P.V tile agree afterwards
+            hot = __any_sync(0xffffffffu, (m0 + row_local < p.n) && (en0 + en1 > thr));
+            if (lane == 0 && (m0 >> 5) + q < p.row_blocks)
+              p.block_hot[(static_cast<long long>(batch) * p.row_blocks + (m0 >> 5) + q) * p.col_blocks + (cb >> 6)] = hot ? 1 : 0;
+          }
+          if (!MIXED || hot) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {          // 16-byte chunk = 8 probabilities
+              uint32_t w[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const int j = ch * 8 + h * 2;
+                float e0, e1;
+                if constexpr (MIXED) {
+                  e0 = __uint_as_float(v[j]);
+                  e1 = __uint_as_float(v[j + 1]);
+                } else {
+                  e0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -mxs));
+                  e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mxs));
+                  if (!full) {
+                    if (cb + j >= p.n) e0 = 0.0f;
+                    if (cb + j + 1 >= p.n) e1 = 0.0f;
+                  }
+                }
+                const __half2 hh = __floats2half2_rn(e0, e1);
+                const float2 r = __half22float2(hh);   // normalise by what the P.V GEMM will actually read
+                sum += r.x + r.y;
+                w[h] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+              st_shared_v4(st_u32 + b * kAttnStoreBytes + lane * 128 + ((static_cast<uint32_t>(ch) ^ sw) << 4),
+                           make_uint4(w[0], w[1], w[2], w[3]));
+            }
+          } else {
+            const uint32_t sw8 = static_cast<uint32_t>(lane >> 1) & 3u;   // 64-byte rows, SWIZZLE_64B
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {          // 16-byte chunk = 16 probabilities
+              uint32_t w[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const int j = ch * 16 + h * 4;
+                const uint32_t lo = pack2_e4m3(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                const uint32_t hi = pack2_e4m3(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                const float2 r0 = unpack2_e4m3(lo), r1 = unpack2_e4m3(hi);
+                sum += (r0.x + r0.y) + (r1.x + r1.y);
+                w[h] = lo | (hi << 16);
+              }
+              st_shared_v4(st_u32 + b * kAttnStoreBytes + lane * 64 + ((static_cast<uint32_t>(ch) ^ sw8) << 4),
+                           make_uint4(w[0], w[1], w[2], w[3]));
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -208,7 +312,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
             if (!p.p_tiled) {
               tma_store_4d(&p.tmP, st_ptr + b * kAttnStoreBytes, cb, m0 + q * 32, 0, batch);
             } else if ((m0 >> 5) + q < p.row_blocks) {   // (the last CTA overhangs the last row block of the batch element)
-              tma_store_4d(&p.tmP, st_ptr + b * kAttnStoreBytes, 0, 0, cb >> 6, batch * p.row_blocks + (m0 >> 5) + q);
+              if (!MIXED || hot) tma_store_4d(&p.tmP, st_ptr + b * kAttnStoreBytes, 0, 0, cb >> 6, batch * p.row_blocks + (m0 >> 5) + q);
+              else tma_store_4d(&p.tmP8, st_ptr + b * kAttnStoreBytes, 0, 0, cb >> 6, batch * p.row_blocks + (m0 >> 5) + q);
             }
             bulk_commit();
           }
@@ -237,12 +342,66 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
   }
 }
 
+// P.V on CTA pairs (tcgen05 cta_group::2) multiplies 256 rows per MMA, so the eight 32-row sub-blocks of a pair tile must
+// hold a column block in the same format.  Where they disagree, the e4m3 sub-blocks are rewritten as fp16 IN PLACE (the
+// same values: their rounding already happened and was judged harmless) and the pair bitmap says "fp16".  One warp per
+// (pair tile, column block); a sub-block is [32][64] bytes at the start of its 4 KiB slot and becomes [32][64] halfs.
+__global__ void __launch_bounds__(256) attn_harmonize_kernel(uint8_t* pbuf, const uint8_t* hot, uint8_t* pair_hot, int pairs, int cb,
+                                                             int row_blocks) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp, pr = blockIdx.y, b = blockIdx.z;
+  if (c >= cb) return;
+  const int rb0 = pr * 8;
+  uint32_t f = 0;
+  if (lane < 8 && rb0 + lane < row_blocks) f = hot[(static_cast<long long>(b) * row_blocks + rb0 + lane) * cb + c];
+  const uint32_t hot_mask = __ballot_sync(0xffffffffu, f != 0);
+  if (lane == 0) pair_hot[(static_cast<long long>(b) * pairs + pr) * cb + c] = hot_mask ? 1 : 0;
+  if (hot_mask == 0) return;
+  for (int sub = 0; sub < 8; ++sub) {
+    const int rbk = rb0 + sub;
+    if (rbk >= row_blocks) break;
+    if ((hot_mask >> sub) & 1u) continue;
+    uint8_t* slot = pbuf + ((static_cast<long long>(b) * row_blocks + rbk) * cb + c) * 4096;
+    uint4 in[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) in[i] = reinterpret_cast<const uint4*>(slot + lane * 64)[i];
+    __syncwarp();                                  // every lane holds its row before any lane overwrites the slot
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t w[4] = {in[i].x, in[i].y, in[i].z, in[i].w};
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(o[2 * j]) : "h"(static_cast<uint16_t>(w[j] & 0xffffu)));
+        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(o[2 * j + 1]) : "h"(static_cast<uint16_t>(w[j] >> 16)));
+      }
+      uint4* dst = reinterpret_cast<uint4*>(slot + lane * 128 + i * 32);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace atdn
 
 using namespace atdn;
 
+extern "C" int atdn_attn_harmonize(void* p16, int64_t p_pitch, const uint8_t* block_hot, uint8_t* pair_hot, int32_t batch, int32_t n,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int e = require_sm100()) return e;
+  ATDN_REQUIRE(p16 && block_hot && pair_hot && batch > 0 && n > 0 && p_pitch == (int64_t)ceil_div(n, 64) * 64, ATDN_ERR_ARG,
+               "atdn_attn_harmonize: null / empty argument or p_pitch != ceil64(n)");
+  const int pairs = ceil_div(n, 256), cb = (int)(p_pitch / 64);
+  attn_harmonize_kernel<<<dim3(ceil_div(cb, 8), pairs, batch), 256, 0, stream>>>(static_cast<uint8_t*>(p16), block_hot, pair_hot, pairs, cb,
+                                                                               ceil_div(n, 32));
+  ATDN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, int64_t p_pitch, int32_t p_tiled, float* inv_sum,
-                               int32_t batch, int32_t n, float scale, void* stream_) {
+                               int32_t batch, int32_t n, float scale, uint8_t* block_hot, float hot_energy, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int e = require_sm100()) return e;
   ATDN_REQUIRE(qk16 && p16 && inv_sum && batch > 0 && n > 0, ATDN_ERR_ARG, "atdn_attn_probs: null / empty argument");
@@ -250,6 +409,8 @@ extern "C" int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, in
                "atdn_attn_probs: qk_pitch %lld / p_pitch %lld", (long long)qk_pitch, (long long)p_pitch);
   ATDN_REQUIRE(scale > 0.0f, ATDN_ERR_ARG, "atdn_attn_probs: scale must be positive (row maxima are taken before scaling)");
   ATDN_REQUIRE(!p_tiled || p_pitch % 64 == 0, ATDN_ERR_ALIGN, "atdn_attn_probs: the tiled layout needs p_pitch %% 64 == 0, got %lld", (long long)p_pitch);
+  ATDN_REQUIRE(!block_hot || (p_tiled && p_pitch == (int64_t)ceil_div(n, 64) * 64 && hot_energy > 0.0f), ATDN_ERR_ARG,
+               "atdn_attn_probs: mixed storage needs the tiled layout with p_pitch = ceil64(n) and hot_energy > 0");
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.n = n;
@@ -269,6 +430,14 @@ extern "C" int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, in
     const int64_t pdims[4] = {64, 32, cb, (int64_t)batch * p.row_blocks};
     const int64_t pstr[3] = {64, 2048, cb * 2048};
     if (int e = make_map_f16(&p.tmP, p16, pdims, pstr, pbox, ones, "P (tiled)")) return e;
+    if (block_hot) {   // the same 4 KiB slots seen as bytes: an e4m3 block fills the first 2 KiB, 64-byte rows
+      const int64_t dims8[4] = {64, 32, cb, (int64_t)batch * p.row_blocks};
+      const int64_t str8[3] = {64, 4096, cb * 4096};
+      if (int e = make_map(&p.tmP8, 1, CU_TENSOR_MAP_SWIZZLE_64B, p16, dims8, str8, pbox, ones, "P (tiled, e4m3 blocks)")) return e;
+      p.block_hot = block_hot;
+      p.col_blocks = (int)cb;
+      p.hot_thr = (hot_energy * 256.0f) * (hot_energy * 256.0f);
+    }
   } else {
     const int64_t pdims[4] = {n, n, 1, batch};
     const int64_t pstr[3] = {p_pitch, (int64_t)n * p_pitch, (int64_t)n * p_pitch};
@@ -276,10 +445,12 @@ extern "C" int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, in
   }
   static DeviceOnce configured;
   if (configured.pending()) {
-    ATDN_CUDA(cudaFuncSetAttribute(attn_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    ATDN_CUDA(cudaFuncSetAttribute(attn_probs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    ATDN_CUDA(cudaFuncSetAttribute(attn_probs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     configured.done();
   }
-  attn_probs_kernel<<<dim3(ceil_div(n, 128), batch), kAttnThreads, kAttnSmem, stream>>>(p);
+  if (block_hot) attn_probs_kernel<true><<<dim3(ceil_div(n, 128), batch), kAttnThreads, kAttnSmem, stream>>>(p);
+  else attn_probs_kernel<false><<<dim3(ceil_div(n, 128), batch), kAttnThreads, kAttnSmem, stream>>>(p);
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }

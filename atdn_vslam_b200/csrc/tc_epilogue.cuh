@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "../../include/atdn_b200.h"
+#include "tc_ptx.cuh"
 
 namespace atdn {
 
@@ -25,6 +26,8 @@ struct EpiParams {
   const float* aux32;
   const float* gamma;
   int img_w, img_h;   // FLOW: output image size (pixel coordinates of `pix`)
+  uint8_t* out8;      // STORE16 of a ROWS GEMM: second copy of the output as two e4m3 planes, hi = e4m3(y), lo = e4m3(y - hi):
+  int out8_rows;      //   [batch][2][out8_rows][out_pitch] bytes (out8_rows = GEMM rows per batch element)
 };
 
 // 1/(1+e^-x) and tanh through MUFU.EX2 + MUFU.RCP: ~1e-6 relative, far below the fp16 operand rounding (5e-4)
@@ -210,6 +213,20 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, bool valid, l
 #pragma unroll
         for (int j = 0; j < 8; ++j) y[g * 8 + j] = fmaxf(r[j] + y[g * 8 + j], 0.0f);
       }
+    }
+    if (p.out8 != nullptr && n + 32 <= p.out_pitch) {   // columns past n_valid are zero accumulators: the pad stays finite
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t a = pack2_e4m3(y[4 * i], y[4 * i + 1]), b = pack2_e4m3(y[4 * i + 2], y[4 * i + 3]);
+        const float2 fa = unpack2_e4m3(a), fb = unpack2_e4m3(b);
+        hi[i] = a | (b << 16);
+        lo[i] = pack2_e4m3(y[4 * i] - fa.x, y[4 * i + 1] - fa.y) | (pack2_e4m3(y[4 * i + 2] - fb.x, y[4 * i + 3] - fb.y) << 16);
+      }
+      const long long bidx = pix / p.out8_rows;
+      uint8_t* d8 = p.out8 + (pix + bidx * p.out8_rows) * p.out_pitch + n;     // one 32-byte sector per plane and row
+      st_global_v8(d8, hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]);
+      st_global_v8(d8 + static_cast<long long>(p.out8_rows) * p.out_pitch, lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]);
     }
     if (st_row != 0) {
 #pragma unroll

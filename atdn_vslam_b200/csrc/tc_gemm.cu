@@ -23,13 +23,14 @@ constexpr int kABytes = kTileM * kChunkK * 2;  // 16 KiB
 constexpr int kThreads = 192;
 
 struct alignas(64) TcParams {
-  CUtensorMap tmA, tmA2, tmB, tmOut;
+  CUtensorMap tmA, tmA2, tmB, tmOut, tmB8;
   int a_mode, tiles_w, out_h, out_w, m_rows;
   int out_tma;            // STORE16 (single-CTA kernel): fp16 output boxes staged in shared memory, written by TMA stores
   int taps_w, pad_h, pad_w, stride;
   int chunks_a, chunks_a2, c_a, c_a2, num_k_iters;
   int b_batched, a_shared;
   int a_tiled, a_row_blocks;   // ATDN_F_A_TILED: A in blocks of 32 rows x 64 columns, ceil(rows / 32) row blocks per batch element
+  const uint8_t* a_hot;        // ATDN_F_A_MIXED: per (batch, 256-row pair tile, 64-column block) 1 = fp16 block, 0 = e4m3 block (tmA2 / tmB8)
   int corr_h, corr_w, corr_tiles_w;
   int lvl_pitch[4];
   float* lvl[3];
@@ -358,7 +359,84 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
 
   const int chunks = p.chunks_a + p.chunks_a2;
 
-  if (warp == 4) {
+  // ATDN_F_A_MIXED on CTA pairs: one bitmap row per 256-row tile (atdn_attn_harmonize); an e4m3 block stages 8 KiB of A per
+  // CTA and this CTA's 64 B rows of both e4m3 planes (2 x 4 KiB) -- 16 KiB per CTA and block through the L2 -> SM path
+  // instead of the 32 KiB of the single-CTA fp16 kernel, which that path, not HBM, was bounding.
+  bool mixed = false;
+  const uint8_t* hot_row = nullptr;
+  if constexpr (EPI == ATDN_EPI_PV && (BN == 128 || BN == 64)) {
+    mixed = p.a_hot != nullptr;
+    if (mixed) hot_row = p.a_hot + (static_cast<long long>(batch) * (gridDim.x >> 1) + pair) * p.num_k_iters;
+  }
+
+  if (warp == 4 && mixed) {
+    if constexpr (EPI == ATDN_EPI_PV && (BN == 128 || BN == 64)) {
+      int stage = 0;
+      uint32_t phase = 0, hot32 = 0;
+      const int rb = batch * p.a_row_blocks + (m0 >> 5);
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        if ((it & 31) == 0) hot32 = (it + lane < p.num_k_iters) ? hot_row[it + lane] : 0u;   // 32 blocks of the bitmap row, one per lane
+        const uint32_t hot = __shfl_sync(0xffffffffu, hot32, it & 31);
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one_sync()) {
+          uint8_t* sA = smem + stage * kStageBytes;
+          uint8_t* sB = sA + kABytes;
+          if (hot) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+            tma_load_4d_pair(sA, &p.tmA, &full_bar[stage], 0, 0, it, rb);
+            tma_load_4d_pair(sB, &p.tmB, &full_bar[stage], it * kChunkK, n0 + rank * (BN / 2), 0, batch);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes / 2 + kBHalfBytes));
+            tma_load_4d_pair(sA, &p.tmA2, &full_bar[stage], 0, 0, it, rb);
+            tma_load_4d_pair(sB, &p.tmB8, &full_bar[stage], it * kChunkK, n0 + rank * (BN / 2), 0, batch);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 5 && mixed) {
+    if constexpr (EPI == ATDN_EPI_PV && (BN == 128 || BN == 64)) {
+      if (rank == 0) {
+        int stage = 0;
+        uint32_t phase = 0, hot32 = 0;
+        const uint32_t smem_base_u32 = smem_u32(smem);
+        for (int it = 0; it < p.num_k_iters; ++it) {
+          if ((it & 31) == 0) hot32 = (it + lane < p.num_k_iters) ? hot_row[it + lane] : 0u;
+          const uint32_t hot = __shfl_sync(0xffffffffu, hot32, it & 31);
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_base_u32 + stage * kStageBytes;
+          const uint32_t acc0 = it > 0 ? 1u : 0u;
+          if (hot) {
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+            const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16_pair(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, k == 0 ? acc0 : 1u);
+              umma_commit_pair(&empty_bar[stage]);
+              if (it == p.num_k_iters - 1) umma_commit_pair(&tmem_full_bar);
+            }
+          } else {
+            const uint64_t a_desc = make_smem_desc_sw64(a_addr);
+            const uint64_t bh_desc = make_smem_desc_sw64(a_addr + kABytes);
+            const uint64_t bl_desc = make_smem_desc_sw64(a_addr + kABytes + kBHalfBytes / 2);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_f8_pair(tmem_base, a_desc + 2u * k, bh_desc + 2u * k, kIdesc, k == 0 ? acc0 : 1u);
+                umma_f8_pair(tmem_base, a_desc + 2u * k, bl_desc + 2u * k, kIdesc, 1u);
+              }
+              umma_commit_pair(&empty_bar[stage]);
+              if (it == p.num_k_iters - 1) umma_commit_pair(&tmem_full_bar);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 4) {
     int stage = 0;
     uint32_t phase = 0;
     int chunk = 0, dx = 0, dy = 0;
@@ -373,6 +451,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
           const int chh = h0 * p.stride + dy - p.pad_h;
           if (chunk < p.chunks_a) tma_load_4d_pair(sA, &p.tmA, &full_bar[stage], chunk * kChunkK, cw, chh, batch);
           else tma_load_4d_pair(sA, &p.tmA2, &full_bar[stage], (chunk - p.chunks_a) * kChunkK, cw, chh, batch);
+        } else if (p.a_tiled) {
+          tma_load_4d_pair(sA, &p.tmA, &full_bar[stage], 0, 0, it, batch * p.a_row_blocks + (m0 >> 5));
         } else {
           tma_load_4d_pair(sA, &p.tmA, &full_bar[stage], it * kChunkK, m0, 0, p.a_shared ? 0 : batch);
         }
@@ -548,6 +628,13 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
   p.e.gamma = d->gamma;
   p.e.img_h = d->out_h > 0 ? d->out_h : 1;   // pixel decode of the tiled recurrent-state layout (tc_epilogue.cuh)
   p.e.img_w = d->out_w > 0 ? d->out_w : 1;
+  if (d->out8) {
+    ATDN_REQUIRE(d->epi == ATDN_EPI_STORE16 && d->a_mode == ATDN_MODE_ROWS && !(d->flags & ATDN_F_PAIR) && aligned16(d->out8) &&
+                 d->out_pitch % 32 == 0 && d->out_ch_off == 0 && !d->bias, ATDN_ERR_ARG,
+                 "atdn_tc_gemm: out8 needs a single-CTA ROWS STORE16 GEMM without bias, out_pitch %% 32 == 0 and out_ch_off == 0");
+    p.e.out8 = static_cast<uint8_t*>(d->out8);
+    p.e.out8_rows = (int)d->a_dims[1];
+  }
   ATDN_REQUIRE(p.e.out != nullptr || d->epi == ATDN_EPI_GRU_ZR, ATDN_ERR_ARG, "atdn_tc_gemm: null output");
 
   const uint32_t ones[4] = {1, 1, 1, 1};
@@ -584,8 +671,8 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
     grid.x = pair ? 2 * p.tiles_w * ceil_div(d->out_h, 16) : p.tiles_w * ceil_div(d->out_h, 8);
   } else {
     if (d->flags & ATDN_F_A_TILED) {
-      ATDN_REQUIRE(!pair && !(d->flags & ATDN_F_A_SHARED) && c_a % 64 == 0, ATDN_ERR_ARG,
-                   "atdn_tc_gemm: A_TILED needs the single-CTA kernel, a batched A and a column count that is a multiple of 64");
+      ATDN_REQUIRE(!(d->flags & ATDN_F_A_SHARED) && c_a % 64 == 0, ATDN_ERR_ARG,
+                   "atdn_tc_gemm: A_TILED needs a batched A and a column count that is a multiple of 64");
       p.a_tiled = 1;
       p.a_row_blocks = ceil_div((int)d->a_dims[1], 32);
       const int64_t cb = c_a / 64;
@@ -593,6 +680,18 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
       const int64_t str[3] = {64, 2048, cb * 2048};
       const uint32_t box[4] = {64, 32, 1, 4};            // 4 row blocks = the 128 rows of an M tile, 4 KiB contiguous each
       if (int e = make_map_f16(&p.tmA, d->a, dims, str, box, ones, "A (tiled)")) return e;
+      if (d->flags & ATDN_F_A_MIXED) {
+        ATDN_REQUIRE(pair && d->epi == ATDN_EPI_PV && (d->bn == 128 || d->bn == 64) && d->b8 && d->a_hot && (d->flags & ATDN_F_B_BATCHED) &&
+                     d->b_strides[0] % 16 == 0, ATDN_ERR_ARG,
+                     "atdn_tc_gemm: A_MIXED needs ATDN_F_PAIR, EPI_PV, bn 128 or 64, a batched B with its e4m3 planes (b8) and the pair bitmap (a_hot)");
+        const int64_t str8[3] = {64, 4096, cb * 4096};     // the same slots seen as bytes: an e4m3 sub-block is the first 2 KiB
+        if (int e = make_map(&p.tmA2, 1, CU_TENSOR_MAP_SWIZZLE_64B, d->a, dims, str8, box, ones, "A (tiled, e4m3 blocks)")) return e;
+        const int64_t bdims[4] = {d->b_dims[0], d->b_dims[1], 2, d->b_dims[3]};
+        const int64_t bstr[3] = {d->b_strides[0], d->b_dims[1] * d->b_strides[0], 2 * d->b_dims[1] * d->b_strides[0]};
+        const uint32_t bbox[4] = {64, (uint32_t)d->bn / 2, 2, 1};   // this CTA's half of the tile's rows, both planes
+        if (int e = make_map(&p.tmB8, 1, CU_TENSOR_MAP_SWIZZLE_64B, d->b8, bdims, bstr, bbox, ones, "B (e4m3 planes)")) return e;
+        p.a_hot = d->a_hot;
+      }
     } else {
       const uint32_t box[4] = {64, 128, 1, 1};
       if (int e = make_map_f16(&p.tmA, d->a, d->a_dims, d->a_strides, box, ones, "A")) return e;

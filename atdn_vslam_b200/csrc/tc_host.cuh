@@ -21,13 +21,13 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 // 4-D tensor map, dims innermost first, strides in ELEMENTS for dims 1..3 (byte strides must be multiples of
-// 16), zero OOB fill (loads) / clipping (stores).  esize = bytes per element (2: fp16, 4: fp32).
+// 16), zero OOB fill (loads) / clipping (stores).  esize = bytes per element (1: bytes / e4m3, 2: fp16, 4: fp32).
 inline int make_map(CUtensorMap* m, int esize, CUtensorMapSwizzle swz, const void* ptr, const int64_t dims[4],
                     const int64_t strides[3], const uint32_t box[4], const uint32_t estr[4], const char* what) {
   EncodeTiledFn fn = get_encode_fn();
   ATDN_REQUIRE(fn != nullptr, ATDN_ERR_ARCH, "cuTensorMapEncodeTiled is not available from the driver");
   ATDN_REQUIRE(ptr != nullptr && aligned16(ptr), ATDN_ERR_ALIGN, "%s: pointer must be non-null and 16-byte aligned", what);
-  ATDN_REQUIRE(esize == 2 || esize == 4, ATDN_ERR_ARG, "%s: element size %d", what, esize);
+  ATDN_REQUIRE(esize == 1 || esize == 2 || esize == 4, ATDN_ERR_ARG, "%s: element size %d", what, esize);
   cuuint64_t gd[4], gs[3];
   cuuint32_t bx[4], es[4];
   for (int i = 0; i < 4; ++i) {
@@ -41,7 +41,7 @@ inline int make_map(CUtensorMap* m, int esize, CUtensorMapSwizzle swz, const voi
                  "%s: strides[%d] = %lld elements is not a positive multiple of 16 bytes", what, i, (long long)strides[i]);
     gs[i] = (cuuint64_t)strides[i] * (cuuint64_t)esize;
   }
-  CUresult r = fn(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+  CUresult r = fn(m, esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                   const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ATDN_REQUIRE(r == CUDA_SUCCESS, (int)r, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);

@@ -194,6 +194,17 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 on a CTA pair (8-bit operands, here e4m3 x e4m3; K = 32 per instruction, fp32 accumulate).  MMAs of both kinds
+// may accumulate into the same TMEM columns: the accumulator is plain fp32 either way.
+__device__ __forceinline__ void umma_f8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives on the mbarrier at this smem offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -261,8 +272,31 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// K-major operand tile with 64-byte rows (64 e4m3 values), SWIZZLE_64B, 8-row groups 512 B apart (the layout TMA writes
+// for a {64 bytes, rows} box with CU_TENSOR_MAP_SWIZZLE_64B); layout type 4.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+// Two fp32 -> packed e4m3 pair (`lo` in the low byte), round to nearest, saturating at +-448; and back as two floats.
+__device__ __forceinline__ uint32_t pack2_e4m3(float lo, float hi) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2_e4m3(uint32_t pair) {
+  uint32_t h2;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(static_cast<uint16_t>(pair)));
+  return __half22float2(*reinterpret_cast<const __half2*>(&h2));
+}
 // Instruction descriptor, kind::f16: D = fp32 (bits [4,6) = 1), A = B = fp16 (0), both K-major,
-// N >> 3 at bits [17,23), M >> 4 at bits [24,29).
+// N >> 3 at bits [17,23), M >> 4 at bits [24,29).  kind::f8f6f4 with e4m3 operands (format code 0 as well) uses the
+// same bits.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }

@@ -83,6 +83,11 @@ _PV_PAIR = os.environ.get("ATDN_PV_PAIR") == "1"      # A/B: P.V on CTA pairs (h
 # attention probabilities in blocks of 32 rows x 64 columns: the store boxes of attn_probs and the operand boxes of P.V are
 # contiguous 4 KiB runs instead of 128-byte rows 14.6 KB apart (ATDN_P_ROWMAJOR=1: plain [N, Np] rows)
 _P_TILED = os.environ.get("ATDN_P_ROWMAJOR") != "1" and not _PV_PAIR
+# Mixed-precision attention probabilities (include/atdn_b200.h, atdn_attn_probs block_hot): 128 x 64 blocks of P whose
+# e4m3 rounding cannot move a row's aggregate stay out of the fp16 stream that P.V re-reads 12 times per pair.
+# ATDN_P_MIXED=0: every block fp16.  ATDN_P_HOT_ENERGY: the criterion's threshold (tools/fp8_attention_sensitivity.py).
+_P_MIXED = os.environ.get("ATDN_P_MIXED", "1") == "1" and _P_TILED
+_P_HOT_ENERGY = float(os.environ.get("ATDN_P_HOT_ENERGY", "1e-2"))
 _GRU_PRE32 = os.environ.get("ATDN_GRU_PRE32") == "1"
 _PRE16 = 0 if _GRU_PRE32 else L.F_PRE16
 _Z16 = 0 if os.environ.get("ATDN_GRU_Z32") == "1" else L.F_Z16
@@ -252,6 +257,11 @@ class _Plan:
         self.p16 = f16(b, (n + 31) // 32, self.np_ // 64, 32, 64) if _P_TILED else f16(b, n, self.np_)
         self.inv_sum = f32(b * n)
         self.vt = f16(b, 128, self.np_)
+        self.mixed = _P_MIXED        # at every batch size: the rounding of a pair must not depend on how pairs are batched
+        if self.mixed:
+            self.v8 = torch.empty(b, 2, 128, self.np_, dtype=torch.uint8, device=dev)          # e4m3 planes hi, lo of v^T
+            self.p_hot = torch.empty(b, (n + 31) // 32, self.np_ // 64, dtype=torch.uint8, device=dev)      # per 32-row sub-block
+            self.p_hot2 = torch.empty(b, (n + 255) // 256, self.np_ // 64, dtype=torch.uint8, device=dev)   # per 256-row P.V tile
         self.coords1 = f32(b, h8, w8, 2)
         self.flow = f32(b, h8, w8, 2)
         self.corrfeat = f16(b, h8, w8, 328)
@@ -553,7 +563,12 @@ class RAFTGMA(nn.Module):
         """Attention.forward (gma.py:54-76) on the context features HX[128:256]: q.k^T * scale -> un-normalised softmax
         numerators P (fp16) + 1 / row sums."""
         _conv_s1(View(plan.hx, 128, 128), wts.to_qk, View(plan.qk), cout=256, taps=(1, 1))
-        ops.attn_probs(plan.qk, plan.p16, plan.inv_sum, 128 ** -0.5, tiled=_P_TILED)
+        ops.attn_probs(plan.qk, plan.p16, plan.inv_sum, 128 ** -0.5, tiled=_P_TILED, block_hot=plan.p_hot if plan.mixed else None,
+                       hot_energy=_P_HOT_ENERGY)
+        if plan.mixed:
+            ops.attn_harmonize(plan.p16, plan.p_hot, plan.p_hot2, plan.n)
+            if L.PROFILER is not None:    # bench.py's byte accounting of the mixed P.V stream (one host read, profiling only)
+                L.PV_HOT_FRACTION = float(plan.p_hot2.float().mean())
 
     def _aggregate(self, plan, wts):
         """Aggregate.forward (gma.py:102-115) on the motion features HX[256:384] -> HX[384:512]:
@@ -569,12 +584,16 @@ class RAFTGMA(nn.Module):
         L._set(d.b_strides, (512, n * 512, n * 512))
         d.n_valid, d.alpha = n, 1.0
         d.out, d.out_pitch = L.ptr(plan.vt), np_
+        if plan.mixed:
+            d.out8 = L.ptr(plan.v8)
         L.tc_gemm(d)
         small = b * math.ceil(n / 128) <= _SMALL_TILES
         ops.gemm_rows(L.ptr(plan.p16), np_ if _P_TILED else n, n, np_, b, L.ptr(plan.vt), 128, np_, L.ptr(hx, 384), 512, n_valid=128,
                       b_bstride=128 * np_, bn=64 if small else 128, epi=L.EPI_PV, b_k=n,
-                      flags=(L.F_PAIR if (_PV_PAIR and not small) else 0) | (L.F_A_TILED if _P_TILED else 0), resid_ptr=L.ptr(hx, 256), resid_pitch=512,
-                      aux32=plan.inv_sum, gamma=wts.gamma)
+                      flags=(L.F_PAIR if ((_PV_PAIR and not small) or plan.mixed) else 0) | (L.F_A_TILED if _P_TILED else 0) |
+                      (L.F_A_MIXED if plan.mixed else 0),
+                      resid_ptr=L.ptr(hx, 256), resid_pitch=512, aux32=plan.inv_sum, gamma=wts.gamma,
+                      b8=plan.v8 if plan.mixed else None, a_hot=plan.p_hot2 if plan.mixed else None)
 
     def _update(self, plan, wts, m_tiles):
         """One refinement iteration: lookup + GMAUpdateBlock (update.py:127-139) + coords update."""

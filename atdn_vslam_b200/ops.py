@@ -129,10 +129,11 @@ def conv_tc(a, wp, bias, out, *, cout, taps=(1, 1), pad=(0, 0), stride=1, bn=128
 
 def gemm_rows(a, a_k, a_rows, a_pitch, batch, b, b_rows, b_pitch, out_ptr, out_pitch, *, n_valid, a_bstride=None,
               b_bstride=None, bn=128, epi=L.EPI_STORE16, flags=0, alpha=1.0, bias=None, resid_ptr=None,
-              resid_pitch=0, aux32=None, gamma=None, b_k=None):
+              resid_pitch=0, aux32=None, gamma=None, b_k=None, b8=None, a_hot=None):
     """Batched D[b] = A[b] (a_rows x a_k) . B[b]^T (b_rows x a_k); pointers are ctypes void pointers,
     pitches in elements.  ``b_bstride=None`` shares B across the batch.  ``b_k``: true K extent of B when A's column
-    count is padded (F_A_TILED: A is read in whole 64-column blocks, B is zero-filled past its extent)."""
+    count is padded (F_A_TILED: A is read in whole 64-column blocks, B is zero-filled past its extent).  ``b8`` / ``a_hot``:
+    the e4m3 planes of B and the block bitmap of A for F_A_MIXED."""
     d = L.TcDesc()
     d.bn, d.epi, d.a_mode, d.b_mode = bn, epi, L.MODE_ROWS, L.MODE_ROWS
     d.flags = flags | (L.F_B_BATCHED if b_bstride is not None else 0)
@@ -150,6 +151,7 @@ def gemm_rows(a, a_k, a_rows, a_pitch, batch, b, b_rows, b_pitch, out_ptr, out_p
     if resid_ptr is not None:
         d.resid16, d.resid_pitch, d.resid_ch_off = resid_ptr, resid_pitch, 0
     d.aux32, d.gamma = L.ptr(aux32), L.ptr(gamma)
+    d.b8, d.a_hot = L.ptr(b8), L.ptr(a_hot)
     L.tc_gemm(d)
 
 
@@ -364,21 +366,30 @@ def inorm_apply(x, stats, y, resid=None, relu=True):
                                       x.B, x.H * x.W, x.c, int(relu), L.stream_ptr()), "atdn_inorm_apply")
 
 
-def attn_probs(qk, p16, inv_sum, scale, tiled=False):
+def attn_probs(qk, p16, inv_sum, scale, tiled=False, block_hot=None, hot_energy=1e-2):
     """qk fp16 [B,H8,W8,256] (q | k) -> p16 [B,N,Np] un-normalised probabilities, inv_sum [B*N] (gma.py:66-73).
-    ``tiled``: p16 is [B, ceil(N/32), Np/64, 32, 64] (blocks of 32 rows x 64 columns, see atdn_attn_probs)."""
+    ``tiled``: p16 is [B, ceil(N/32), Np/64, 32, 64] (blocks of 32 rows x 64 columns, see atdn_attn_probs).
+    ``block_hot`` uint8 [B, ceil(N/128), Np/64]: mixed fp16 / e4m3 storage, the bitmap is written (1 = fp16 block)."""
     b, h8, w8, pitch = qk.shape
     n = h8 * w8
 
     def go():
         L.check(L.load().atdn_attn_probs(L.ptr(qk), C.c_int64(pitch), L.ptr(p16), C.c_int64(p16.shape[-1] if not tiled else p16.shape[2] * 64),
-                                         1 if tiled else 0, L.ptr(inv_sum), b, n, C.c_float(scale), L.stream_ptr()), "atdn_attn_probs")
+                                         1 if tiled else 0, L.ptr(inv_sum), b, n, C.c_float(scale), L.ptr(block_hot), C.c_float(hot_energy),
+                                         L.stream_ptr()), "atdn_attn_probs")
     if L.PROFILER is not None:
         # algorithmic: one q.k^T (2*N*N*128 flop) and N*N fp16 probabilities written per image
         with L.PROFILER("attn_probs", 2.0 * b * n * n * 128, 2.0 * b * n * n):
             go()
         return
     go()
+
+
+@_profiled
+def attn_harmonize(p16, block_hot, pair_hot, n):
+    """Mixed-precision P for the CTA-pair P.V kernel: 256-row bitmap, e4m3 halves next to fp16 halves rewritten as fp16."""
+    L.check(L.load().atdn_attn_harmonize(L.ptr(p16), C.c_int64(p16.shape[2] * 64), L.ptr(block_hot), L.ptr(pair_hot), p16.shape[0], n,
+                                         L.stream_ptr()), "atdn_attn_harmonize")
 
 
 @_profiled

@@ -93,7 +93,11 @@ enum {
   ATDN_F_A_TILED   = 4096, /* ROWS A (single-CTA kernel) is stored in blocks of 32 rows x 64 columns, [batch][ceil(rows/32)][cols/64][32][64]
                               (the layout atdn_attn_probs writes with p_tiled != 0: its 32 x 64 store boxes and the 128 x 64 operand
                               boxes read here are contiguous 4 KiB runs); a_dims = {cols, rows, 1, batch}, a_strides are ignored,
-                              cols must be a multiple of 64 with every column block fully written (zeros past the true extent) */
+                              cols must be a multiple of 64 with every column block fully written (zeros past the true extent); also on CTA pairs */
+  ATDN_F_A_MIXED   = 8192, /* with ATDN_F_PAIR | ATDN_F_A_TILED, ATDN_EPI_PV, bn = 128 or 64: the A blocks of 256 rows x 64 columns are fp16 or e4m3
+                              per block as atdn_attn_probs (block_hot != NULL) + atdn_attn_harmonize left them (a_hot = the pair bitmap);
+                              an e4m3 block is multiplied with the e4m3 copy of B (b8, two planes hi + lo, written by a STORE16 GEMM
+                              with out8) by two tcgen05.mma.kind::f8f6f4 per 32 columns, into the same fp32 accumulator as the fp16 blocks */
   ATDN_F_STATS     = 128, /* STORE16 on the halo kernel with mt = 4, bn = 64 (n_valid = 64): per-channel partial sums of
                             (acc + bias) and its square over the in-image pixels each epilogue warp sees in one tile go to
                             aux32 as [batch, parts, 64, 2] fp32, parts = ceil(H/16) * ceil(W/(32*cl)) * cl * 4 (cl = 2 with
@@ -144,6 +148,12 @@ typedef struct atdn_tc_desc {
    * accumulator buffers).  Instances: (mt, bn) = (1,256) (1,192) (1,128) (2,128) (2,96) (2,64) (4,64) (4,32);
    * epilogues STORE16, STORE32, GRU_ZR, GRU_Q, FLOW (bn 32).  mt = 0: one 8 x 16 pixel tile per CTA.       */
   int32_t mt;
+  /* mixed-precision attention operands (ATDN_F_A_MIXED; all NULL otherwise) */
+  void* out8;             /* STORE16 of a ROWS GEMM (mt = 0): also write the output as two e4m3 planes, hi = e4m3(y) and
+                             lo = e4m3(y - hi): bytes [batch][2][rows][out_pitch]; columns [n_valid, out_pitch) of a started 32-column
+                             chunk are written as zeros, later chunks are untouched (allocate zeroed)                  */
+  const void* b8;         /* ATDN_F_A_MIXED: e4m3 planes of B, bytes [batch][2][b_dims[1]][b_strides[0]] (an out8 buffer)       */
+  const uint8_t* a_hot;   /* ATDN_F_A_MIXED: [batch][ceil(rows/256)][cols/64], 1 = fp16 block, 0 = e4m3 block (atdn_attn_harmonize) */
 } atdn_tc_desc;
 
 int atdn_tc_gemm(const atdn_tc_desc* desc, void* stream);
@@ -192,9 +202,22 @@ int atdn_corr_pyramid(const void* fmap1, const void* fmap2, int64_t fmap_pitch, 
  *   of 64 >= n; columns [n, p_pitch) of the last written block are zeros): every store box is one contiguous 4 KiB run
  *   instead of 32 rows p_pitch apart (strided rows cost the TMA store path ~27%, tools/tma_store_bench.cu), and the P.V GEMM
  *   reads it with ATDN_F_A_TILED.
+ * block_hot != NULL (needs p_tiled and p_pitch = ceil64(n)): MIXED storage.  Every value is stored scaled by 256 (inv_sum
+ *   follows, so consumers see no difference), and each sub-block of 32 rows x 64 columns is either fp16 as above or e4m3:
+ *   [32][64] BYTES in the first 2 KiB of its 4 KiB slot.  A sub-block stays fp16 ("hot", block_hot[b][i/32][j/64] = 1) when
+ *   for one of its rows sqrt(sum_block p^2) > hot_energy * sum_row p, i.e. when the e4m3 rounding of the block could move
+ *   that row's aggregate by more than ~hot_energy / 16 relative.  The row sums of the criterion are ESTIMATES from the first
+ *   pass (online softmax over every 4th column, floored by the row maximum: exact for flat rows, within ~4x for rows carried
+ *   by a few keys); inv_sum comes from the ROUNDED stored values as before.  block_hot: [batch][ceil(n/32)][p_pitch/64].
  * ---------------------------------------------------------------------------------------------- */
 int atdn_attn_probs(const void* qk16, int64_t qk_pitch, void* p16, int64_t p_pitch, int32_t p_tiled, float* inv_sum,
-                    int32_t batch, int32_t n, float scale, void* stream);
+                    int32_t batch, int32_t n, float scale, uint8_t* block_hot, float hot_energy, void* stream);
+
+/* Second step of the mixed storage, for the CTA-pair P.V kernel (ATDN_F_PAIR | ATDN_F_A_TILED | ATDN_F_A_MIXED) whose MMAs span
+ * 256 rows: pair_hot[b][i/256][j/64] = OR of the eight sub-block flags; where they disagree the e4m3 sub-blocks are rewritten
+ * in place as fp16 (identical values: their rounding already happened).  P.V then reads ~(1 + hot fraction) / 2 of the fp16
+ * bytes.  p16 / p_pitch / block_hot as passed to atdn_attn_probs; pair_hot: [batch][ceil(n/256)][p_pitch/64]. */
+int atdn_attn_harmonize(void* p16, int64_t p_pitch, const uint8_t* block_hot, uint8_t* pair_hot, int32_t batch, int32_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Correlation lookup -- GMA.whl!/GMA/core/corr.py:32-53 + utils/utils.py:59-73 (grid_sample).

@@ -420,7 +420,184 @@ def check_aggregate(h8=47, w8=154, batch=2, sharp=1.0, same_qk=False):
     return ok
 
 
+def decode_mixed_p(p16, fmt_rb, n):
+    """Tiled mixed-precision P buffer [B, ceil(N/32), Np/64, 32, 64] fp16 slots + per-sub-block format [B, ceil(N/32), Np/64]
+    (1 = fp16) -> fp32 [B, N, Np] of the stored values (fp16 sub-blocks as they are; e4m3 sub-blocks = the first 2 KiB of the
+    slot as [32][64] bytes) and the per-element format mask."""
+    import torch
+    b, rb, cb = p16.shape[:3]
+    f16 = p16.float()
+    raw = p16.contiguous().view(torch.uint8).view(b, rb, cb, 4096)[..., :2048].contiguous()
+    f8 = raw.view(torch.float8_e4m3fn).float().view(b, rb, cb, 32, 64)
+    is16 = fmt_rb.bool()[..., None, None]
+    vals = torch.where(is16, f16, f8)
+    flat = vals.permute(0, 1, 3, 2, 4).reshape(b, rb * 32, cb * 64)[:, :n]
+    el = is16.expand(b, rb, cb, 32, 64).permute(0, 1, 3, 2, 4).reshape(b, rb * 32, cb * 64)[:, :n]
+    return flat, el
+
+
+def check_aggregate_mixed(h8=47, w8=154, batch=2, sharp=1.0, energy=1e-2, reps=0, small_tiles=0):
+    """Mixed fp16 / e4m3 attention probabilities (atdn_attn_probs block_hot -> atdn_attn_harmonize -> ATDN_F_A_MIXED P.V on CTA
+    pairs, out8 planes of v^T), each stage against torch on the SAME stored operands -- the kernels must be exact up to
+    accumulation order -- and the whole aggregate against the fp32 oracle (what the rounding costs).  ``small_tiles``: the
+    small-problem threshold of gma.py (0: the 128-column P.V tiles of the batched path; None: the default, 64-column tiles here)."""
+    import torch
+    import gpu_e2e
+    from atdn_vslam_b200 import gma
+    from oracle import gma_oracle
+    m, sd = gpu_e2e._gma()
+    sd = {k[7:]: v for k, v in sd.items()}
+    dev = torch.device("cuda")
+    wts = m._weights(dev)
+    old = gma._P_MIXED, gma._P_HOT_ENERGY, gma._SMALL_TILES
+    gma._P_MIXED, gma._P_HOT_ENERGY, gma._SMALL_TILES = True, energy, (old[2] if small_tiles is None else small_tiles)
+    try:
+        plan = gma._Plan(batch, h8 * 8, w8 * 8, dev)
+        n, np_ = plan.n, plan.np_
+        rb, cb = plan.p_hot.shape[1:]
+        g = torch.Generator().manual_seed(31)
+        inp = (torch.relu(torch.randn(batch, 128, h8, w8, generator=g)) * sharp).half()
+        mf = torch.relu(torch.randn(batch, 128, h8, w8, generator=g)).half()
+        plan.hx.zero_()
+        plan.hx[..., 128:256] = inp.permute(0, 2, 3, 1).cuda()
+        plan.hx[..., 256:384] = mf.permute(0, 2, 3, 1).cuda()
+        plan.p16.fill_(float("nan"))
+        plan.p_hot.fill_(7)
+        plan.p_hot2.fill_(7)
+        plan.v8.fill_(0x7f)                      # e4m3 NaN: an unwritten byte inside the K extent would poison the output
+        m._attention(plan, wts)
+        m._aggregate(plan, wts)
+        torch.cuda.synchronize()
+        ok = bool(((plan.p_hot == 0) | (plan.p_hot == 1)).all())
+        if reps:
+            print(f"fp16 blocks {100 * float(plan.p_hot2.float().mean()):.1f}%", flush=True)
+            for name, fn in (("attn_probs mixed + harmonize", lambda: m._attention(plan, wts)), ("to_v + P.V mixed", lambda: m._aggregate(plan, wts))):
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                fn()
+                s0.record()
+                for _ in range(reps):
+                    fn()
+                s1.record()
+                torch.cuda.synchronize()
+                print(f"TIME {name} batch={batch}: {s0.elapsed_time(s1) / reps:.3f} ms", flush=True)
+            return ok
+        # 0. the pair bitmap is the OR of the eight sub-block flags of a 256-row tile; it is the storage format after harmonisation
+        want2 = torch.nn.functional.pad(plan.p_hot, (0, 0, 0, (-rb) % 8)).view(batch, -1, 8, cb).amax(2)
+        same = bool(torch.equal(plan.p_hot2, want2))
+        fmt = plan.p_hot2.repeat_interleave(8, dim=1)[:, :rb]
+        print(f"{'PASS' if same else 'FAIL'} pair bitmap = OR of its sub-blocks; hot sub-blocks {100 * float(plan.p_hot.float().mean()):.1f}%, "
+              f"fp16 blocks after harmonisation {100 * float(fmt.float().mean()):.1f}%", flush=True)
+        ok &= same
+        stored, fmt_el = decode_mixed_p(plan.p16, fmt, n)
+        hot_el = plan.p_hot.bool()[..., None, None].expand(batch, rb, cb, 32, 64).permute(0, 1, 3, 2, 4).reshape(batch, rb * 32, np_)[:, :n]
+        # 1. stored values = 256 * exp(s - rowmax) of the product's own fp16 q, k: fp16 rounding in the sub-blocks attn_probs kept
+        #    hot, e4m3 rounding in the others (also where harmonisation rewrote them as fp16 afterwards)
+        q, k = plan.qk.float().reshape(batch, n, 256).split(128, dim=2)
+        sl = torch.matmul(q, k.transpose(1, 2)) * 128 ** -0.5
+        pref = torch.exp(sl - sl.max(dim=2, keepdim=True).values) * 256.0
+        err = (stored[:, :, :n] - pref).abs()
+        tol = torch.where(hot_el[:, :, :n], pref * 1.5e-3 + 1e-5, pref * 0.0635 + 2.0 ** -10)
+        bad = int((err > tol).sum())
+        print(f"{'PASS' if bad == 0 else 'FAIL'} mixed P values: {bad} of {err.numel()} outside their format's rounding", flush=True)
+        ok &= bad == 0
+        ok &= bool((stored[:, :, n:] == 0).all())
+        # 2. the sub-block flags follow the energy criterion; the kernel's row sums are estimates from every 4th column with the row
+        #    maximum as a floor (exact for flat rows, up to ~4x off for rows carried by a few keys): only sub-blocks a factor 4.6
+        #    away from the threshold are held to it
+        rows = pref.sum(2, keepdim=True)
+        pad = rb * 32 - n
+        e2 = torch.nn.functional.pad(pref, (0, np_ - n, 0, pad)).pow(2).reshape(batch, rb, 32, cb, 64).sum(4).sqrt()
+        ratio = (e2 / torch.nn.functional.pad(rows, (0, 0, 0, pad), value=float("inf")).reshape(batch, rb, 32, 1)).amax(2)
+        want_hot, want_cold = ratio > energy * 4.6, ratio < energy / 4.6
+        wrong = int((want_hot & (plan.p_hot == 0)).sum() + (want_cold & (plan.p_hot == 1)).sum())
+        print(f"{'PASS' if wrong == 0 else 'FAIL'} mixed P bitmap: {wrong} sub-blocks on the wrong side of the criterion "
+              f"({int((~want_hot & ~want_cold).sum())} of {ratio.numel()} within 4.6x of it)", flush=True)
+        ok &= wrong == 0
+        inv = plan.inv_sum.view(batch, n)
+        ok &= _cmp("mixed inv_sum = 1 / sum of the stored values", inv, 1.0 / stored.sum(2), 1e-4)
+        # 3. e4m3 planes of v^T: hi + lo reproduces the fp32 product to ~2^-7 relative; the fp16 copy is untouched
+        vt32 = torch.matmul(wts.to_v.float().view(128, 128), plan.hx[..., 256:384].float().reshape(batch, n, 128).transpose(1, 2))
+        v8 = plan.v8.view(torch.float8_e4m3fn).float()
+        hi, lo = v8[:, 0, :, :n], v8[:, 1, :, :n]
+        ok &= _cmp("v8 hi plane = e4m3(v)", hi, vt32, 0.07)
+        e = ((hi + lo) - vt32).abs()
+        badv = int((e > vt32.abs() * 2.0 ** -7 + 2.0 ** -9).sum())
+        print(f"{'PASS' if badv == 0 else 'FAIL'} v^T e4m3 planes: hi + lo within 2^-7 relative of the fp32 product ({badv} outliers, max abs err {float(e.max()):.2e})", flush=True)
+        ok &= badv == 0
+        # 4. P.V on exactly these operands: fp16 blocks x fp16 v, e4m3 blocks x (hi + lo)
+        v16 = plan.vt[:, :, :n].float()
+        st_n, f_n = stored[:, :, :n], fmt_el[:, :, :n]
+        acc = torch.matmul(torch.where(f_n, st_n, torch.zeros_like(st_n)), v16.transpose(1, 2)) + \
+            torch.matmul(torch.where(f_n, torch.zeros_like(st_n), st_n), (hi + lo).transpose(1, 2))
+        gamma = float(wts.gamma)
+        resid = plan.hx[..., 256:384].float().reshape(batch, n, 128)
+        got = plan.hx[..., 384:512].float().reshape(batch, n, 128)
+        ok &= _cmp(f"mixed P.V {h8}x{w8} batch={batch} on the stored operands", got, resid + gamma * acc * inv.unsqueeze(2), 1e-3)
+        ok &= _cmp("mixed P.V minus residual", got - resid, gamma * acc * inv.unsqueeze(2), 4e-3)
+        # 5. against the fp32 oracle: what the rounding costs
+        attn = gma_oracle.attention(inp.float(), sd)
+        ref = gma_oracle.aggregate(attn, mf.float(), sd)
+        neff = float((1.0 / attn.pow(2).sum(-1)).mean())
+        ok &= _cmp(f"mixed aggregate vs fp32 oracle (effective support {neff:.0f} of {n})", got.reshape(batch, h8, w8, 128).permute(0, 3, 1, 2), ref, 2e-3)
+    finally:
+        gma._P_MIXED, gma._P_HOT_ENERGY, gma._SMALL_TILES = old
+    return ok
+
+
+def check_mixed_determinism(h8=47, w8=154, batch=3, sharp=1.5, energy=2e-2, runs=4):
+    """The mixed-precision attention path twice over on the same inputs: bitmaps, stored probabilities, row sums, e4m3
+    planes and the aggregate must repeat bit for bit (no launch-order dependence, no uninitialised reads)."""
+    import torch
+    import gpu_e2e
+    from atdn_vslam_b200 import gma
+    m, _ = gpu_e2e._gma()
+    dev = torch.device("cuda")
+    wts = m._weights(dev)
+    old = gma._P_MIXED, gma._P_HOT_ENERGY, gma._SMALL_TILES
+    gma._P_MIXED, gma._P_HOT_ENERGY, gma._SMALL_TILES = True, energy, 0
+    ok = True
+    try:
+        plan = gma._Plan(batch, h8 * 8, w8 * 8, dev)
+        n = plan.n
+        rb = plan.p_hot.shape[1]
+        g = torch.Generator().manual_seed(5)
+        plan.hx.zero_()
+        plan.hx[..., 128:256] = (torch.relu(torch.randn(batch, h8, w8, 128, generator=g)) * sharp).half().cuda()
+        plan.hx[..., 256:384] = torch.relu(torch.randn(batch, h8, w8, 128, generator=g)).half().cuda()
+        snaps = []
+        for r in range(runs):
+            plan.p16.fill_(float(r))             # different stale bytes under every run
+            plan.v8.fill_(r)
+            m._attention(plan, wts)
+            m._aggregate(plan, wts)
+            torch.cuda.synchronize()
+            fmt = plan.p_hot2.repeat_interleave(8, dim=1)[:, :rb]
+            stored, _ = decode_mixed_p(plan.p16, fmt, n)
+            snaps.append({"p_hot": plan.p_hot.clone(), "p_hot2": plan.p_hot2.clone(), "stored": stored, "inv_sum": plan.inv_sum.clone(),
+                          "v8": plan.v8[..., :n].clone(), "vt": plan.vt[..., :n].clone(), "out": plan.hx[..., 384:512].clone()})
+        for key in snaps[0]:
+            same = all(torch.equal(snaps[0][key], sn[key]) for sn in snaps[1:])
+            if not same:
+                d = [(snaps[0][key].float() - sn[key].float()).abs() for sn in snaps[1:]]
+                print(f"FAIL {key} differs between runs: max abs diff {max(float(x.max()) for x in d):.3e}, elements {[int((x > 0).sum()) for x in d]}", flush=True)
+            else:
+                print(f"PASS {key} repeats bit for bit over {runs} runs", flush=True)
+            ok &= same
+        print(f"hot sub-blocks {100 * float(plan.p_hot.float().mean()):.1f}%, fp16 blocks {100 * float(plan.p_hot2.float().mean()):.1f}%", flush=True)
+    finally:
+        gma._P_MIXED, gma._P_HOT_ENERGY, gma._SMALL_TILES = old
+    return ok
+
+
 CHECKS = {
+    "mixed_determinism": lambda: check_mixed_determinism(),
+    "mixed_determinism_flat": lambda: check_mixed_determinism(sharp=1.0, energy=1e-2, batch=2),
+    "aggregate_mixed_full": lambda: check_aggregate_mixed(),
+    "aggregate_mixed_peaked": lambda: check_aggregate_mixed(batch=1, sharp=2.0),
+    "aggregate_mixed_small_odd": lambda: check_aggregate_mixed(h8=23, w8=39, batch=3, energy=2e-2),
+    "aggregate_mixed_partly_hot": lambda: check_aggregate_mixed(batch=1, sharp=1.5, energy=2e-2),
+    "aggregate_mixed_partly_hot_bn64": lambda: check_aggregate_mixed(batch=1, sharp=1.5, energy=2e-2, small_tiles=None),
+    "time_aggregate_mixed": lambda: check_aggregate_mixed(batch=27, reps=5),
     "aggregate_full": lambda: check_aggregate(),
     "aggregate_peaked": lambda: check_aggregate(batch=1, sharp=2.0),
     "aggregate_very_peaked_same_qk": lambda: check_aggregate(batch=1, sharp=3.0, same_qk=True),

@@ -306,7 +306,9 @@ template <int BN, int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_kernel(const __grid_constant__ TcParams p) {
   constexpr int kBHalfBytes = (BN / 2) * kChunkK * 2;
   constexpr int kStageBytes = kABytes + kBHalfBytes;
-  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  // P.V keeps a second accumulator half for the lo plane of the e4m3 blocks (ATDN_F_A_MIXED): columns [BN, 2 BN)
+  constexpr int kAccN = (EPI == ATDN_EPI_PV && (BN == 128 || BN == 64)) ? 2 * BN : BN;
+  constexpr uint32_t kTmemCols = kAccN <= 32 ? 32 : kAccN <= 64 ? 64 : kAccN <= 128 ? 128 : 256;
   constexpr uint32_t kIdesc = make_idesc_f16(2 * kTileM, BN);
 
   extern __shared__ uint8_t smem_raw[];
@@ -350,6 +352,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
     tma_prefetch_desc(&p.tmB);
     if (p.chunks_a2 > 0) tma_prefetch_desc(&p.tmA2);
   }
+  if constexpr (EPI == ATDN_EPI_PV && (BN == 128 || BN == 64)) {
+    if (p.a_hot != nullptr) {   // 8 KiB of zeros behind the ring: the operand tile of the accumulator-clearing MMA
+      uint4* z = reinterpret_cast<uint4*>(smem + STAGES * kStageBytes);
+      for (int i = threadIdx.x; i < 8192 / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+      fence_proxy_async_smem();
+    }
+  }
   if (warp == 5) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
@@ -360,8 +369,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
   const int chunks = p.chunks_a + p.chunks_a2;
 
   // ATDN_F_A_MIXED on CTA pairs: one bitmap row per 256-row tile (atdn_attn_harmonize); an e4m3 block stages 8 KiB of A per
-  // CTA and this CTA's 64 B rows of both e4m3 planes (2 x 4 KiB) -- 16 KiB per CTA and block through the L2 -> SM path
-  // instead of the 32 KiB of the single-CTA fp16 kernel, which that path, not HBM, was bounding.
+  // CTA and ONE e4m3 plane of the B tile (CTA 0 the hi plane, CTA 1 the lo plane: BN x 64 bytes) -- 16 KiB per CTA and block
+  // through the L2 -> SM path instead of the 32 KiB of the single-CTA fp16 kernel.  The pair's MMA then has N = 2 BN: B rows
+  // [0, BN) come from CTA 0 (hi -> accumulator columns [0, BN), where the fp16 blocks accumulate as well) and rows
+  // [BN, 2 BN) from CTA 1 (lo -> columns [BN, 2 BN)); the epilogue adds the halves.  One N = 2 BN instruction per 32
+  // columns reads the A operand from shared memory once for both planes (two N = BN instructions: 96 instead of 64
+  // bytes per clock, the regime in which every N = 128 kernel here stops at ~0.65 of the tensor peak).
   bool mixed = false;
   const uint8_t* hot_row = nullptr;
   if constexpr (EPI == ATDN_EPI_PV && (BN == 128 || BN == 64)) {
@@ -388,7 +401,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
           } else {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes / 2 + kBHalfBytes));
             tma_load_4d_pair(sA, &p.tmA2, &full_bar[stage], 0, 0, it, rb);
-            tma_load_4d_pair(sB, &p.tmB8, &full_bar[stage], it * kChunkK, n0 + rank * (BN / 2), 0, batch);
+            tma_load_4d_pair(sB, &p.tmB8, &full_bar[stage], it * kChunkK, n0, rank, batch);
           }
         }
         __syncwarp();
@@ -401,32 +414,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
         int stage = 0;
         uint32_t phase = 0, hot32 = 0;
         const uint32_t smem_base_u32 = smem_u32(smem);
+        constexpr uint32_t kIdesc2 = make_idesc_f16(2 * kTileM, 2 * BN);
+        // both accumulator halves start at zero: one MMA over the zeroed operand tile behind the ring (a first fp16 block
+        // would leave the lo half uninitialised, and one instruction cannot overwrite one half and accumulate into the other)
+        const uint64_t z_desc = make_smem_desc_sw64(smem_base_u32 + STAGES * kStageBytes);
+        if (elect_one_sync()) umma_f8_pair(tmem_base, z_desc, z_desc, kIdesc2, 0u);
+        __syncwarp();
         for (int it = 0; it < p.num_k_iters; ++it) {
           if ((it & 31) == 0) hot32 = (it + lane < p.num_k_iters) ? hot_row[it + lane] : 0u;
           const uint32_t hot = __shfl_sync(0xffffffffu, hot32, it & 31);
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_base_u32 + stage * kStageBytes;
-          const uint32_t acc0 = it > 0 ? 1u : 0u;
           if (hot) {
             const uint64_t a_desc = make_smem_desc_sw128(a_addr);
             const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
             if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16_pair(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, k == 0 ? acc0 : 1u);
+              for (int k = 0; k < 4; ++k) umma_f16_pair(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);
               umma_commit_pair(&empty_bar[stage]);
               if (it == p.num_k_iters - 1) umma_commit_pair(&tmem_full_bar);
             }
           } else {
             const uint64_t a_desc = make_smem_desc_sw64(a_addr);
-            const uint64_t bh_desc = make_smem_desc_sw64(a_addr + kABytes);
-            const uint64_t bl_desc = make_smem_desc_sw64(a_addr + kABytes + kBHalfBytes / 2);
+            const uint64_t b_desc = make_smem_desc_sw64(a_addr + kABytes);
             if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                umma_f8_pair(tmem_base, a_desc + 2u * k, bh_desc + 2u * k, kIdesc, k == 0 ? acc0 : 1u);
-                umma_f8_pair(tmem_base, a_desc + 2u * k, bl_desc + 2u * k, kIdesc, 1u);
-              }
+              for (int k = 0; k < 2; ++k) umma_f8_pair(tmem_base, a_desc + 2u * k, b_desc + 2u * k, kIdesc2, 1u);
               umma_commit_pair(&empty_bar[stage]);
               if (it == p.num_k_iters - 1) umma_commit_pair(&tmem_full_bar);
             }
@@ -522,6 +536,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(trow + c * 32, v);
+        if constexpr (kAccN == 2 * BN) {
+          if (mixed) {             // + the lo-plane half of the accumulator
+            uint32_t w[32];
+            tmem_ld_32x32(trow + BN + c * 32, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+          }
+        }
         tmem_ld_wait();
         epilogue_chunk<EPI>(p.e, valid, pix, n0 + c * 32, v);
       }
@@ -556,7 +579,7 @@ static int launch(const TcParams& p, dim3 grid, cudaStream_t stream) {
 
 template <int BN, int STAGES, int EPI>
 static int launch2(const TcParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + (BN / 2) * kChunkK * 2) + 1024;
+  constexpr int smem = STAGES * (kABytes + (BN / 2) * kChunkK * 2) + 1024 + (EPI == ATDN_EPI_PV ? 8192 : 0);   // PV: + the zero tile
   static DeviceOnce configured;
   if (configured.pending()) {
     ATDN_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -688,7 +711,7 @@ extern "C" int atdn_tc_gemm(const atdn_tc_desc* d, void* stream_) {
         if (int e = make_map(&p.tmA2, 1, CU_TENSOR_MAP_SWIZZLE_64B, d->a, dims, str8, box, ones, "A (tiled, e4m3 blocks)")) return e;
         const int64_t bdims[4] = {d->b_dims[0], d->b_dims[1], 2, d->b_dims[3]};
         const int64_t bstr[3] = {d->b_strides[0], d->b_dims[1] * d->b_strides[0], 2 * d->b_dims[1] * d->b_strides[0]};
-        const uint32_t bbox[4] = {64, (uint32_t)d->bn / 2, 2, 1};   // this CTA's half of the tile's rows, both planes
+        const uint32_t bbox[4] = {64, (uint32_t)d->bn, 1, 1};       // all rows of the tile, one plane per CTA of the pair
         if (int e = make_map(&p.tmB8, 1, CU_TENSOR_MAP_SWIZZLE_64B, d->b8, bdims, bstr, bbox, ones, "B (e4m3 planes)")) return e;
         p.a_hot = d->a_hot;
       }

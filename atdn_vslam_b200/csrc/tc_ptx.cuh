@@ -289,6 +289,11 @@ __device__ __forceinline__ uint32_t pack2_e4m3(float lo, float hi) {
   asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ __half2 unpack2_e4m3_h2(uint32_t pair) {   // exact: every e4m3 value is an fp16 value
+  uint32_t h2;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(static_cast<uint16_t>(pair)));
+  return *reinterpret_cast<const __half2*>(&h2);
+}
 __device__ __forceinline__ float2 unpack2_e4m3(uint32_t pair) {
   uint32_t h2;
   asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(static_cast<uint16_t>(pair)));

@@ -19,6 +19,7 @@ Two sharding schemes:
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -44,11 +45,14 @@ def shard_ranges(num_pairs, world):
     return out
 
 
+_FIRST_BATCH_DIV = int(os.environ.get("ATDN_FIRST_BATCH_DIV", "4"))     # A/B: size of the short first batch of a streamed run
+
+
 def batch_ranges(num_pairs, batch_pairs, short_first=False):
     """Pair ranges [start, end) of the batches of one rank.  ``short_first``: the first batch of a streamed (host
     frames) run cannot overlap its own host->device copy, so it is a quarter batch -- the start-up bubble is the copy of
     ~batch_pairs/4 frames instead of a whole batch."""
-    first = max(1, batch_pairs // 4) if (short_first and num_pairs > batch_pairs) else batch_pairs
+    first = max(1, batch_pairs // _FIRST_BATCH_DIV) if (short_first and num_pairs > batch_pairs) else batch_pairs
     out, s = [], 0
     while s < num_pairs:
         e = min(num_pairs, s + (first if s == 0 else batch_pairs))

@@ -514,7 +514,8 @@ def check_aggregate_mixed(h8=47, w8=154, batch=2, sharp=1.0, energy=1e-2, reps=0
               f"({int((~want_hot & ~want_cold).sum())} of {ratio.numel()} within 4.6x of it)", flush=True)
         ok &= wrong == 0
         inv = plan.inv_sum.view(batch, n)
-        ok &= _cmp("mixed inv_sum = 1 / sum of the stored values", inv, 1.0 / stored.sum(2), 1e-4)
+        # (e4m3 blocks are summed pairwise in fp16 first: exact for neighbours within 2^6 of each other, else ~2^-12 per level)
+        ok &= _cmp("mixed inv_sum = 1 / sum of the stored values", inv, 1.0 / stored.sum(2), 3e-4)
         # 3. e4m3 planes of v^T: hi + lo reproduces the fp32 product to ~2^-7 relative; the fp16 copy is untouched
         vt32 = torch.matmul(wts.to_v.float().view(128, 128), plan.hx[..., 256:384].float().reshape(batch, n, 128).transpose(1, 2))
         v8 = plan.v8.view(torch.float8_e4m3fn).float()

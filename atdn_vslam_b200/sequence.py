@@ -30,8 +30,9 @@ SLAM_SIZE = (376, 1232)   # neural_slam.py:54,198: every frame is resized to thi
 
 # measured on B200 (profiles/r02o_scan_bench.txt, r02n_bench_8gpu.json): one scan call costs ~0.1 ms + ~14-15 us per pair
 # (two grid barriers per LSTM step); in the sharded run rank 0 spent 82.6 ms per 4540 pairs in 11 calls.  The pair-parallel
-# part costs ~1.3 ms per pair.  Rounds are scanned in groups of at least SCAN_MIN_PAIRS pairs.
-SCAN_US_PER_CALL, SCAN_US_PER_PAIR, FLOW_US_PER_PAIR, SCAN_MIN_PAIRS = 500.0, 17.0, 1320.0, 400
+# part costs ~1.23 ms per pair (1.32 before the mixed-precision attention probabilities; with the old constant rank 0 was the
+# critical rank by 14 ms of a 720 ms step, profiles/r02al_bench_8gpu.json).  Rounds are scanned in groups of at least SCAN_MIN_PAIRS pairs.
+SCAN_US_PER_CALL, SCAN_US_PER_PAIR, FLOW_US_PER_PAIR, SCAN_MIN_PAIRS = 500.0, 17.0, 1230.0, 400
 
 
 def shard_ranges(num_pairs, world):

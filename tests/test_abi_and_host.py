@@ -377,7 +377,7 @@ def test_interleaved_rounds_cover_the_sequence_in_order():
         assert max(sizes[1:] or [0]) - min(sizes[1:] or [0]) <= 1        # the remainder is spread evenly
         for r in range(world):
             assert sum(e - s for s, e in local_frame_ranges(rounds, r)) == sum(row[r][1] - row[r][0] for row in rounds)
-    assert default_lead_pairs(1, 54) == 54 and default_lead_pairs(8, 54) == 48 and default_lead_pairs(2, 54) == 52
+    assert default_lead_pairs(1, 54) == 54 and default_lead_pairs(8, 54) == 47 and default_lead_pairs(2, 54) == 52
 
 
 class _StubFlow(torch.nn.Module):

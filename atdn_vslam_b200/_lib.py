@@ -20,7 +20,7 @@ EXPORTS = (
     "atdn_last_error", "atdn_version", "atdn_check_device", "atdn_tc_gemm", "atdn_corr_lookup",
     "atdn_stem_pack", "atdn_flow_pack", "atdn_inorm_stats", "atdn_inorm_apply",
     "atdn_convex_upsample", "atdn_coords_init", "atdn_conv32", "atdn_linear32",
-    "atdn_lstm_cell", "atdn_keyframe_search", "atdn_attn_probs", "atdn_corr_pyramid", "atdn_clvo_lstm_scan", "atdn_pose_chain", "atdn_flow_head_gather", "atdn_inorm_finalize", "atdn_attn_harmonize",
+    "atdn_lstm_cell", "atdn_keyframe_search", "atdn_attn_probs", "atdn_corr_pyramid", "atdn_clvo_lstm_scan", "atdn_pose_chain", "atdn_flow_head_gather", "atdn_inorm_finalize", "atdn_attn_harmonize", "atdn_resize_aa",
 )
 
 

@@ -386,6 +386,21 @@ def attn_probs(qk, p16, inv_sum, scale, tiled=False, block_hot=None, hot_energy=
 
 
 @_profiled
+def resize_aa(frames, size):
+    """frames [T,C,H,W] float32 or uint8 (CUDA, contiguous) -> [T,C,size[0],size[1]] float32, antialiased bilinear
+    (TF.resize of neural_slam.py:197-199)."""
+    L.require_cuda(frames)
+    if frames.dtype not in (torch.float32, torch.uint8):
+        frames = frames.float()
+    frames = frames.contiguous()
+    t, c, h, w = frames.shape
+    out = torch.empty(t, c, size[0], size[1], dtype=torch.float32, device=frames.device)
+    L.check(L.load().atdn_resize_aa(L.ptr(frames), 1 if frames.dtype == torch.uint8 else 0, L.ptr(out), t * c, h, w, size[0], size[1],
+                                    L.stream_ptr()), "atdn_resize_aa")
+    return out
+
+
+@_profiled
 def attn_harmonize(p16, block_hot, pair_hot, n):
     """Mixed-precision P for the CTA-pair P.V kernel: 256-row bitmap, e4m3 halves next to fp16 halves rewritten as fp16."""
     L.check(L.load().atdn_attn_harmonize(L.ptr(p16), C.c_int64(p16.shape[2] * 64), L.ptr(block_hot), L.ptr(pair_hot), p16.shape[0], n,

@@ -235,6 +235,14 @@ int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitch[4], int32
 /* ------------------------------------------------------------------------------------------------
  * Element-wise / data-movement kernels of the flow net
  * ---------------------------------------------------------------------------------------------- */
+/* Caller-side resize of the SLAM loop -- neural_slam.py:197-199 (TF.resize: bilinear, antialias=True) -- replacing
+ * torch.nn.functional.interpolate(..., antialias=True).  src: [planes, in_h, in_w] fp32 or uint8 (src_is_u8), dst: [planes, out_h,
+ * out_w] fp32.  ATen's separable triangle filter: per axis scale = in / out, support = max(scale, 1), center = scale * (o + 0.5),
+ * taps lo = max(int(center - support + 0.5), 0) .. min(int(center + support + 0.5), in), weight max(0, 1 - |(i - center + 0.5) /
+ * max(scale, 1)|) normalised to sum 1; rows are filtered first.  Equal sizes on an axis give the identity on that axis.
+ * Down-scaling by more than 5x is refused (ATDN_ERR_UNSUP). */
+int atdn_resize_aa(const void* src, int32_t src_is_u8, float* dst, int32_t planes, int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w,
+                   void* stream);
 /* The two 7x7 convolutions on thin inputs (3-channel image, 2-channel flow) run on atdn_tc_gemm after their
  * HORIZONTAL taps have been folded into channels; the vertical taps stay implicit in the convolution.
  *

@@ -214,6 +214,35 @@ def test_sequence_pipeline_matches_per_pair_calls_and_keyframes():
     assert keys == o_keys and torch.equal(poses, o_poses)
 
 
+@pytest.mark.parametrize("shape", [(376, 1241), (370, 1226), (375, 1242), (400, 1300), (188, 620), (376, 1232)])
+def test_resize_aa_matches_tf_resize(shape):
+    """atdn_resize_aa (the caller-side resize of neural_slam.py:197-199) against torch's antialiased bilinear interpolate, the op
+    behind TF.resize, on the CPU (what the reference computes with device="cpu") and on CUDA; float and uint8 frames."""
+    import torch.nn.functional as F
+    from atdn_vslam_b200 import ops
+    from atdn_vslam_b200.sequence import SLAM_SIZE, preprocess
+    g = torch.Generator().manual_seed(shape[0] * 7 + shape[1])
+    host = torch.rand(3, 3, *shape, generator=g) * 255.0
+    for frames in (host, host.round().to(torch.uint8)):
+        want_cpu = F.interpolate(frames.float(), size=SLAM_SIZE, mode="bilinear", antialias=True, align_corners=False)
+        got = preprocess(frames.cuda())
+        assert got.dtype == torch.float32 and tuple(got.shape) == (3, 3) + SLAM_SIZE
+        if shape == SLAM_SIZE:
+            assert torch.equal(got.cpu(), frames.float())
+            continue
+        want_cuda = F.interpolate(frames.cuda().float(), size=SLAM_SIZE, mode="bilinear", antialias=True, align_corners=False)
+        err_cpu = float((got.cpu() - want_cpu).abs().max())
+        err_cuda = float((got - want_cuda).abs().max())
+        ref_gap = float((want_cuda.cpu() - want_cpu).abs().max())
+        print(f"resize {shape}: vs CPU {err_cpu:.2e}, vs torch CUDA {err_cuda:.2e} (torch CUDA vs CPU {ref_gap:.2e})")
+        # values are 0..255: 1e-4 is 4e-7 relative.  ATen's CPU kernel itself sits 1.5e-2 away from its CUDA kernel (different weight
+        # arithmetic); the kernel follows the CUDA one, which is what this path used before
+        assert err_cuda <= 1e-4 and err_cpu <= max(1e-4, 1.5 * ref_gap)
+    got3 = ops.resize_aa(host.cuda(), (94, 308))                             # 4x down-scaling, both axes (9 taps each)
+    want3 = F.interpolate(host.cuda(), size=(94, 308), mode="bilinear", antialias=True, align_corners=False)
+    assert float((got3 - want3).abs().max()) <= 1e-4
+
+
 def test_host_streamed_frames_equal_device_frames():
     """pipe.run on pinned HOST frames (H2D streamed under the compute, raw 376x1241 size -> resize) must give
     bit-identical poses to the same frames already on the device."""

@@ -23,6 +23,8 @@
 
 #include <cuda_fp16.h>
 
+#include "tc_ptx.cuh"
+
 namespace atdn {
 namespace lks {
 
@@ -112,6 +114,8 @@ __device__ __forceinline__ void stage(const LevelLane& c, const float* coords, l
 template <bool OUT32>
 __global__ void __launch_bounds__(kWarps * 32, 4) corr_lookup_strip_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
+  pdl_launch_dependents();
+  pdl_wait();               // the coordinates come from the preceding kernel (ATDN_PDL: only the launch overlaps its tail)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wbase = smem + warp * kWarpBytes;
   const uint32_t win_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(wbase));

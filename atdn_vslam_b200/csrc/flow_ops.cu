@@ -6,6 +6,8 @@
 #include <cuda_fp16.h>
 
 #include "common.h"
+#include "tc_host.cuh"
+#include "tc_ptx.cuh"
 #include "corr_lookup_strip.cuh"
 
 namespace atdn {
@@ -252,6 +254,8 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict_
 // (14 channels + 2 zeros, 32 bytes per pixel); the 7 vertical taps stay implicit (7x1 convolution, pad 3).
 __global__ void __launch_bounds__(256) flow_pack_kernel(const float* __restrict__ flow, __half* __restrict__ x, int B, int H,
                                                         int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(B) * H * W * 2;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -476,6 +480,8 @@ static void launch_inorm_apply_fixed(const __half* x, long long pitch, const flo
 __global__ void __launch_bounds__(256) flow_head_gather_kernel(const float* __restrict__ d, long long pitch,
                                                                const float* __restrict__ bias, float* __restrict__ coords1,
                                                                float* __restrict__ flow, int B, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long npix = static_cast<long long>(B) * H * W;
   const long long pix = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (pix >= npix) return;
@@ -697,8 +703,8 @@ extern "C" int atdn_corr_lookup(const void* const lvl[4], const int32_t lvl_pitc
     }
     const long long per_cta = static_cast<long long>(lks::kWarps) * lks::kQueriesPerWarp;
     const unsigned ctas = static_cast<unsigned>((nq + per_cta - 1) / per_cta);
-    if (out32) lks::corr_lookup_strip_kernel<true><<<ctas, lks::kWarps * 32, lks::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
-    else lks::corr_lookup_strip_kernel<false><<<ctas, lks::kWarps * 32, lks::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+    if (out32) ATDN_CUDA(launch_pdl(lks::corr_lookup_strip_kernel<true>, dim3(ctas), dim3(lks::kWarps * 32), lks::kSmemBytes, static_cast<cudaStream_t>(stream), p));
+    else ATDN_CUDA(launch_pdl(lks::corr_lookup_strip_kernel<false>, dim3(ctas), dim3(lks::kWarps * 32), lks::kSmemBytes, static_cast<cudaStream_t>(stream), p));
   } else {
     LookupParams p;
     int h = h8;
@@ -758,8 +764,8 @@ extern "C" int atdn_flow_pack(const float* flow, void* x16, int32_t batch, int32
   if (int e = require_sm100()) return e;
   ATDN_REQUIRE(flow && x16 && aligned16(x16) && (reinterpret_cast<uintptr_t>(flow) & 7u) == 0, ATDN_ERR_ARG, "atdn_flow_pack: bad arguments");
   const long long total = static_cast<long long>(batch) * h8 * w8 * 2;
-  flow_pack_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(flow, static_cast<__half*>(x16), batch, h8, w8);
-  ATDN_CUDA(cudaGetLastError());
+  ATDN_CUDA(launch_pdl(flow_pack_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), flow, static_cast<__half*>(x16),
+                       batch, h8, w8));
   return 0;
 }
 
@@ -815,9 +821,8 @@ extern "C" int atdn_flow_head_gather(const float* d32, int64_t pitch, const floa
   ATDN_REQUIRE(d32 && bias && coords1 && flow, ATDN_ERR_ARG, "atdn_flow_head_gather: null argument");
   ATDN_REQUIRE(pitch >= 18 && pitch % 2 == 0 && (reinterpret_cast<uintptr_t>(d32) & 7u) == 0, ATDN_ERR_ALIGN, "atdn_flow_head_gather: d32 must be 8-byte aligned with an even pitch >= 18");
   const long long npix = static_cast<long long>(batch) * h8 * w8;
-  flow_head_gather_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d32, pitch, bias, coords1, flow, batch, h8, w8);
-  ATDN_CUDA(cudaGetLastError());
+  ATDN_CUDA(launch_pdl(flow_head_gather_kernel, dim3(static_cast<unsigned>((npix + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                       d32, static_cast<long long>(pitch), bias, coords1, flow, batch, h8, w8));
   return 0;
 }
 

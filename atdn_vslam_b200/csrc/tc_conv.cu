@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
   const int t_begin = static_cast<int>(static_cast<long long>(cid) * p.total_tiles / ncl);
   const int t_end = static_cast<int>(static_cast<long long>(cid + 1) * p.total_tiles / ncl);
 
+  pdl_launch_dependents();     // the next kernel may set itself up while this grid drains (no-op without ATDN_PDL)
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -135,6 +136,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
   const int chunks = p.chunks_a + p.chunks_a2;
   const bool stamp = p.stamps != nullptr && blockIdx.x == 0;
   if (stamp && threadIdx.x == 0) p.stamps[0] = clock64();
+
+  // Everything above, and the weight loads of warp 1 (constants), may overlap the tail of the preceding grid; the
+  // activations, the recurrent state and every store of this kernel must not.
+  if (warp != 1 && warp != 2) pdl_wait();
 
   if (warp == 0) {
     // ===== A producer (whole warp loops, one elected lane issues): one halo box per (tile, 64-channel chunk) =====
@@ -396,13 +401,15 @@ static int launch_conv(const ConvParams& p, int smem, cudaStream_t stream) {
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = env_switches().pdl ? 2 : 1;
   ATDN_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<MT, BN, EPI, PAIR>, p));
   return 0;
 }

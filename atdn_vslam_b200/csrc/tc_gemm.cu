@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
     bw0 = (blockIdx.y % p.corr_tiles_w) * 32;
   }
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();                  // operands, bitmaps and outputs are global memory: not before the preceding grid is complete
 
   const int chunks = p.chunks_a + p.chunks_a2;
 
@@ -339,6 +341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
     bw0 = (blockIdx.y % p.corr_tiles_w) * 32;
   }
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -365,6 +368,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads) tc_gemm2_k
   cluster_sync_all();          // the peer's barriers are initialised before any remote arrive / complete_tx
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();                  // operands, bitmaps and outputs are global memory: not before the preceding grid is complete
 
   const int chunks = p.chunks_a + p.chunks_a2;
 
@@ -572,8 +576,18 @@ static int launch(const TcParams& p, dim3 grid, cudaStream_t stream) {
     ATDN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured.done();
   }
-  tc_gemm_kernel<BN, STAGES, EPI><<<grid, kThreads, smem, stream>>>(p);
-  ATDN_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_switches().pdl ? 1 : 0;
+  ATDN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, STAGES, EPI>, p));
   return 0;
 }
 
@@ -585,8 +599,18 @@ static int launch2(const TcParams& p, dim3 grid, cudaStream_t stream) {
     ATDN_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured.done();
   }
-  tc_gemm2_kernel<BN, STAGES, EPI><<<grid, kThreads, smem, stream>>>(p);
-  ATDN_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_switches().pdl ? 1 : 0;
+  ATDN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm2_kernel<BN, STAGES, EPI>, p));   // (the cluster shape is the kernel's __cluster_dims__)
   return 0;
 }
 

@@ -1,5 +1,7 @@
 // Host-side helpers shared by the tensor-core translation units: TMA tensor-map construction.
 #pragma once
+#include <string.h>
+
 #include "common.h"
 
 namespace atdn {
@@ -54,6 +56,24 @@ inline int make_map_f16(CUtensorMap* m, const void* ptr, const int64_t dims[4], 
   return make_map(m, 2, CU_TENSOR_MAP_SWIZZLE_128B, ptr, dims, strides, box, estr, what);
 }
 
+
+// Launch with programmatic stream serialization when ATDN_PDL is on (tc_ptx.cuh: pdl_launch_dependents / pdl_wait); the
+// kernel must call pdl_wait() before its first global access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_switches().pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // CTA-pair / persistent conv kernel entry (tc_conv.cu); called by atdn_tc_gemm when desc->mt > 0
 int launch_conv_halo(const atdn_tc_desc* d, cudaStream_t stream);

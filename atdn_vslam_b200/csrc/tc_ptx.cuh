@@ -29,6 +29,14 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 
+// Programmatic dependent launch (launch attribute cudaLaunchAttributeProgrammaticStreamSerialization, ATDN_PDL): the next
+// kernel of the stream may become resident -- and run its prologue: barrier init, TMEM allocation, descriptor prefetch, loads
+// of constant operands -- while this grid drains, once every CTA of this grid has executed launch_dependents (or exited);
+// it must execute pdl_wait() before touching anything a preceding grid wrote or still reads.  Both are no-ops in a launch
+// without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------

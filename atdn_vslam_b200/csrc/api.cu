@@ -65,8 +65,7 @@ const EnvSwitches& env_switches() {
     v.no_out_tma = on("ATDN_NO_OUT_TMA");
     v.b_resident = on("ATDN_B_RESIDENT");
     v.corr_no_pair = on("ATDN_CORR_NO_PAIR");
-    const char* pdl = getenv("ATDN_PDL");
-    v.pdl = !(pdl && pdl[0] == '0');      // on by default
+    v.pdl = on("ATDN_PDL");               // opt-in: measured neutral to slightly negative on the batched step
     const char* dbg = getenv("ATDN_CORR_DBG");
     v.corr_dbg = dbg ? atoi(dbg) : 0;
     return v;

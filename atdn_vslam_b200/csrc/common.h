@@ -56,7 +56,7 @@ int num_sms();
 // environment switches (A/B experiments), read ONCE per process
 struct EnvSwitches {
   bool no_out_tma, b_resident, corr_no_pair;
-  bool pdl;       // ATDN_PDL=0 turns programmatic dependent launch of the per-iteration kernels off (tc_ptx.cuh)
+  bool pdl;       // ATDN_PDL=1: programmatic dependent launch of the flow-net kernels (tc_ptx.cuh); off by default
   int corr_dbg;
 };
 const EnvSwitches& env_switches();

@@ -211,6 +211,8 @@ __global__ void __launch_bounds__(kLkWarps * 32) corr_lookup_kernel(LookupParams
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ img, __half* __restrict__ x, int B, int H,
                                                         int W, int OH, int OW) {
+  pdl_launch_dependents();
+  pdl_wait();
   // grid = (ceil(OW*6/256), OH, B): no 64-bit divisions
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= static_cast<unsigned>(OW) * 6u) return;
@@ -285,6 +287,8 @@ __global__ void __launch_bounds__(256) flow_pack_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) inorm_partial_kernel(const __half* __restrict__ x, long long pitch, int HW,
                                                             int C, int parts, float* __restrict__ scratch) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[256 * 16];
   const int b = blockIdx.y, part = blockIdx.x;
   const int groups = C >> 3;
@@ -325,6 +329,8 @@ __global__ void __launch_bounds__(256) inorm_partial_kernel(const __half* __rest
 // one warp per (image, channel): lanes stride over the partial sums in a fixed order, fixed shuffle tree
 __global__ void __launch_bounds__(256) inorm_finalize_kernel(const float* __restrict__ scratch, int parts, int C, int HW,
                                                              int BC, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int wid = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (wid >= BC) return;
   const int b = wid / C, c = wid - b * C;
@@ -354,6 +360,8 @@ constexpr int kApplyU = 4;
 __global__ void __launch_bounds__(256) inorm_apply_kernel(const __half* __restrict__ x, long long pitch, const float* __restrict__ stats,
                                                           const __half* __restrict__ resid, long long rpitch, __half* __restrict__ y,
                                                           long long ypitch, int B, int HW, int C, int relu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const unsigned groups = static_cast<unsigned>(C) >> 3;
   const unsigned per_image = static_cast<unsigned>(HW) * groups;
   const unsigned base = blockIdx.x * (256u * kApplyU) + threadIdx.x;
@@ -418,6 +426,8 @@ __global__ void __launch_bounds__(C == 96 ? 192 : 256) inorm_apply_fixed_kernel(
                                                                               const __half* __restrict__ resid, long long rpitch,
                                                                               __half* __restrict__ y, long long ypitch, int HW,
                                                                               int relu) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int G = C / 8, T = (C == 96 ? 192 : 256), LANES = T / G, U = 8;
   const int g = threadIdx.x % G, pl = threadIdx.x / G, b = blockIdx.y;
   float mean[8], rstd[8];
@@ -469,7 +479,8 @@ template <int C>
 static void launch_inorm_apply_fixed(const __half* x, long long pitch, const float* stats, const __half* resid, long long rpitch,
                                      __half* y, long long ypitch, int batch, int hw, int relu, cudaStream_t s) {
   constexpr int T = (C == 96 ? 192 : 256), LANES = T / (C / 8), U = 8;
-  inorm_apply_fixed_kernel<C><<<dim3((hw + LANES * U - 1) / (LANES * U), batch), T, 0, s>>>(x, pitch, stats, resid, rpitch, y, ypitch, hw, relu);
+  (void)launch_pdl(inorm_apply_fixed_kernel<C>, dim3((hw + LANES * U - 1) / (LANES * U), batch), dim3(T), 0, s, x, pitch, stats, resid, rpitch, y, ypitch,
+                   hw, relu);     // (the caller checks cudaGetLastError)
 }
 
 // flow_head.conv2 as "1x1 conv + gather": the tensor-core kernel evaluates all nine taps on the UNSHIFTED pixel,
@@ -511,6 +522,8 @@ __global__ void __launch_bounds__(256) convex_upsample_kernel(const MaskT* __res
                                                               const float* __restrict__ flow,
                                                               float* __restrict__ up, float* __restrict__ lo, int B,
                                                               int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int j = threadIdx.x & 7, px = threadIdx.x >> 3;   // blockDim.x = 32
   const int i = threadIdx.y;                              // blockDim.y = 8
   const int x = blockIdx.x * 4 + px, y = blockIdx.y, b = blockIdx.z;
@@ -553,6 +566,8 @@ __global__ void __launch_bounds__(256) convex_upsample_kernel(const MaskT* __res
 
 __global__ void coords_init_kernel(float* __restrict__ coords1, float* __restrict__ flow,
                                    const float* __restrict__ init, int B, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long n = static_cast<long long>(B) * H * W;
   for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < n;
        pix += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -755,8 +770,8 @@ extern "C" int atdn_stem_pack(const float* image, void* x16, int32_t batch, int3
                ATDN_ERR_ARG, "atdn_stem_pack: bad arguments (even h, w >= 8; 8-byte aligned image, 16-byte aligned output)");
   const int oh = h / 2, ow = w / 2;
   ATDN_REQUIRE(oh <= 65535 && batch <= 65535, ATDN_ERR_UNSUP, "atdn_stem_pack: image too large");
-  stem_pack_kernel<<<dim3((ow * 6 + 255) / 256, oh, batch), 256, 0, static_cast<cudaStream_t>(stream)>>>(image, static_cast<__half*>(x16), batch, h, w, oh, ow);
-  ATDN_CUDA(cudaGetLastError());
+  ATDN_CUDA(launch_pdl(stem_pack_kernel, dim3((ow * 6 + 255) / 256, oh, batch), dim3(256), 0, static_cast<cudaStream_t>(stream), image,
+                       static_cast<__half*>(x16), batch, h, w, oh, ow));
   return 0;
 }
 
@@ -775,18 +790,16 @@ extern "C" int atdn_inorm_stats(const void* x16, int64_t pitch, int32_t batch, i
   ATDN_REQUIRE(x16 && scratch && stats && parts >= 1, ATDN_ERR_ARG, "atdn_inorm_stats: null argument");
   ATDN_REQUIRE(c % 8 == 0 && c >= 8 && c <= 256 && pitch % 8 == 0 && aligned16(x16), ATDN_ERR_ALIGN, "atdn_inorm_stats: C=%d pitch=%lld", c, (long long)pitch);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  inorm_partial_kernel<<<dim3(parts, batch), 256, 0, s>>>(static_cast<const __half*>(x16), pitch, hw, c, parts, scratch);
-  ATDN_CUDA(cudaGetLastError());
-  inorm_finalize_kernel<<<(batch * c + 7) / 8, 256, 0, s>>>(scratch, parts, c, hw, batch * c, stats);
-  ATDN_CUDA(cudaGetLastError());
+  ATDN_CUDA(launch_pdl(inorm_partial_kernel, dim3(parts, batch), dim3(256), 0, s, static_cast<const __half*>(x16), pitch, hw, c, parts, scratch));
+  ATDN_CUDA(launch_pdl(inorm_finalize_kernel, dim3((batch * c + 7) / 8), dim3(256), 0, s, scratch, parts, c, hw, batch * c, stats));
   return 0;
 }
 
 extern "C" int atdn_inorm_finalize(const float* scratch, int32_t parts, int32_t batch, int32_t c, int32_t hw, float* stats, void* stream) {
   if (int e = require_sm100()) return e;
   ATDN_REQUIRE(scratch && stats && parts >= 1 && batch >= 1 && c >= 1 && hw >= 1, ATDN_ERR_ARG, "atdn_inorm_finalize: bad arguments");
-  inorm_finalize_kernel<<<(batch * c + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(scratch, parts, c, hw, batch * c, stats);
-  ATDN_CUDA(cudaGetLastError());
+  ATDN_CUDA(launch_pdl(inorm_finalize_kernel, dim3((batch * c + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), scratch, parts, c, hw,
+                       batch * c, stats));
   return 0;
 }
 
@@ -832,9 +845,11 @@ extern "C" int atdn_convex_upsample(const void* mask, int32_t mask_is_half, int6
   ATDN_REQUIRE(mask && flow && flow_up && mask_pitch >= 576, ATDN_ERR_ARG, "atdn_convex_upsample: bad arguments");
   const dim3 grid((w8 + 3) / 4, h8, batch), block(32, 8);
   if (mask_is_half)
-    convex_upsample_kernel<__half><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(mask), mask_pitch, flow, flow_up, flow_lo, batch, h8, w8);
+    ATDN_CUDA(launch_pdl(convex_upsample_kernel<__half>, grid, block, 0, static_cast<cudaStream_t>(stream), static_cast<const __half*>(mask), mask_pitch, flow,
+                         flow_up, flow_lo, batch, h8, w8));
   else
-    convex_upsample_kernel<float><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(mask), mask_pitch, flow, flow_up, flow_lo, batch, h8, w8);
+    ATDN_CUDA(launch_pdl(convex_upsample_kernel<float>, grid, block, 0, static_cast<cudaStream_t>(stream), static_cast<const float*>(mask), mask_pitch, flow,
+                         flow_up, flow_lo, batch, h8, w8));
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -844,7 +859,7 @@ extern "C" int atdn_coords_init(float* coords1, float* flow, const float* flow_i
   if (int e = require_sm100()) return e;
   ATDN_REQUIRE(coords1 && flow, ATDN_ERR_ARG, "atdn_coords_init: null argument");
   const long long n = static_cast<long long>(batch) * h8 * w8;
-  coords_init_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(coords1, flow, flow_init, batch, h8, w8);
+  ATDN_CUDA(launch_pdl(coords_init_kernel, dim3(grid_for(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), coords1, flow, flow_init, batch, h8, w8));
   ATDN_CUDA(cudaGetLastError());
   return 0;
 }

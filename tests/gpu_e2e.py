@@ -122,6 +122,58 @@ def check_gma_full():
     return ok
 
 
+def check_gma_peaked_attention(temp=3.0, pairs=2):
+    """Trained GMA attention is peaked; the seeded weights give nearly flat rows, for which the mixed fp16 / e4m3 storage of the
+    probabilities keeps every block in e4m3.  Here q . k is scaled by ``temp`` (as in tools/fp8_attention_sensitivity.py), so that a
+    part of the blocks carries the mass and stays fp16, and the whole forward (iters=12) is held to the oracle in IEEE fp32 on
+    the same GPU -- with the same 1e-2 px bar on the mean end-point error -- next to the fp16-only storage (ATDN_P_MIXED=0)."""
+    import torch
+    from atdn_vslam_b200 import gma, synth
+    from oracle import gma_oracle
+    sd = dict(synth.gma_state_dict(module_prefix=True))
+    sd["module.att.to_qk.weight"] = sd["module.att.to_qk.weight"] * (temp ** 0.5)
+    frames = synth.frame_sequence(pairs + 1, 376, 1232, seed=synth.FRAME_SEED + 3).cuda()
+
+    class Args:
+        mixed_precision, num_heads, position_only, position_and_content = True, 1, False, False
+
+        def __contains__(self, k):
+            return hasattr(self, k)
+
+    ups, hot = {}, None
+    old = gma._P_MIXED
+    try:
+        for mixed in (True, False):
+            gma._P_MIXED = mixed
+            m = gma.RAFTGMA(Args())
+            m.load_state_dict(sd)
+            m = m.to("cuda").eval()
+            m.capture_forward = False
+            _, up = m.forward_frames(frames, iters=12, test_mode=True)
+            ups[mixed] = up.clone()
+            if mixed:
+                plan = next(iter(m._plans.values())) if hasattr(m, "_plans") else None
+                if plan is not None and getattr(plan, "mixed", False):
+                    hot = (float(plan.p_hot.float().mean()), float(plan.p_hot2.float().mean()))
+    finally:
+        gma._P_MIXED = old
+    osd = {k[7:]: v.cuda() for k, v in sd.items()}
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = torch.cat([gma_oracle.raftgma_forward(osd, frames[t:t + 1], frames[t + 1:t + 2], iters=12, aten_ops=True)[1].float() for t in range(pairs)])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    e_mixed = (ups[True] - ref).pow(2).sum(1).sqrt().flatten(1).mean(1)
+    e_fp16 = (ups[False] - ref).pow(2).sum(1).sqrt().flatten(1).mean(1)
+    delta = (ups[True] - ups[False]).pow(2).sum(1).sqrt().flatten(1).mean(1)
+    ok = float(e_mixed.max()) <= 1e-2 and float(e_fp16.max()) <= 1e-2
+    print(f"{'PASS' if ok else 'FAIL'} logit scale {temp}: flow_up mean EPE vs fp32 oracle  mixed {[f'{float(v):.3e}' for v in e_mixed]}  "
+          f"fp16 only {[f'{float(v):.3e}' for v in e_fp16]}  mixed vs fp16 {[f'{float(v):.3e}' for v in delta]}  "
+          f"hot sub-blocks / fp16 blocks {hot}", flush=True)
+    return ok
+
+
 def check_atdnvo():
     import numpy as np
     import torch

@@ -214,6 +214,11 @@ def test_sequence_pipeline_matches_per_pair_calls_and_keyframes():
     assert keys == o_keys and torch.equal(poses, o_poses)
 
 
+@pytest.mark.parametrize("temp", [3.0, 8.0])
+def test_flow_parity_with_peaked_attention(temp):
+    assert gpu_e2e.check_gma_peaked_attention(temp)
+
+
 @pytest.mark.parametrize("shape", [(376, 1241), (370, 1226), (375, 1242), (400, 1300), (188, 620), (376, 1232)])
 def test_resize_aa_matches_tf_resize(shape):
     """atdn_resize_aa (the caller-side resize of neural_slam.py:197-199) against torch's antialiased bilinear interpolate, the op

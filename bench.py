@@ -233,6 +233,44 @@ def localization_extras(dev, frame, pk, keyframes=8192, reps=10):
                        "found_planted_row": found == len(index) - 1}}
 
 
+def peaked_attention_extra(flow, dev, dev_frames, batch_pairs, pk, temps=(1.0, 3.0, 8.0), reps=3):
+    """The seeded weights give nearly flat attention rows, the regime in which the mixed fp16 / e4m3 storage keeps EVERY block
+    of the probabilities in e4m3 -- the best case for P.V.  Trained attention is peaked: here q . k is scaled by ``temp``
+    (tools/fp8_attention_sensitivity.py) on a copy of the flow net, the attention of one batch is rebuilt from real context
+    features and one to_v + P.V iteration is timed next to the share of blocks that stayed fp16."""
+    from atdn_vslam_b200 import gma
+    out = []
+    frames = dev_frames[: batch_pairs + 1]
+    for temp in temps:
+        m = type(flow)(flow.args)
+        sd = {k: v.clone() for k, v in flow.state_dict().items()}
+        key = next(k for k in sd if k.endswith("att.to_qk.weight"))
+        sd[key] = sd[key] * (temp ** 0.5)
+        m.load_state_dict(sd)
+        m = m.to(dev).eval()
+        m.capture_forward = False
+        m.forward_frames(frames, iters=1, test_mode=True)          # fills the plan: context features, attention, motion features
+        plan = m._plan(batch_pairs, frames.shape[-2], frames.shape[-1], dev)
+        wts = m._weights(dev)
+        m._aggregate(plan, wts)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            m._aggregate(plan, wts)
+        s1.record()
+        torch.cuda.synchronize()
+        ent = {"logit_scale": temp, "to_v_plus_pv_ms": round(s0.elapsed_time(s1) / reps, 4)}
+        if getattr(plan, "mixed", False):
+            ent["fp16_blocks"] = round(float(plan.p_hot2.float().mean()), 4)
+            ent["hot_sub_blocks"] = round(float(plan.p_hot.float().mean()), 4)
+        out.append(ent)
+        del m, plan, wts
+        torch.cuda.empty_cache()
+    return {"batch_pairs": batch_pairs, "regimes": out,
+            "note": "one to_v + P.V iteration per batch; logit_scale 1 = the benchmarked weights, 3 / 8 = peaked rows as in trained GMA"}
+
+
 def training_shape_extra(flow, vo, dev, reps=2):
     """BASELINE.json configs[2] (train_odometry.py:32-48): 24 sequences x 7 frames = 144 frame pairs at 376x1241 (resized to
     the SLAM size), flow for every pair, then ATDNVO on batch 24 x 6 steps (one stateful scan with a reset before it).
@@ -564,6 +602,10 @@ def run_ours(args):
                 line["training_shape_b24x6"] = training_shape_extra(flow, vo, dev)
             except Exception as exc:
                 line["training_shape_b24x6"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+            try:
+                line["attention_regimes"] = peaked_attention_extra(flow, dev, dev_frames, args.batch_pairs, pk)
+            except Exception as exc:
+                line["attention_regimes"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
             try:
                 line["torch_eager_b200"] = torch_eager_extra(dev, dev_frames)
             except Exception as exc:

@@ -476,11 +476,11 @@ __global__ void __launch_bounds__(C == 96 ? 192 : 256) inorm_apply_fixed_kernel(
 }
 
 template <int C>
-static void launch_inorm_apply_fixed(const __half* x, long long pitch, const float* stats, const __half* resid, long long rpitch,
+static cudaError_t launch_inorm_apply_fixed(const __half* x, long long pitch, const float* stats, const __half* resid, long long rpitch,
                                      __half* y, long long ypitch, int batch, int hw, int relu, cudaStream_t s) {
   constexpr int T = (C == 96 ? 192 : 256), LANES = T / (C / 8), U = 8;
-  (void)launch_pdl(inorm_apply_fixed_kernel<C>, dim3((hw + LANES * U - 1) / (LANES * U), batch), dim3(T), 0, s, x, pitch, stats, resid, rpitch, y, ypitch,
-                   hw, relu);     // (the caller checks cudaGetLastError)
+  return launch_pdl(inorm_apply_fixed_kernel<C>, dim3((hw + LANES * U - 1) / (LANES * U), batch), dim3(T), 0, s, x, pitch, stats, resid, rpitch, y, ypitch,
+                    hw, relu);
 }
 
 // flow_head.conv2 as "1x1 conv + gather": the tensor-core kernel evaluates all nine taps on the UNSHIFTED pixel,
@@ -814,10 +814,9 @@ extern "C" int atdn_inorm_apply(const void* x16, int64_t pitch, const float* sta
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const __half *xx = static_cast<const __half*>(x16), *rr = static_cast<const __half*>(resid16);
     __half* yy = static_cast<__half*>(y16);
-    if (c == 64) launch_inorm_apply_fixed<64>(xx, pitch, stats, rr, resid_pitch, yy, y_pitch, batch, hw, relu, st);
-    else if (c == 96) launch_inorm_apply_fixed<96>(xx, pitch, stats, rr, resid_pitch, yy, y_pitch, batch, hw, relu, st);
-    else launch_inorm_apply_fixed<128>(xx, pitch, stats, rr, resid_pitch, yy, y_pitch, batch, hw, relu, st);
-    ATDN_CUDA(cudaGetLastError());
+    if (c == 64) ATDN_CUDA(launch_inorm_apply_fixed<64>(xx, pitch, stats, rr, resid_pitch, yy, y_pitch, batch, hw, relu, st));
+    else if (c == 96) ATDN_CUDA(launch_inorm_apply_fixed<96>(xx, pitch, stats, rr, resid_pitch, yy, y_pitch, batch, hw, relu, st));
+    else ATDN_CUDA(launch_inorm_apply_fixed<128>(xx, pitch, stats, rr, resid_pitch, yy, y_pitch, batch, hw, relu, st));
     return 0;
   }
   const unsigned per_image = static_cast<unsigned>(hw) * static_cast<unsigned>(c / 8);

@@ -73,6 +73,10 @@ def _fold_bn(w, b, sd, name):
 # 47x154 x 24 pairs / encoder resolutions (profiles/r01b_halo_conv_timings.log)
 _HALO_CFG = {64: (4, 64, True), 96: (2, 96, True), 128: (2, 128, True), 192: (1, 192, True), 256: (1, 256, True),
              576: (1, 192, False)}
+for _item in filter(None, os.environ.get("ATDN_HALO_CFG", "").split(";")):      # A/B: "128:1,128,1;192:1,192,0" = cout:mt,bn,pair
+    _cout, _cfg = _item.split(":")
+    _mt, _bn, _pair = (int(v) for v in _cfg.split(","))
+    _HALO_CFG[int(_cout)] = (_mt, _bn, bool(_pair))
 
 
 FMAP_SCALE = 0.25      # plan.buffer("fmap*") holds fnet(x) * FMAP_SCALE (see _EncoderWeights.out)

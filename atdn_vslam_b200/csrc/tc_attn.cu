@@ -9,10 +9,13 @@
 // Recomputing S costs 2 x 13.9 GFLOP per pair (0.02 ms of tensor time) and removes 0.42 GB of HBM traffic per
 // pair; the only HBM traffic left is the P write (2 bytes per logit) that the P.V GEMM needs anyway.
 //
-// Warp roles (384 threads): warp 0 = TMA producer (Q once, K tiles through a ring), warp 1 = TMEM allocator +
-// MMA issuer, warps 4..11 = epilogue.  The 512 TMEM columns hold two 128 x 256 fp32 accumulators; epilogue group
-// g (warps 4+4g .. 7+4g, warp w reads TMEM lanes 32 (w & 3) ..) drains accumulator g, i.e. every second key
-// tile, while the MMA warp fills the other one.  Row maxima / sums of the two groups meet in shared memory.
+// Warp roles (576 threads): warp 0 = TMA producer (Q once, K tiles through a ring), warp 1 = TMEM allocator +
+// MMA issuer, warps 2..17 = epilogue.  The 512 TMEM columns hold two 128 x 256 fp32 accumulators; four epilogue
+// groups of four warps (warp w reads TMEM lanes 32 (w & 3) ..): groups 0 / 1 drain the two 128-column halves of
+// accumulator 0, groups 2 / 3 those of accumulator 1, i.e. every second key tile, while the MMA warp fills the
+// other one.  (Eight epilogue warps left the issue slots 57% used: the epilogue is a chain of TMEM load -> exp ->
+// pack -> staging store per chunk, and two warps per scheduler cannot hide it.)  Row maxima / sums of the four
+// groups meet in shared memory.
 //
 // MIXED storage (block_hot != NULL): P.V re-reads P twelve times per pair at the HBM roofline, so every 32-row x
 // 64-column sub-block whose rounding error cannot matter is stored as e4m3 (64-byte rows, half the bytes) and read back
@@ -30,13 +33,14 @@
 
 namespace atdn {
 
-constexpr int kAttnThreads = 384;
+constexpr int kAttnEpiWarps = 16;                  // 4 groups of 4 warps: (accumulator buffer 0 / 1) x (column half 0 / 1)
+constexpr int kAttnThreads = (2 + kAttnEpiWarps) * 32;   // warp 0 producer, warp 1 TMEM allocator + MMA issuer
 constexpr int kAttnBN = 256;                       // keys per tile
-constexpr int kAttnKStages = 4;                    // ring of 256 x 64 fp16 K chunks (32 KiB each)
+constexpr int kAttnKStages = 3;                    // ring of 256 x 64 fp16 K chunks (32 KiB each); 16 staging boxes take the rest
 constexpr int kAttnQBytes = 2 * 128 * 128;         // 2 chunks of 128 rows x 64 fp16
 constexpr int kAttnKStageBytes = kAttnBN * 128;
-constexpr int kAttnStoreBytes = 32 * 128;          // one 32-row x 64-column fp16 box per warp and buffer
-constexpr int kAttnSmem = kAttnQBytes + kAttnKStages * kAttnKStageBytes + 8 * 2 * kAttnStoreBytes + 1024;
+constexpr int kAttnStoreBytes = 32 * 128;          // one 32-row x 64-column fp16 box per epilogue warp
+constexpr int kAttnSmem = kAttnQBytes + kAttnKStages * kAttnKStageBytes + kAttnEpiWarps * kAttnStoreBytes + 1024;
 
 struct alignas(64) AttnParams {
   CUtensorMap tmQ, tmK, tmP, tmP8;
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, k_full[kAttnKStages], k_empty[kAttnKStages], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float xbuf[2][128];                   // row maxima, later row sums, of the two epilogue groups
+  __shared__ float xbuf[4][128];                   // row maxima, later row sums, of the four epilogue groups
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;
@@ -72,10 +76,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
   if (threadIdx.x == 0) {
     mbar_init(&q_full, 1);
     for (int s = 0; s < kAttnKStages; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     fence_barrier_init();
   }
-  if (warp == 2 && lane == 0) {
+  if (warp == 3 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmP);
@@ -138,50 +142,51 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
         if (++stage == kAttnKStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue =====
-    const int q = warp & 3, g = (warp - 4) >> 2;
+  } else {
+    // ===== epilogue: warp e = warp - 2 reads TMEM lanes 32 (warp & 3) .. (any four consecutive warps cover the 128 rows);
+    // group e >> 2 drains accumulator buffer g = group >> 1 (every second key tile) and, of its 256 columns, the half hc = group & 1
+    const int e = warp - 2;
+    const int q = warp & 3, g = e >> 3, hc = (e >> 2) & 1, grp = e >> 2;
     const int row_local = q * 32 + lane;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * kAttnBN);
-    const uint32_t st_u32 = smem_u32(smem_st + (warp - 4) * 2 * kAttnStoreBytes);
-    const uint8_t* st_ptr = smem_st + (warp - 4) * 2 * kAttnStoreBytes;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * kAttnBN + hc * (kAttnBN / 2));
+    const uint32_t st_u32 = smem_u32(smem_st + e * kAttnStoreBytes);
+    const uint8_t* st_ptr = smem_st + e * kAttnStoreBytes;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     float mx = -INFINITY, mxs = 0.0f, sum = 0.0f;
     float s1 = 0.0f, thr = 0.0f;                     // MIXED: pass-1 row sum (relative to mx), hot threshold on sum_block p^2
     uint32_t pf = 0;
     bool exchanged = false;
-    int nstore = 0;
 
     auto exchange = [&]() {
-      xbuf[g][row_local] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float m0v = xbuf[0][row_local], m1v = xbuf[1][row_local];
-      mx = fmaxf(m0v, m1v);
+      xbuf[grp][row_local] = mx;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      const float mv[4] = {xbuf[0][row_local], xbuf[1][row_local], xbuf[2][row_local], xbuf[3][row_local]};
+      mx = fmaxf(fmaxf(mv[0], mv[1]), fmaxf(mv[2], mv[3]));
       mxs = mx * p.scale_log2;
       if constexpr (MIXED) {   // second round through the same buffer: the pass-1 row sums, each relative to its group's maximum
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        xbuf[g][row_local] = s1;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        // a group that saw no tile holds (-inf, 0): ex2(-inf) = 0
-        const float srow = xbuf[0][row_local] * ex2_approx((m0v - mx) * p.scale_log2) +
-                           xbuf[1][row_local] * ex2_approx((m1v - mx) * p.scale_log2);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        xbuf[grp][row_local] = s1;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        float srow = 0.0f;     // a group that saw no column holds (-inf, 0): ex2(-inf) = 0
+#pragma unroll
+        for (int i = 0; i < 4; ++i) srow += xbuf[i][row_local] * ex2_approx((mv[i] - mx) * p.scale_log2);
         const float sfl = fmaxf(srow, 1.0f);          // the row maximum itself contributes 1: a floor under the sampled estimate
         thr = p.hot_thr * sfl * sfl;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // xbuf is reused for the row sums
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // xbuf is reused for the row sums
       exchanged = true;
     };
 
     for (int gi = g; gi < 2 * T; gi += 2) {
       const bool second = gi >= T;
       if (second && !exchanged) exchange();
-      const int col0 = (second ? gi - T : gi) * kAttnBN;
+      const int col0 = (second ? gi - T : gi) * kAttnBN + hc * (kAttnBN / 2);
       mbar_wait(&acc_full[g], pf);
       pf ^= 1u;
       tcgen05_fence_after();
       if (!second) {
 #pragma unroll 1
-        for (int c = 0; c < kAttnBN / 32; ++c) {
+        for (int c = 0; c < kAttnBN / 64; ++c) {
           const int cb = col0 + c * 32;
           if (cb >= p.n) break;
           uint32_t v[32];
@@ -226,11 +231,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
         }
       } else {
 #pragma unroll 1
-        for (int cg = 0; cg < kAttnBN / 64; ++cg) {
+        for (int cg = 0; cg < kAttnBN / 128; ++cg) {
           const int cb = col0 + cg * 64;
           if (cb >= p.n) break;
-          const int b = nstore & 1;
-          if (lane == 0) bulk_wait_read<1>();       // the store that last read this buffer has drained it
+          constexpr int b = 0;                      // one staging box per warp (16 warps x 4 KiB)
+          if (lane == 0) bulk_wait_read<0>();       // the previous store of this warp has drained the box
           __syncwarp();
           uint32_t v[64];
           tmem_ld_32x32(trow + cg * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -322,7 +327,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
             }
             bulk_commit();
           }
-          ++nstore;
         }
       }
       tcgen05_fence_before();
@@ -330,10 +334,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_probs_kernel(const __gri
       if (lane == 0) mbar_arrive(&acc_empty[g]);
     }
     if (!exchanged) exchange();
-    xbuf[g][row_local] = sum;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (g == 0 && m0 + row_local < p.n)
-      p.inv_sum[static_cast<long long>(batch) * p.n + m0 + row_local] = 1.0f / (xbuf[0][row_local] + xbuf[1][row_local]);
+    xbuf[grp][row_local] = sum;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (grp == 0 && m0 + row_local < p.n)
+      p.inv_sum[static_cast<long long>(batch) * p.n + m0 + row_local] =
+          1.0f / ((xbuf[0][row_local] + xbuf[1][row_local]) + (xbuf[2][row_local] + xbuf[3][row_local]));
     if (lane == 0) bulk_wait_read<0>();             // shared memory stays valid until the last store has read it
     __syncwarp();
   }
